@@ -1,0 +1,228 @@
+/*
+ * skagrid.h -- C ABI of libskagrid.so, the B200-native (sm_100a) AW-projection gridding hot path.
+ *
+ * This is the drop-in boundary for the Haskell reference sakehl/SKA-SDP-Accelerate-gridding: every
+ * entry point replaces one top-level of src/Gridding.hs / src/ImageDataset.hs that today builds an
+ * Accelerate AST and hands it to a backend `run` (src/Gridding.hs:28 `Runners`).  The calling
+ * convention mirrors the reference's own FFI idiom (src/Hdf5.hs:30-67 `foreign import ccall`,
+ * hdf5/hdf5.cc:59-186 `extern "C"`): flat functions, POD arguments only.
+ *
+ * Data conventions (src/Types.hs:7-28, src/Hdf5.hs:136,165-167, hdf5/hdf5.cc:14-17):
+ *   F            double
+ *   complex      interleaved (re, im) doubles; an array of n complex numbers is `double[2n]`
+ *   indices      int64_t (Haskell Int / Int64)
+ *   arrays       row-major, outermost dimension first, exactly the HDF5 / Accelerate order
+ *   uvw          structure of arrays: three `const double*` (what `toForeignPtrs` yields)
+ *   kernels      gcf  [qpx, qpx, gh, gw]  (Types.Kernel,   DIM4)   index (yf, xf, i->y, j->x)
+ *                wkern[nw, qpx, qpx, s, s] (Types.WKernels, DIM5)
+ *                akern[nant, s, s]         (Types.AKernels, DIM3)
+ *   grids        [height, width] complex, grid[y, x]; y from v, x from u (src/Gridding.hs:106-109)
+ *
+ * Ownership: the caller allocates every input and output; the library never frees or keeps caller
+ * memory after the call returns.  Device memory lives in the opaque context.
+ *
+ * Errors: every function returns 0 on success or a negative SKAGRID_E* code; the message is at
+ * skagrid_last_error(ctx).  No function aborts the process.  There is NO CPU fallback: without a
+ * CUDA device skagrid_create fails.
+ *
+ * Threading: one context per host thread; calls on a context are serialised by the caller.
+ * Haskell should bind with `foreign import ccall safe` (calls block for ms..s).
+ *
+ * Host-pointer functions ("skagrid_<name>") copy inputs H2D, compute, copy results D2H.
+ * Device-pointer functions ("skagrid_dev_<name>") work on device-resident buffers on a caller
+ * stream and never synchronise the host unless documented (used by bench.py, the multi-GPU host
+ * layer, and callers that keep kernels/grids resident across calls).
+ */
+#ifndef SKAGRID_H
+#define SKAGRID_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct skagrid_ctx skagrid_ctx;
+typedef struct skagrid_plan skagrid_plan;
+
+enum {
+    SKAGRID_OK = 0,
+    SKAGRID_EINVAL = -1,   /* bad argument */
+    SKAGRID_ECUDA = -2,    /* CUDA / cuFFT runtime error */
+    SKAGRID_ENOMEM = -3,   /* device or host allocation failed */
+    SKAGRID_ENODEV = -4,   /* no usable CUDA device */
+    SKAGRID_ERANGE = -5    /* an index (wbin, antenna, cell) is out of range */
+};
+
+/* flags for the binning functions */
+enum {
+    SKAGRID_FRAC_RAW = 0,       /* literal src/Gridding.hs:126-140 (frac may be -1 or qpx on ties) */
+    SKAGRID_FRAC_NORMALISE = 1  /* fold frac into [0,qpx) adjusting the cell (default of the gridders) */
+};
+
+/* ------------------------------------------------------------------ context */
+int skagrid_create(int device, skagrid_ctx **out);
+void skagrid_destroy(skagrid_ctx *ctx);
+const char *skagrid_last_error(const skagrid_ctx *ctx);
+const char *skagrid_version(void);
+/* CUDA-event milliseconds of the device work of the last host-pointer call on ctx. */
+double skagrid_last_device_ms(const skagrid_ctx *ctx);
+/* Number of kernels launched by this context since creation (bench.py "gpu_launches"). */
+int64_t skagrid_launch_count(const skagrid_ctx *ctx);
+/* Measures the FP64 FMA peak of the device with a register-resident DFMA loop (TFLOP/s). */
+int skagrid_measure_fp64_tflops(skagrid_ctx *ctx, double *tflops);
+
+/* ------------------------------------------------------------------ binning (bit-exact)
+ * frac_coord  src/Gridding.hs:126-140, frac_coords :142-151 (x,xf from u with width; y,yf from v with height) */
+int skagrid_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, int64_t count, const double *p,
+                       int64_t *fl, int64_t *frac, int flags);
+int skagrid_frac_coords(skagrid_ctx *ctx, int64_t height, int64_t width, int64_t qpx, int64_t count,
+                        const double *u, const double *v, int64_t *x, int64_t *xf, int64_t *y,
+                        int64_t *yf, int flags);
+/* findClosest src/Gridding.hs:895-907 (w above the last plane clamps to nw-1, Q4). */
+int skagrid_find_closest(skagrid_ctx *ctx, int64_t nw, const double *wbins, int64_t count,
+                         const double *w, int64_t *out);
+
+/* ------------------------------------------------------------------ pre-steps (in place)
+ * uvw_lambda src/ImageDataset.hs:181-187; mirror_uvw src/Gridding.hs:551-562; doweight :564-583 */
+int skagrid_uvw_lambda(skagrid_ctx *ctx, double freq, int64_t count, double *u, double *v, double *w);
+int skagrid_mirror_uvw(skagrid_ctx *ctx, int64_t count, double *u, double *v, double *w, double *vis);
+/* u,v in wavelengths (the function divides by lam itself, as the reference does). vis is divided
+ * by the number of visibilities sharing its cell.  Out-of-grid cells -> SKAGRID_ERANGE. */
+int skagrid_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *u,
+                     const double *v, double *vis);
+
+/* ------------------------------------------------------------------ gridding (grid += ...)
+ * grid          src/Gridding.hs:95-112   nearest cell
+ * convgrid      src/Gridding.hs:153-197  gcf[qpx,qpx,gh,gw]
+ * convgrid2     src/Gridding.hs:199-244  gcf[nw,qpx,qpx,gh,gw] + wbin per visibility
+ * convgrid_aw   src/Gridding.hs:246-317 (convgrid3) and :318-396 (convgrid4): same result
+ * u,v are "p" coordinates (uvw/lam, in (-.5,.5)).  `grid` is read, accumulated into and written back.
+ * Out-of-grid taps are dropped (fixoutofbounds, src/Gridding.hs:883-891). */
+int skagrid_grid(skagrid_ctx *ctx, int64_t height, int64_t width, double *grid, int64_t count,
+                 const double *u, const double *v, const double *vis);
+int skagrid_convgrid(skagrid_ctx *ctx, int64_t qpx, int64_t gh, int64_t gw, const double *gcf,
+                     int64_t height, int64_t width, double *grid, int64_t count, const double *u,
+                     const double *v, const double *vis);
+int skagrid_convgrid2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw,
+                      const double *gcf, int64_t height, int64_t width, double *grid, int64_t count,
+                      const double *u, const double *v, const int64_t *wbin, const double *vis);
+int skagrid_convgrid_aw(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t s, const double *wkerns,
+                        int64_t nant, const double *akerns, int64_t height, int64_t width,
+                        double *grid, int64_t count, const double *u, const double *v,
+                        const int64_t *wbin, const int64_t *a1, const int64_t *a2, const double *vis);
+
+/* ------------------------------------------------------------------ degridding (new; exact adjoints)
+ * vis_out[k] = sum_{i,j} conj(c_k[i,j]) * grid[y_k - gh/2 + i, x_k - gw/2 + j], c_k being the factor the
+ * matching gridder multiplies vis_k with (gcf slice, or conj(AW_k)).  Not in the reference. */
+int skagrid_convdegrid(skagrid_ctx *ctx, int64_t qpx, int64_t gh, int64_t gw, const double *gcf,
+                       int64_t height, int64_t width, const double *grid, int64_t count,
+                       const double *u, const double *v, double *vis_out);
+int skagrid_convdegrid2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw,
+                        const double *gcf, int64_t height, int64_t width, const double *grid,
+                        int64_t count, const double *u, const double *v, const int64_t *wbin,
+                        double *vis_out);
+int skagrid_convdegrid_aw(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t s, const double *wkerns,
+                          int64_t nant, const double *akerns, int64_t height, int64_t width,
+                          const double *grid, int64_t count, const double *u, const double *v,
+                          const int64_t *wbin, const int64_t *a1, const int64_t *a2, double *vis_out);
+
+/* ------------------------------------------------------------------ AW kernel formation
+ * convolve2d src/Gridding.hs:795-811 (direct evaluation of its FFT route, incl. the padder transpose);
+ * aw_kernel = aw_kernel_fn2 src/Gridding.hs:761-775 for `count` (wbin,yf,xf,a1,a2) tuples -> out[count,s,s]
+ * (NOT conjugated: conjugation happens in processOne2, src/Gridding.hs:391). */
+int skagrid_convolve2d(skagrid_ctx *ctx, int64_t n, const double *a1, const double *a2, double *out);
+int skagrid_aw_kernel(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t s, const double *wkerns,
+                      int64_t nant, const double *akerns, int64_t count, const int64_t *wbin,
+                      const int64_t *yf, const int64_t *xf, const int64_t *a1, const int64_t *a2,
+                      double *out);
+
+/* ------------------------------------------------------------------ grid -> image
+ * make_grid_hermitian src/Gridding.hs:585-605; ifft :828-829 (centred, 1/N^2); fft :821-826 (centred,
+ * zero-padded to the next power of two and cropped back, as the reference does). n x n complex. */
+int skagrid_make_grid_hermitian(skagrid_ctx *ctx, int64_t n, const double *grid, double *out);
+int skagrid_ifft(skagrid_ctx *ctx, int64_t n, const double *grid, double *out);
+int skagrid_fft(skagrid_ctx *ctx, int64_t n, const double *grid, double *out);
+/* Fused make_grid_hermitian -> ifft -> real -> maximum (src/ImageDataset.hs:74-77).
+ * image may be NULL when only the maximum is wanted. */
+int skagrid_grid_to_image(skagrid_ctx *ctx, int64_t n, const double *grid, double *image, double *max_out);
+
+/* ------------------------------------------------------------------ imaging drivers
+ * simple_imaging src/Gridding.hs:84-93; conv_imaging :115-124; aw_imaging :452-478 (aw_imagingOld
+ * :480-506 gives the same grid).  u,v,w in wavelengths; grid_out is n x n with n = round(theta*lam). */
+int skagrid_simple_imaging(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *u,
+                           const double *v, const double *w, const double *vis, double *grid_out);
+int skagrid_conv_imaging(skagrid_ctx *ctx, int64_t qpx, int64_t gh, int64_t gw, const double *gcf,
+                         double theta, int64_t lam, int64_t count, const double *u, const double *v,
+                         const double *w, const double *vis, double *grid_out);
+int skagrid_aw_imaging(skagrid_ctx *ctx, double theta, int64_t lam, int64_t nw, int64_t qpx, int64_t s,
+                       const double *wkerns, const double *wbins, int64_t nant, const double *akerns,
+                       int64_t count, const double *u, const double *v, const double *w,
+                       const int64_t *a1, const int64_t *a2, const double *vis, double *grid_out);
+/* ImageDataset.aw_gridding from the loaded arrays on (src/ImageDataset.hs:47-77): uvw in METRES,
+ * uvw_lambda(freq), doweight on the un-mirrored uvw, mirror_uvw, aw_imaging, make_grid_hermitian,
+ * real(ifft), maximum.  image (n x n doubles) and grid_out (n x n complex) may each be NULL. */
+int skagrid_aw_gridding(skagrid_ctx *ctx, double theta, int64_t lam, int64_t nw, int64_t qpx, int64_t s,
+                        const double *wkerns, const double *wbins, int64_t nant, const double *akerns,
+                        int64_t count, const double *u_m, const double *v_m, const double *w_m,
+                        const int64_t *a1, const int64_t *a2, double freq, const double *vis,
+                        double *image, double *max_out, double *grid_out);
+
+/* ------------------------------------------------------------------ w-kernel generation
+ * w_kernel src/Gridding.hs:610-728 for `nw` w values -> out[nw,qpx,qpx,npixkern,npixkern];
+ * conjugate != 0 applies the `map conjugate` of w_cache_imaging (src/Gridding.hs:441). */
+int skagrid_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *w, int64_t npixff,
+                      int64_t npixkern, int64_t qpx, int conjugate, double *out);
+
+/* ================================================================== device-resident API
+ * All pointers are DEVICE pointers on ctx's device; `stream` is a cudaStream_t passed as void*
+ * (NULL = the context's own stream).  Nothing here synchronises the host except where stated. */
+
+typedef struct skagrid_geom {
+    int64_t height, width;   /* full grid size (binning uses these) */
+    int64_t row0, row1;      /* rows [row0,row1) are owned: `grid` points at row0 and has row1-row0
+                                rows; taps outside are dropped (uv-tile-sharded mode). 0,height = all */
+    int64_t nw, qpx, gh, gw; /* kernel table shape [nw,qpx,qpx,gh,gw] (nw = 1 for convgrid) */
+} skagrid_geom;
+
+/* A plan holds `count` visibilities binned (bit-exact) and bucketed by (uv tile, 2x2 micro-tile).
+ * wbin may be NULL (all 0); vis may be NULL for a degrid-only plan.  slice_override != 0: the kernel slice of visibility k is k itself
+ * (per-visibility kernels, the AW path) instead of (wbin,yf,xf).  Synchronises `stream` once. */
+int skagrid_dev_plan_create(skagrid_ctx *ctx, const skagrid_geom *geom, int64_t count, const double *u,
+                            const double *v, const int64_t *wbin, const double *vis, int slice_override,
+                            void *stream, skagrid_plan **out);
+void skagrid_dev_plan_destroy(skagrid_ctx *ctx, skagrid_plan *plan);
+/* Re-bin and re-bucket a new batch of at most the plan's capacity into an existing plan (no
+ * allocation, no host synchronisation). */
+int skagrid_dev_plan_update(skagrid_ctx *ctx, skagrid_plan *plan, int64_t count, const double *u,
+                            const double *v, const int64_t *wbin, const double *vis, void *stream);
+/* Plan statistics: [0] visibilities kept, [1] dropped (no tap on the owned rows), [2] work items,
+ * [3] uv tiles, [4] non-empty tiles.  Synchronises `stream`. */
+int skagrid_dev_plan_stats(skagrid_ctx *ctx, skagrid_plan *plan, void *stream, int64_t stats[5]);
+
+/* grid[row0:row1, :] += sum over the plan's visibilities of vis_k * table[slice_k].
+ * variant: 0 = tiled shared-memory gridder (default), 1 = one-thread-per-tap global-atomic gridder
+ * (the literal `permute (+)`; baseline and cross-check). */
+int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, double *grid,
+                     int variant, void *stream);
+/* vis_out[k] = sum conj(table[slice_k][i,j]) * grid[...] for the plan's visibilities (others = 0). */
+int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, const double *grid,
+                       double *vis_out, void *stream);
+/* In-place grid -> image stage on an n x n device grid: hermitian + centred inverse FFT; writes
+ * real(image) into image (n*n doubles, may alias nothing) and the maximum into max_out (1 double). */
+int skagrid_dev_grid_to_image(skagrid_ctx *ctx, int64_t n, double *grid, double *image,
+                              double *max_out, void *stream);
+/* Synthetic SKA1-Low-shaped visibilities generated on the device: counter-based
+ * splitmix64(seed, index).  Fills u,v (p coordinates, v>=0 after mirroring), w-plane index, vis. */
+int skagrid_dev_synth_vis(skagrid_ctx *ctx, uint64_t seed, int64_t first, int64_t count, int64_t n,
+                          int64_t support, int64_t nw, int uniform, double *u, double *v,
+                          int64_t *wbin, double *vis, void *stream);
+
+/* w_kernel table built directly into device memory (w values on the host). */
+int skagrid_dev_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *w_host, int64_t npixff,
+                          int64_t npixkern, int64_t qpx, int conjugate, double *d_out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKAGRID_H */

@@ -1,0 +1,615 @@
+// api.cu -- the host-pointer C ABI (include/skagrid.h): what the reference's Haskell layer binds with
+// `foreign import ccall`.  Every function copies its inputs to the device, runs the sm_100a kernels and
+// copies the results back; there is no CPU implementation of any of them in this library.
+//
+// The table gridders / degridders stream the visibilities in chunks: the H2D copy of chunk c+1 runs on the
+// copy stream while chunk c is binned, bucketed and gridded on the compute stream (pinned caller buffers
+// make the copy truly asynchronous; pageable ones still work).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "common.cuh"
+
+static const i64 VIS_CHUNK = (i64)1 << 23;  // visibilities per pipelined chunk of the table gridders
+static const i64 AW_CHUNK = (i64)1 << 15;   // visibilities per chunk of the AW path (one S x S kernel each)
+
+struct Timer {
+    skagrid_ctx *ctx;
+    explicit Timer(skagrid_ctx *c) : ctx(c) { cudaEventRecord(ctx->ev0, ctx->stream); }
+    int finish() {
+        SK_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        SK_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0.f;
+        SK_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        ctx->last_ms = ms;
+        return SKAGRID_OK;
+    }
+};
+
+static int enter(skagrid_ctx *ctx) {
+    if (!ctx) return SKAGRID_EINVAL;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->err.clear();
+    return SKAGRID_OK;
+}
+
+// scratch + H2D on the compute stream
+static int up(skagrid_ctx *ctx, const char *name, const void *host, size_t bytes, void **dev) {
+    SK_TRY(sk_scratch(ctx, name, bytes ? bytes : 16, dev));
+    if (bytes) SK_CUDA(ctx, cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return SKAGRID_OK;
+}
+static int down(skagrid_ctx *ctx, void *host, const void *dev, size_t bytes) {
+    if (bytes) SK_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return SKAGRID_OK;
+}
+static int check_flags(skagrid_ctx *ctx, const char *what) {
+    uint32_t f = 0;
+    SK_TRY(sk_take_flags(ctx, ctx->stream, &f));
+    if (f & 1u) return sk_fail(ctx, SKAGRID_ERANGE, "%s: a w-plane, oversampling or antenna index is out of range", what);
+    if (f & 2u) return sk_fail(ctx, SKAGRID_ERANGE, "%s: a visibility falls outside the weight grid", what);
+    return SKAGRID_OK;
+}
+
+#define NEED(ctx, cond, what) \
+    do { if (!(cond)) return sk_fail((ctx), SKAGRID_EINVAL, "%s", (what)); } while (0)
+
+// ------------------------------------------------------------------------------------------ binning
+extern "C" int skagrid_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, int64_t count, const double *p, int64_t *fl, int64_t *frac,
+                                  int flags) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, n > 0 && qpx > 0 && count >= 0, "frac_coord: n, qpx must be positive");
+    if (count == 0) return SKAGRID_OK;
+    NEED(ctx, p && fl && frac, "frac_coord: NULL pointer");
+    Timer t(ctx);
+    void *dp, *dfl, *dfr;
+    SK_TRY(up(ctx, "fc_p", p, (size_t)count * 8, &dp));
+    SK_TRY(sk_scratch(ctx, "fc_fl", (size_t)count * 8, &dfl));
+    SK_TRY(sk_scratch(ctx, "fc_fr", (size_t)count * 8, &dfr));
+    SK_TRY(sk_frac_coord_dev(ctx, n, qpx, count, (double *)dp, (i64 *)dfl, (i64 *)dfr, flags & SKAGRID_FRAC_NORMALISE, ctx->stream));
+    SK_TRY(down(ctx, fl, dfl, (size_t)count * 8));
+    SK_TRY(down(ctx, frac, dfr, (size_t)count * 8));
+    return t.finish();
+}
+
+extern "C" int skagrid_frac_coords(skagrid_ctx *ctx, int64_t height, int64_t width, int64_t qpx, int64_t count, const double *u,
+                                   const double *v, int64_t *x, int64_t *xf, int64_t *y, int64_t *yf, int flags) {
+    // src/Gridding.hs:142-151: x,xf from u with WIDTH; y,yf from v with HEIGHT
+    SK_TRY(skagrid_frac_coord(ctx, width, qpx, count, u, x, xf, flags));
+    return skagrid_frac_coord(ctx, height, qpx, count, v, y, yf, flags);
+}
+
+extern "C" int skagrid_find_closest(skagrid_ctx *ctx, int64_t nw, const double *wbins, int64_t count, const double *w, int64_t *out) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, nw > 0 && count >= 0, "find_closest: empty wbins");
+    if (count == 0) return SKAGRID_OK;
+    NEED(ctx, wbins && w && out, "find_closest: NULL pointer");
+    Timer t(ctx);
+    void *dws, *dw, *dout;
+    SK_TRY(up(ctx, "fcl_ws", wbins, (size_t)nw * 8, &dws));
+    SK_TRY(up(ctx, "fcl_w", w, (size_t)count * 8, &dw));
+    SK_TRY(sk_scratch(ctx, "fcl_out", (size_t)count * 8, &dout));
+    SK_TRY(sk_find_closest_dev(ctx, nw, (double *)dws, count, (double *)dw, (i64 *)dout, ctx->stream));
+    SK_TRY(down(ctx, out, dout, (size_t)count * 8));
+    return t.finish();
+}
+
+// ------------------------------------------------------------------------------------------ pre-steps
+static int up_uvw(skagrid_ctx *ctx, i64 count, const double *u, const double *v, const double *w, double **du, double **dv, double **dw) {
+    SK_TRY(up(ctx, "pre_u", u, (size_t)count * 8, (void **)du));
+    SK_TRY(up(ctx, "pre_v", v, (size_t)count * 8, (void **)dv));
+    if (w) SK_TRY(up(ctx, "pre_w", w, (size_t)count * 8, (void **)dw));
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_uvw_lambda(skagrid_ctx *ctx, double freq, int64_t count, double *u, double *v, double *w) {
+    SK_TRY(enter(ctx));
+    if (count <= 0) return SKAGRID_OK;
+    NEED(ctx, u && v && w, "uvw_lambda: NULL pointer");
+    Timer t(ctx);
+    double *du, *dv, *dw;
+    SK_TRY(up_uvw(ctx, count, u, v, w, &du, &dv, &dw));
+    const double a = freq / 299792458.0;  // formed on the host in double, src/ImageDataset.hs:184
+    SK_TRY(sk_scale3_dev(ctx, count, du, dv, dw, a, 0, ctx->stream));
+    SK_TRY(down(ctx, u, du, (size_t)count * 8));
+    SK_TRY(down(ctx, v, dv, (size_t)count * 8));
+    SK_TRY(down(ctx, w, dw, (size_t)count * 8));
+    return t.finish();
+}
+
+extern "C" int skagrid_mirror_uvw(skagrid_ctx *ctx, int64_t count, double *u, double *v, double *w, double *vis) {
+    SK_TRY(enter(ctx));
+    if (count <= 0) return SKAGRID_OK;
+    NEED(ctx, u && v && w && vis, "mirror_uvw: NULL pointer");
+    Timer t(ctx);
+    double *du, *dv, *dw;
+    void *dvis;
+    SK_TRY(up_uvw(ctx, count, u, v, w, &du, &dv, &dw));
+    SK_TRY(up(ctx, "pre_vis", vis, (size_t)count * 16, &dvis));
+    SK_TRY(sk_mirror_dev(ctx, count, du, dv, dw, (double *)dvis, ctx->stream));
+    SK_TRY(down(ctx, u, du, (size_t)count * 8));
+    SK_TRY(down(ctx, v, dv, (size_t)count * 8));
+    SK_TRY(down(ctx, w, dw, (size_t)count * 8));
+    SK_TRY(down(ctx, vis, dvis, (size_t)count * 16));
+    return t.finish();
+}
+
+static i64 grid_side(double theta, i64 lam) { return (i64)llround(theta * (double)lam); }
+
+extern "C" int skagrid_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *u, const double *v, double *vis) {
+    SK_TRY(enter(ctx));
+    if (count <= 0) return SKAGRID_OK;
+    NEED(ctx, u && v && vis, "doweight: NULL pointer");
+    const i64 n = grid_side(theta, lam);
+    NEED(ctx, n > 0, "doweight: round(theta*lam) must be positive");
+    Timer t(ctx);
+    double *du, *dv, *dw = nullptr;
+    void *dvis;
+    SK_TRY(up_uvw(ctx, count, u, v, nullptr, &du, &dv, &dw));
+    SK_TRY(up(ctx, "pre_vis", vis, (size_t)count * 16, &dvis));
+    SK_TRY(sk_doweight_dev(ctx, n, (double)lam, count, du, dv, (double *)dvis, ctx->d_flags, ctx->stream));
+    SK_TRY(down(ctx, vis, dvis, (size_t)count * 16));
+    SK_TRY(t.finish());
+    return check_flags(ctx, "doweight");
+}
+
+// ------------------------------------------------------------------------------------------ table gridders
+// Device-side core: streams `count` host visibilities through a plan in double-buffered chunks.
+//   degrid == 0: d_grid[row0:row1] += sum vis_k * d_table[slice_k]      (vis is the input)
+//   degrid != 0: vis_out[k] = sum conj(d_table[slice_k]) * d_grid[...]  (vis_out is the output, host)
+static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double *d_table, double *d_grid, i64 count, const double *u,
+                        const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid) {
+    if (count <= 0) return SKAGRID_OK;
+    const i64 chunk = std::min<i64>(count, VIS_CHUNK);
+    skagrid_plan *plan = nullptr;
+    SK_TRY(sk_plan_alloc(ctx, geom, chunk, 0, &plan));
+    double *du[2], *dv[2], *dvis[2];
+    i64 *dwb[2] = {nullptr, nullptr};
+    int rc = SKAGRID_OK;
+    for (int b = 0; b < 2 && !rc; ++b) {
+        const char *nu = b ? "st_u1" : "st_u0", *nv = b ? "st_v1" : "st_v0", *nwb = b ? "st_w1" : "st_w0", *nvis = b ? "st_vis1" : "st_vis0";
+        rc = sk_scratch(ctx, nu, (size_t)chunk * 8, (void **)&du[b]);
+        if (!rc) rc = sk_scratch(ctx, nv, (size_t)chunk * 8, (void **)&dv[b]);
+        if (!rc && wbin) rc = sk_scratch(ctx, nwb, (size_t)chunk * 8, (void **)&dwb[b]);
+        if (!rc) rc = sk_scratch(ctx, nvis, (size_t)chunk * 16, (void **)&dvis[b]);
+    }
+    if (rc) { sk_plan_free(plan); return rc; }
+    cudaError_t e = cudaSuccess;
+    // the copy stream must not overwrite scratch that earlier work on the compute stream still uses
+    e = cudaEventRecord(ctx->ev_done[0], ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_done[1], ctx->stream);
+    i64 ci = 0;
+    for (i64 off = 0; off < count && e == cudaSuccess && !rc; off += chunk, ++ci) {
+        const int b = (int)(ci & 1);
+        const i64 n = std::min<i64>(chunk, count - off);
+        e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(du[b], u + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dv[b], v + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess && wbin) e = cudaMemcpyAsync(dwb[b], wbin + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess && !degrid) e = cudaMemcpyAsync(dvis[b], vis + 2 * off, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0);
+        if (e != cudaSuccess) break;
+        rc = sk_plan_fill(ctx, plan, n, du[b], dv[b], wbin ? dwb[b] : nullptr, degrid ? nullptr : dvis[b], ctx->stream);
+        if (!rc) {
+            if (degrid) {
+                rc = skagrid_dev_degrid(ctx, plan, d_table, d_grid, dvis[b], ctx->stream);
+                if (!rc) e = cudaMemcpyAsync(vis_out + 2 * off, dvis[b], (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+            } else {
+                rc = skagrid_dev_grid(ctx, plan, d_table, d_grid, 0, ctx->stream);
+            }
+        }
+        if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_done[b], ctx->stream);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    else cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->copy_stream);
+    sk_plan_free(plan);
+    if (rc) return rc;
+    if (e != cudaSuccess) return sk_fail(ctx, SKAGRID_ECUDA, "table gridder: %s", cudaGetErrorString(e));
+    return SKAGRID_OK;
+}
+
+static int check_table_args(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 gh, i64 gw, i64 height, i64 width, i64 count) {
+    NEED(ctx, nw > 0 && qpx > 0 && gh > 0 && gw > 0, "kernel table: non-positive dimension");
+    NEED(ctx, height > 0 && width > 0 && height <= 65536 && width <= 65536, "grid: size outside [1,65536]");
+    NEED(ctx, count >= 0, "negative visibility count");
+    return SKAGRID_OK;
+}
+
+static int table_host(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 gh, i64 gw, const double *gcf, i64 height, i64 width, double *grid, i64 count,
+                      const double *u, const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, const char *what) {
+    SK_TRY(enter(ctx));
+    SK_TRY(check_table_args(ctx, nw, qpx, gh, gw, height, width, count));
+    NEED(ctx, gcf && grid, "NULL kernel table or grid");
+    if (count > 0) NEED(ctx, u && v && (degrid ? vis_out != nullptr : vis != nullptr), "NULL visibility array");
+    Timer t(ctx);
+    void *dtab, *dgrid;
+    const size_t tab_bytes = (size_t)(nw * qpx * qpx * gh * gw) * 16, grid_bytes = (size_t)(height * width) * 16;
+    SK_TRY(up(ctx, "tab", gcf, tab_bytes, &dtab));
+    SK_TRY(up(ctx, "grid", grid, grid_bytes, &dgrid));
+    skagrid_geom geom = {height, width, 0, height, nw, qpx, gh, gw};
+    SK_TRY(stream_table(ctx, &geom, (double *)dtab, (double *)dgrid, count, u, v, wbin, vis, vis_out, degrid));
+    if (!degrid) SK_TRY(down(ctx, grid, dgrid, grid_bytes));
+    SK_TRY(t.finish());
+    return check_flags(ctx, what);
+}
+
+extern "C" int skagrid_convgrid(skagrid_ctx *ctx, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, int64_t height, int64_t width,
+                                double *grid, int64_t count, const double *u, const double *v, const double *vis) {
+    return table_host(ctx, 1, qpx, gh, gw, gcf, height, width, grid, count, u, v, nullptr, vis, nullptr, 0, "convgrid");
+}
+
+extern "C" int skagrid_convgrid2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, int64_t height,
+                                 int64_t width, double *grid, int64_t count, const double *u, const double *v, const int64_t *wbin,
+                                 const double *vis) {
+    if (ctx && count > 0 && !wbin) return sk_fail(ctx, SKAGRID_EINVAL, "convgrid2: wbin is NULL");
+    return table_host(ctx, nw, qpx, gh, gw, gcf, height, width, grid, count, u, v, wbin, vis, nullptr, 0, "convgrid2");
+}
+
+extern "C" int skagrid_convdegrid(skagrid_ctx *ctx, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, int64_t height, int64_t width,
+                                  const double *grid, int64_t count, const double *u, const double *v, double *vis_out) {
+    return table_host(ctx, 1, qpx, gh, gw, gcf, height, width, const_cast<double *>(grid), count, u, v, nullptr, nullptr, vis_out, 1, "convdegrid");
+}
+
+extern "C" int skagrid_convdegrid2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, int64_t height,
+                                   int64_t width, const double *grid, int64_t count, const double *u, const double *v, const int64_t *wbin,
+                                   double *vis_out) {
+    if (ctx && count > 0 && !wbin) return sk_fail(ctx, SKAGRID_EINVAL, "convdegrid2: wbin is NULL");
+    return table_host(ctx, nw, qpx, gh, gw, gcf, height, width, const_cast<double *>(grid), count, u, v, wbin, nullptr, vis_out, 1, "convdegrid2");
+}
+
+extern "C" int skagrid_grid(skagrid_ctx *ctx, int64_t height, int64_t width, double *grid, int64_t count, const double *u, const double *v,
+                            const double *vis) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, height > 0 && width > 0 && grid && count >= 0, "grid: bad size or NULL grid");
+    if (count == 0) return SKAGRID_OK;
+    NEED(ctx, u && v && vis, "grid: NULL visibility array");
+    Timer t(ctx);
+    double *du, *dv, *dw = nullptr;
+    void *dvis, *dgrid;
+    SK_TRY(up_uvw(ctx, count, u, v, nullptr, &du, &dv, &dw));
+    SK_TRY(up(ctx, "pre_vis", vis, (size_t)count * 16, &dvis));
+    SK_TRY(up(ctx, "grid", grid, (size_t)(height * width) * 16, &dgrid));
+    SK_TRY(sk_grid_simple_dev(ctx, height, width, (double *)dgrid, count, du, dv, (double *)dvis, ctx->stream));
+    SK_TRY(down(ctx, grid, dgrid, (size_t)(height * width) * 16));
+    return t.finish();
+}
+
+// ------------------------------------------------------------------------------------------ AW path
+// Device core of convgrid3/convgrid4 (src/Gridding.hs:246-396) and its adjoint.  All pointers are device
+// pointers; u,v are p coordinates.  Per chunk: bin -> per-visibility AW kernels (conjugated, :391) -> plan
+// with slice_k = k -> tiled gridder / degridder.
+static int aw_core_dev(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 s, const double *d_wk, i64 nant, const double *d_ak, i64 height, i64 width,
+                       double *d_grid, i64 count, const double *du, const double *dv, const i64 *dwb, const i64 *da1, const i64 *da2,
+                       double *dvis, int degrid) {
+    if (count <= 0) return SKAGRID_OK;
+    const i64 chunk = std::min<i64>(count, AW_CHUNK);
+    skagrid_geom geom = {height, width, 0, height, 1, qpx, s, s};  // slice_override: the table has one slice per visibility
+    skagrid_plan *plan = nullptr;
+    SK_TRY(sk_plan_alloc(ctx, &geom, chunk, 1, &plan));
+    void *dx, *dxf, *dy, *dyf, *dk;
+    int rc = sk_scratch(ctx, "aw_x", (size_t)chunk * 8, &dx);
+    if (!rc) rc = sk_scratch(ctx, "aw_xf", (size_t)chunk * 8, &dxf);
+    if (!rc) rc = sk_scratch(ctx, "aw_y", (size_t)chunk * 8, &dy);
+    if (!rc) rc = sk_scratch(ctx, "aw_yf", (size_t)chunk * 8, &dyf);
+    if (!rc) rc = sk_scratch(ctx, "aw_kern", (size_t)(chunk * s * s) * 16, &dk);
+    for (i64 off = 0; off < count && !rc; off += chunk) {
+        const i64 n = std::min<i64>(chunk, count - off);
+        rc = sk_frac_coord_dev(ctx, width, qpx, n, du + off, (i64 *)dx, (i64 *)dxf, 1, ctx->stream);
+        if (!rc) rc = sk_frac_coord_dev(ctx, height, qpx, n, dv + off, (i64 *)dy, (i64 *)dyf, 1, ctx->stream);
+        if (!rc) rc = sk_aw_kernels_dev(ctx, nw, qpx, s, d_wk, nant, d_ak, n, dwb + off, (i64 *)dyf, (i64 *)dxf, da1 + off, da2 + off,
+                                        (double *)dk, 1, ctx->d_flags, ctx->stream);
+        if (!rc) rc = sk_plan_fill(ctx, plan, n, du + off, dv + off, nullptr, degrid ? nullptr : dvis + 2 * off, ctx->stream);
+        if (!rc) {
+            if (degrid) rc = skagrid_dev_degrid(ctx, plan, (double *)dk, d_grid, dvis + 2 * off, ctx->stream);
+            else rc = skagrid_dev_grid(ctx, plan, (double *)dk, d_grid, 0, ctx->stream);
+        }
+    }
+    cudaStreamSynchronize(ctx->stream);
+    sk_plan_free(plan);
+    return rc;
+}
+
+static int aw_host(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 s, const double *wkerns, i64 nant, const double *akerns, i64 height, i64 width,
+                   double *grid, i64 count, const double *u, const double *v, const int64_t *wbin, const int64_t *a1, const int64_t *a2,
+                   const double *vis, double *vis_out, int degrid, const char *what) {
+    SK_TRY(enter(ctx));
+    SK_TRY(check_table_args(ctx, nw, qpx, s, s, height, width, count));
+    NEED(ctx, nant > 0 && wkerns && akerns && grid, "NULL kernels / grid or nant <= 0");
+    NEED(ctx, s <= 63, "AW path: support above 63 is not supported");
+    if (count > 0) NEED(ctx, u && v && wbin && a1 && a2 && (degrid ? vis_out != nullptr : vis != nullptr), "NULL visibility array");
+    Timer t(ctx);
+    void *dwk, *dak, *dgrid, *du, *dv, *dwb, *da1, *da2, *dvis;
+    SK_TRY(up(ctx, "aw_wk", wkerns, (size_t)(nw * qpx * qpx * s * s) * 16, &dwk));
+    SK_TRY(up(ctx, "aw_ak", akerns, (size_t)(nant * s * s) * 16, &dak));
+    SK_TRY(up(ctx, "grid", grid, (size_t)(height * width) * 16, &dgrid));
+    SK_TRY(up(ctx, "pre_u", u, (size_t)count * 8, &du));
+    SK_TRY(up(ctx, "pre_v", v, (size_t)count * 8, &dv));
+    SK_TRY(up(ctx, "aw_wb", wbin, (size_t)count * 8, &dwb));
+    SK_TRY(up(ctx, "aw_a1", a1, (size_t)count * 8, &da1));
+    SK_TRY(up(ctx, "aw_a2", a2, (size_t)count * 8, &da2));
+    if (degrid) SK_TRY(sk_scratch(ctx, "pre_vis", (size_t)std::max<i64>(count, 1) * 16, &dvis));
+    else SK_TRY(up(ctx, "pre_vis", vis, (size_t)count * 16, &dvis));
+    SK_TRY(aw_core_dev(ctx, nw, qpx, s, (double *)dwk, nant, (double *)dak, height, width, (double *)dgrid, count, (double *)du, (double *)dv,
+                       (i64 *)dwb, (i64 *)da1, (i64 *)da2, (double *)dvis, degrid));
+    if (degrid) SK_TRY(down(ctx, vis_out, dvis, (size_t)count * 16));
+    else SK_TRY(down(ctx, grid, dgrid, (size_t)(height * width) * 16));
+    SK_TRY(t.finish());
+    return check_flags(ctx, what);
+}
+
+extern "C" int skagrid_convgrid_aw(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t s, const double *wkerns, int64_t nant,
+                                   const double *akerns, int64_t height, int64_t width, double *grid, int64_t count, const double *u,
+                                   const double *v, const int64_t *wbin, const int64_t *a1, const int64_t *a2, const double *vis) {
+    return aw_host(ctx, nw, qpx, s, wkerns, nant, akerns, height, width, grid, count, u, v, wbin, a1, a2, vis, nullptr, 0, "convgrid_aw");
+}
+
+extern "C" int skagrid_convdegrid_aw(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t s, const double *wkerns, int64_t nant,
+                                     const double *akerns, int64_t height, int64_t width, const double *grid, int64_t count,
+                                     const double *u, const double *v, const int64_t *wbin, const int64_t *a1, const int64_t *a2,
+                                     double *vis_out) {
+    return aw_host(ctx, nw, qpx, s, wkerns, nant, akerns, height, width, const_cast<double *>(grid), count, u, v, wbin, a1, a2, nullptr,
+                   vis_out, 1, "convdegrid_aw");
+}
+
+extern "C" int skagrid_convolve2d(skagrid_ctx *ctx, int64_t n, const double *a1, const double *a2, double *out) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, n > 0 && n <= 64 && a1 && a2 && out, "convolve2d: size outside [1,64] or NULL pointer");
+    Timer t(ctx);
+    void *d1, *d2, *dout;
+    SK_TRY(up(ctx, "cv_a", a1, (size_t)(n * n) * 16, &d1));
+    SK_TRY(up(ctx, "cv_b", a2, (size_t)(n * n) * 16, &d2));
+    SK_TRY(sk_scratch(ctx, "cv_out", (size_t)(n * n) * 16, &dout));
+    SK_TRY(sk_convolve2d_dev(ctx, n, 1, (double *)d1, nullptr, (double *)d2, nullptr, (double *)dout, 0, ctx->stream));
+    SK_TRY(down(ctx, out, dout, (size_t)(n * n) * 16));
+    return t.finish();
+}
+
+extern "C" int skagrid_aw_kernel(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t s, const double *wkerns, int64_t nant,
+                                 const double *akerns, int64_t count, const int64_t *wbin, const int64_t *yf, const int64_t *xf,
+                                 const int64_t *a1, const int64_t *a2, double *out) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, nw > 0 && qpx > 0 && s > 0 && s <= 64 && nant > 0 && count >= 0, "aw_kernel: bad dimension");
+    if (count == 0) return SKAGRID_OK;
+    NEED(ctx, wkerns && akerns && wbin && yf && xf && a1 && a2 && out, "aw_kernel: NULL pointer");
+    Timer t(ctx);
+    void *dwk, *dak, *dwb, *dyf, *dxf, *da1, *da2, *dout;
+    SK_TRY(up(ctx, "aw_wk", wkerns, (size_t)(nw * qpx * qpx * s * s) * 16, &dwk));
+    SK_TRY(up(ctx, "aw_ak", akerns, (size_t)(nant * s * s) * 16, &dak));
+    SK_TRY(up(ctx, "aw_wb", wbin, (size_t)count * 8, &dwb));
+    SK_TRY(up(ctx, "aw_yf", yf, (size_t)count * 8, &dyf));
+    SK_TRY(up(ctx, "aw_xf", xf, (size_t)count * 8, &dxf));
+    SK_TRY(up(ctx, "aw_a1", a1, (size_t)count * 8, &da1));
+    SK_TRY(up(ctx, "aw_a2", a2, (size_t)count * 8, &da2));
+    SK_TRY(sk_scratch(ctx, "aw_kern", (size_t)(count * s * s) * 16, &dout));
+    SK_TRY(sk_aw_kernels_dev(ctx, nw, qpx, s, (double *)dwk, nant, (double *)dak, count, (i64 *)dwb, (i64 *)dyf, (i64 *)dxf, (i64 *)da1,
+                             (i64 *)da2, (double *)dout, 0, ctx->d_flags, ctx->stream));
+    SK_TRY(down(ctx, out, dout, (size_t)(count * s * s) * 16));
+    SK_TRY(t.finish());
+    return check_flags(ctx, "aw_kernel");
+}
+
+// ------------------------------------------------------------------------------------------ grid -> image
+extern "C" int skagrid_make_grid_hermitian(skagrid_ctx *ctx, int64_t n, const double *grid, double *out) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, n > 0 && grid && out, "make_grid_hermitian: bad size or NULL pointer");
+    Timer t(ctx);
+    void *dg;
+    SK_TRY(up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg));
+    SK_TRY(sk_hermitian_dev(ctx, n, (double *)dg, (double *)dg, ctx->stream));
+    SK_TRY(down(ctx, out, dg, (size_t)(n * n) * 16));
+    return t.finish();
+}
+
+extern "C" int skagrid_ifft(skagrid_ctx *ctx, int64_t n, const double *grid, double *out) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, n > 0 && grid && out, "ifft: bad size or NULL pointer");
+    Timer t(ctx);
+    void *dg;
+    SK_TRY(up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg));
+    SK_TRY(sk_fft2c_dev(ctx, n, (double *)dg, (double *)dg, 1, ctx->stream));
+    SK_TRY(down(ctx, out, dg, (size_t)(n * n) * 16));
+    return t.finish();
+}
+
+extern "C" int skagrid_fft(skagrid_ctx *ctx, int64_t n, const double *grid, double *out) {
+    // src/Gridding.hs:821-826: pad to the next power of two (transposing padder), centred forward FFT, crop
+    SK_TRY(enter(ctx));
+    NEED(ctx, n > 0 && grid && out, "fft: bad size or NULL pointer");
+    Timer t(ctx);
+    i64 big = 1;
+    while (big < n) big <<= 1;
+    void *dg;
+    SK_TRY(up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg));
+    if (big == n) {
+        SK_TRY(sk_fft2c_dev(ctx, n, (double *)dg, (double *)dg, 0, ctx->stream));
+        SK_TRY(down(ctx, out, dg, (size_t)(n * n) * 16));
+    } else {
+        void *db;
+        SK_TRY(sk_scratch(ctx, "fft_big", (size_t)(big * big) * 16, &db));
+        SK_TRY(sk_pad_crop_dev(ctx, n, (double *)dg, big, (double *)db, ctx->stream));
+        SK_TRY(sk_fft2c_dev(ctx, big, (double *)db, (double *)db, 0, ctx->stream));
+        SK_TRY(sk_pad_crop_dev(ctx, big, (double *)db, n, (double *)dg, ctx->stream));
+        SK_TRY(down(ctx, out, dg, (size_t)(n * n) * 16));
+    }
+    return t.finish();
+}
+
+extern "C" int skagrid_grid_to_image(skagrid_ctx *ctx, int64_t n, const double *grid, double *image, double *max_out) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, n > 0 && grid, "grid_to_image: bad size or NULL grid");
+    Timer t(ctx);
+    void *dg, *dimg = nullptr, *dmax;
+    SK_TRY(up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg));
+    if (image) SK_TRY(sk_scratch(ctx, "image", (size_t)(n * n) * 8, &dimg));
+    SK_TRY(sk_scratch(ctx, "image_max", 16, &dmax));
+    SK_TRY(sk_grid_to_image_dev(ctx, n, (double *)dg, (double *)dimg, (double *)dmax, ctx->stream));
+    if (image) SK_TRY(down(ctx, image, dimg, (size_t)(n * n) * 8));
+    if (max_out) SK_TRY(down(ctx, max_out, dmax, 8));
+    return t.finish();
+}
+
+extern "C" int skagrid_dev_grid_to_image(skagrid_ctx *ctx, int64_t n, double *grid, double *image, double *max_out, void *stream) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, n > 0 && grid, "dev_grid_to_image: bad size or NULL grid");
+    return sk_grid_to_image_dev(ctx, n, grid, image, max_out, sk_stream(ctx, stream));
+}
+
+// ------------------------------------------------------------------------------------------ imaging drivers
+extern "C" int skagrid_simple_imaging(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *u, const double *v,
+                                      const double *w, const double *vis, double *grid_out) {
+    SK_TRY(enter(ctx));
+    const i64 n = grid_side(theta, lam);
+    NEED(ctx, n > 0 && grid_out && count >= 0, "simple_imaging: bad size or NULL grid");
+    (void)w;
+    Timer t(ctx);
+    void *dgrid;
+    SK_TRY(sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid));
+    SK_CUDA(ctx, cudaMemsetAsync(dgrid, 0, (size_t)(n * n) * 16, ctx->stream));
+    if (count > 0) {
+        NEED(ctx, u && v && vis, "simple_imaging: NULL visibility array");
+        double *du, *dv, *dw = nullptr;
+        void *dvis;
+        SK_TRY(up_uvw(ctx, count, u, v, nullptr, &du, &dv, &dw));
+        SK_TRY(up(ctx, "pre_vis", vis, (size_t)count * 16, &dvis));
+        void *dscr;  // div3 divides all three coordinates; w is not used by `grid`
+        SK_TRY(sk_scratch(ctx, "pre_w", (size_t)count * 8, &dscr));
+        SK_CUDA(ctx, cudaMemsetAsync(dscr, 0, (size_t)count * 8, ctx->stream));
+        SK_TRY(sk_scale3_dev(ctx, count, du, dv, (double *)dscr, (double)lam, 1, ctx->stream));
+        SK_TRY(sk_grid_simple_dev(ctx, n, n, (double *)dgrid, count, du, dv, (double *)dvis, ctx->stream));
+    }
+    SK_TRY(down(ctx, grid_out, dgrid, (size_t)(n * n) * 16));
+    return t.finish();
+}
+
+extern "C" int skagrid_conv_imaging(skagrid_ctx *ctx, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, double theta, int64_t lam,
+                                    int64_t count, const double *u, const double *v, const double *w, const double *vis, double *grid_out) {
+    SK_TRY(enter(ctx));
+    const i64 n = grid_side(theta, lam);
+    SK_TRY(check_table_args(ctx, 1, qpx, gh, gw, n, n, count));
+    NEED(ctx, gcf && grid_out, "conv_imaging: NULL kernel or grid");
+    (void)w;
+    Timer t(ctx);
+    void *dgrid, *dtab;
+    SK_TRY(up(ctx, "tab", gcf, (size_t)(qpx * qpx * gh * gw) * 16, &dtab));
+    SK_TRY(sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid));
+    SK_CUDA(ctx, cudaMemsetAsync(dgrid, 0, (size_t)(n * n) * 16, ctx->stream));
+    if (count > 0) {
+        NEED(ctx, u && v && vis, "conv_imaging: NULL visibility array");
+        double *du, *dv, *dw = nullptr;
+        void *dvis;
+        SK_TRY(up_uvw(ctx, count, u, v, nullptr, &du, &dv, &dw));
+        SK_TRY(up(ctx, "pre_vis", vis, (size_t)count * 16, &dvis));
+        void *dscr;
+        SK_TRY(sk_scratch(ctx, "pre_w", (size_t)count * 8, &dscr));
+        SK_CUDA(ctx, cudaMemsetAsync(dscr, 0, (size_t)count * 8, ctx->stream));
+        SK_TRY(sk_scale3_dev(ctx, count, du, dv, (double *)dscr, (double)lam, 1, ctx->stream));
+        skagrid_geom geom = {n, n, 0, n, 1, qpx, gh, gw};
+        skagrid_plan *plan = nullptr;
+        SK_TRY(sk_plan_alloc(ctx, &geom, count, 0, &plan));
+        int rc = sk_plan_fill(ctx, plan, count, du, dv, nullptr, (double *)dvis, ctx->stream);
+        if (!rc) rc = skagrid_dev_grid(ctx, plan, (double *)dtab, (double *)dgrid, 0, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        sk_plan_free(plan);
+        SK_TRY(rc);
+    }
+    SK_TRY(down(ctx, grid_out, dgrid, (size_t)(n * n) * 16));
+    return t.finish();
+}
+
+// aw_imaging on device-resident inputs: p = uvw/lam (in place), wbin = findClosest wbins w (w in wavelengths,
+// NOT divided: src/Gridding.hs:473 uses the original w), convgrid4.  d_grid must be zeroed by the caller.
+static int aw_imaging_dev(skagrid_ctx *ctx, i64 n, i64 lam, i64 nw, i64 qpx, i64 s, const double *d_wk, const double *d_wbins, i64 nant,
+                          const double *d_ak, i64 count, double *du, double *dv, double *dw, const i64 *da1, const i64 *da2, double *dvis,
+                          double *d_grid) {
+    if (count <= 0) return SKAGRID_OK;
+    void *dwb;
+    SK_TRY(sk_scratch(ctx, "aw_wb", (size_t)count * 8, &dwb));
+    SK_TRY(sk_find_closest_dev(ctx, nw, d_wbins, count, dw, (i64 *)dwb, ctx->stream));
+    SK_TRY(sk_scale3_dev(ctx, count, du, dv, dw, (double)lam, 1, ctx->stream));
+    return aw_core_dev(ctx, nw, qpx, s, d_wk, nant, d_ak, n, n, d_grid, count, du, dv, (i64 *)dwb, da1, da2, dvis, 0);
+}
+
+extern "C" int skagrid_aw_imaging(skagrid_ctx *ctx, double theta, int64_t lam, int64_t nw, int64_t qpx, int64_t s, const double *wkerns,
+                                  const double *wbins, int64_t nant, const double *akerns, int64_t count, const double *u, const double *v,
+                                  const double *w, const int64_t *a1, const int64_t *a2, const double *vis, double *grid_out) {
+    return skagrid_aw_gridding(ctx, theta, lam, nw, qpx, s, wkerns, wbins, nant, akerns, count, u, v, w, a1, a2, -1.0, vis, nullptr, nullptr,
+                               grid_out);
+}
+
+// freq < 0 selects plain aw_imaging (no uvw_lambda / doweight / mirror / image stage).
+extern "C" int skagrid_aw_gridding(skagrid_ctx *ctx, double theta, int64_t lam, int64_t nw, int64_t qpx, int64_t s, const double *wkerns,
+                                   const double *wbins, int64_t nant, const double *akerns, int64_t count, const double *u_m,
+                                   const double *v_m, const double *w_m, const int64_t *a1, const int64_t *a2, double freq,
+                                   const double *vis, double *image, double *max_out, double *grid_out) {
+    SK_TRY(enter(ctx));
+    const i64 n = grid_side(theta, lam);
+    SK_TRY(check_table_args(ctx, nw, qpx, s, s, n, n, count));
+    NEED(ctx, nant > 0 && wkerns && wbins && akerns, "aw_gridding: NULL kernels or nant <= 0");
+    NEED(ctx, s <= 63, "AW path: support above 63 is not supported");
+    if (count > 0) NEED(ctx, u_m && v_m && w_m && a1 && a2 && vis, "aw_gridding: NULL visibility array");
+    const bool full = freq >= 0.0;
+    Timer t(ctx);
+    void *dwk, *dak, *dwbins, *dgrid, *du, *dv, *dw, *da1, *da2, *dvis;
+    SK_TRY(up(ctx, "aw_wk", wkerns, (size_t)(nw * qpx * qpx * s * s) * 16, &dwk));
+    SK_TRY(up(ctx, "aw_ak", akerns, (size_t)(nant * s * s) * 16, &dak));
+    SK_TRY(up(ctx, "aw_wbins", wbins, (size_t)nw * 8, &dwbins));
+    SK_TRY(sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid));
+    SK_CUDA(ctx, cudaMemsetAsync(dgrid, 0, (size_t)(n * n) * 16, ctx->stream));
+    SK_TRY(up(ctx, "pre_u", u_m, (size_t)count * 8, &du));
+    SK_TRY(up(ctx, "pre_v", v_m, (size_t)count * 8, &dv));
+    SK_TRY(up(ctx, "pre_w", w_m, (size_t)count * 8, &dw));
+    SK_TRY(up(ctx, "aw_a1", a1, (size_t)count * 8, &da1));
+    SK_TRY(up(ctx, "aw_a2", a2, (size_t)count * 8, &da2));
+    SK_TRY(up(ctx, "pre_vis", vis, (size_t)count * 16, &dvis));
+    if (full && count > 0) {
+        // src/ImageDataset.hs:55-60,72: uvw_lambda; wt = doweight(ones) on the UN-mirrored uvw; mirror; vis*wt
+        SK_TRY(sk_scale3_dev(ctx, count, (double *)du, (double *)dv, (double *)dw, freq / 299792458.0, 0, ctx->stream));
+        void *dwt;
+        SK_TRY(sk_scratch(ctx, "aw_wt", (size_t)count * 16, &dwt));
+        std::vector<double> ones((size_t)count * 2);
+        for (i64 k = 0; k < count; ++k) { ones[2 * k] = 1.0; ones[2 * k + 1] = 0.0; }
+        SK_CUDA(ctx, cudaMemcpyAsync(dwt, ones.data(), (size_t)count * 16, cudaMemcpyHostToDevice, ctx->stream));
+        SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `ones` is pageable and about to go out of scope
+        SK_TRY(sk_doweight_dev(ctx, n, (double)lam, count, (double *)du, (double *)dv, (double *)dwt, ctx->d_flags + 0, ctx->stream));
+        SK_TRY(sk_mirror_dev(ctx, count, (double *)du, (double *)dv, (double *)dw, (double *)dvis, ctx->stream));
+        SK_TRY(sk_cmul_dev(ctx, count, (double *)dvis, (double *)dwt, ctx->stream));
+    }
+    SK_TRY(aw_imaging_dev(ctx, n, lam, nw, qpx, s, (double *)dwk, (double *)dwbins, nant, (double *)dak, count, (double *)du, (double *)dv,
+                          (double *)dw, (i64 *)da1, (i64 *)da2, (double *)dvis, (double *)dgrid));
+    if (grid_out) SK_TRY(down(ctx, grid_out, dgrid, (size_t)(n * n) * 16));
+    if (full && (image || max_out)) {
+        void *dimg = nullptr, *dmax;
+        if (image) SK_TRY(sk_scratch(ctx, "image", (size_t)(n * n) * 8, &dimg));
+        SK_TRY(sk_scratch(ctx, "image_max", 16, &dmax));
+        SK_TRY(sk_grid_to_image_dev(ctx, n, (double *)dgrid, (double *)dimg, (double *)dmax, ctx->stream));
+        if (image) SK_TRY(down(ctx, image, dimg, (size_t)(n * n) * 8));
+        if (max_out) SK_TRY(down(ctx, max_out, dmax, 8));
+    }
+    SK_TRY(t.finish());
+    return check_flags(ctx, "aw_gridding");
+}
+
+// ------------------------------------------------------------------------------------------ w-kernels
+extern "C" int skagrid_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *w, int64_t npixff, int64_t npixkern, int64_t qpx,
+                                 int conjugate, double *out) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, nw > 0 && w && out, "w_kernels: NULL pointer or nw <= 0");
+    Timer t(ctx);
+    const size_t bytes = (size_t)(nw * qpx * qpx * npixkern * npixkern) * 16;
+    void *dout;
+    SK_TRY(sk_scratch(ctx, "wkern_out", bytes, &dout));
+    SK_TRY(sk_w_kernels_dev(ctx, theta, nw, w, npixff, npixkern, qpx, conjugate, (double *)dout, ctx->stream));
+    SK_TRY(down(ctx, out, dout, bytes));
+    return t.finish();
+}
+
+// Device-output variant used by bench.py to build the kernel table without a host round trip.
+extern "C" int skagrid_dev_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *w_host, int64_t npixff, int64_t npixkern,
+                                     int64_t qpx, int conjugate, double *d_out, void *stream) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, nw > 0 && w_host && d_out, "dev_w_kernels: NULL pointer or nw <= 0");
+    return sk_w_kernels_dev(ctx, theta, nw, w_host, npixff, npixkern, qpx, conjugate, d_out, sk_stream(ctx, stream));
+}

@@ -1,0 +1,385 @@
+// plan.cu -- bit-exact binning (frac_coord / findClosest) and the uv-tile bucket sort that feeds the
+// gridder and degridder.
+//
+// Reference semantics restated here:
+//   frac_coord   src/Gridding.hs:126-140      frac_coords  src/Gridding.hs:142-151
+//   findClosest  src/Gridding.hs:895-907      fixoutofbounds (clip, never wrap) src/Gridding.hs:883-891
+// The reference has no sort: its `permute (+)` scatters V*S^2 taps unordered.  Here every visibility
+// gets an integer key (uv tile of its footprint origin, 2x2 micro-tile inside the tile) and a counting
+// sort (histogram -> exclusive scan -> scatter) groups the 32-byte records per key.
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+struct BinParams {
+    double halfwf, wf, halfhf, hf, qpxf, qpxfrac;
+    i64 qpx, width, height, row0, row1, gh, gw, halfgh, halfgw, nw;
+    int ntx, nty, normalise, slice_override;
+    int mt_shift, mtr;  // micro-tile edge = 1 << mt_shift; micro-tiles per tile row
+};
+
+static BinParams make_bin_params(const Geom &g, int slice_override) {
+    BinParams p;
+    p.halfwf = (double)(g.width / 2);   // n `div` 2, n > 0
+    p.wf = (double)g.width;
+    p.halfhf = (double)(g.height / 2);
+    p.hf = (double)g.height;
+    p.qpxf = (double)g.qpx;
+    p.qpxfrac = 0.5 / p.qpxf;
+    p.qpx = g.qpx; p.width = g.width; p.height = g.height; p.row0 = g.row0; p.row1 = g.row1;
+    p.gh = g.gh; p.gw = g.gw; p.halfgh = g.gh / 2; p.halfgw = g.gw / 2; p.nw = g.nw;
+    p.ntx = g.ntx; p.nty = g.nty; p.normalise = g.normalise; p.slice_override = slice_override;
+    p.mt_shift = g.MT == 8 ? 3 : (g.MT == 4 ? 2 : 1); p.mtr = g.MTR;
+    return p;
+}
+
+int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, Geom *g) {
+    if (!in) return sk_fail(ctx, SKAGRID_EINVAL, "geom is NULL");
+    if (in->height <= 0 || in->width <= 0 || in->qpx <= 0 || in->gh <= 0 || in->gw <= 0 || in->nw <= 0)
+        return sk_fail(ctx, SKAGRID_EINVAL, "geom: non-positive dimension");
+    if (in->row0 < 0 || in->row1 > in->height || in->row0 >= in->row1)
+        return sk_fail(ctx, SKAGRID_EINVAL, "geom: bad owned row range [%lld,%lld) for height %lld", (i64)in->row0, (i64)in->row1, (i64)in->height);
+    if (in->gh > 127 || in->gw > 127) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel support %lldx%lld above the supported 127", (i64)in->gh, (i64)in->gw);
+    g->height = in->height; g->width = in->width; g->row0 = in->row0; g->row1 = in->row1;
+    g->nw = in->nw; g->qpx = in->qpx; g->gh = in->gh; g->gw = in->gw;
+    const i64 ntx = (in->width + in->gw - 1 + TILE - 1) / TILE;
+    const i64 nty = ((in->row1 - in->row0) + in->gh - 1 + TILE - 1) / TILE;
+    // register region / micro-tile of the tiled kernels: smallest R in {16,32,64} with R >= S+1, then the
+    // largest power-of-two micro-tile (<= 8) whose footprints still fit: MT - 1 + S <= R
+    const i64 smax = in->gh > in->gw ? in->gh : in->gw;
+    g->R = smax <= 15 ? 16 : (smax <= 31 ? 32 : (smax <= 63 ? 64 : 0));
+    const int rr = g->R ? g->R : 64;
+    g->MT = 2;
+    while (g->MT < 8 && g->MT * 2 - 1 + smax <= rr) g->MT *= 2;
+    g->MTR = TILE / g->MT;
+    g->SG = TILE - g->MT + rr;
+    const i64 nkeys = ntx * nty * g->MTR * g->MTR;
+    if (nkeys >= (i64)0xFFFFFFF0ll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: grid too large for 32-bit bucket keys");
+    if (in->nw * in->qpx * in->qpx >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel table has too many slices");
+    g->ntx = (int)ntx; g->nty = (int)nty; g->nkeys = nkeys; g->normalise = 1;
+    return SKAGRID_OK;
+}
+
+// Computes key / slice / loc of one visibility. Returns false when no tap can land on the owned rows.
+__device__ __forceinline__ bool bin_vis(const BinParams &P, double pu, double pv, i64 wb, i64 k,
+                                        uint32_t &key, uint32_t &slice, uint32_t &loc, bool &range_err) {
+    range_err = false;
+    if (!(fabs(pu) < 1.0e9) || !(fabs(pv) < 1.0e9)) return false;  // NaN / inf / absurd: no tap on the grid
+    i64 x, xf, y, yf;
+    frac_coord_one(pu, P.halfwf, P.wf, P.qpxf, P.qpxfrac, P.qpx, P.normalise, x, xf);
+    frac_coord_one(pv, P.halfhf, P.hf, P.qpxf, P.qpxfrac, P.qpx, P.normalise, y, yf);
+    const i64 ox = x - P.halfgw, oy = y - P.halfgh;
+    if (ox + P.gw <= 0 || ox >= P.width || oy + P.gh <= P.row0 || oy >= P.row1) return false;
+    if (P.slice_override) {
+        slice = (uint32_t)k;
+    } else {
+        if (wb < 0 || wb >= P.nw || xf < 0 || xf >= P.qpx || yf < 0 || yf >= P.qpx) { range_err = true; return false; }
+        slice = (uint32_t)((wb * P.qpx + yf) * P.qpx + xf);
+    }
+    const i64 oxs = ox + P.gw - 1, oys = oy + P.gh - 1 - P.row0;
+    const int tx = (int)(oxs / TILE), ty = (int)(oys / TILE);
+    const int lx = (int)(oxs % TILE), ly = (int)(oys % TILE);
+    const uint32_t mt = (uint32_t)((ly >> P.mt_shift) * P.mtr + (lx >> P.mt_shift));
+    loc = ((uint32_t)ly << 8) | (uint32_t)lx;
+    key = (uint32_t)(ty * P.ntx + tx) * (uint32_t)(P.mtr * P.mtr) + mt;
+    return true;
+}
+
+__global__ void __launch_bounds__(256) bin_hist_kernel(BinParams P, i64 count, const double *__restrict__ u,
+                                                       const double *__restrict__ v, const i64 *__restrict__ wbin,
+                                                       uint32_t *__restrict__ hist, uint32_t *__restrict__ counters,
+                                                       uint32_t *__restrict__ err_flag) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    uint32_t kept = 0, dropped = 0, rerr = 0;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+        uint32_t key, slice, loc; bool re;
+        if (bin_vis(P, u[k], v[k], wbin ? wbin[k] : 0, k, key, slice, loc, re)) { atomicAdd(&hist[key], 1u); ++kept; }
+        else { ++dropped; rerr |= re ? 1u : 0u; }
+    }
+    // block-level reduction of the statistics: one atomic per warp
+    for (int o = 16; o > 0; o >>= 1) {
+        kept += __shfl_xor_sync(0xffffffffu, kept, o);
+        dropped += __shfl_xor_sync(0xffffffffu, dropped, o);
+        rerr |= __shfl_xor_sync(0xffffffffu, rerr, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (kept) atomicAdd(&counters[2], kept);
+        if (dropped) atomicAdd(&counters[3], dropped);
+        if (rerr) atomicOr(err_flag, 1u);
+    }
+}
+
+__global__ void __launch_bounds__(256) bin_scatter_kernel(BinParams P, i64 count, const double *__restrict__ u,
+                                                          const double *__restrict__ v, const i64 *__restrict__ wbin,
+                                                          const double *__restrict__ vis, uint32_t *__restrict__ offs,
+                                                          VisRec *__restrict__ rec) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+        uint32_t key, slice, loc; bool re;
+        if (!bin_vis(P, u[k], v[k], wbin ? wbin[k] : 0, k, key, slice, loc, re)) continue;
+        const uint32_t pos = atomicAdd(&offs[key], 1u);
+        double2 vv = make_double2(0.0, 0.0);
+        if (vis) vv = reinterpret_cast<const double2 *>(vis)[k];
+        // two 16-byte stores per record
+        double2 *dst = reinterpret_cast<double2 *>(rec + pos);
+        dst[0] = vv;
+        uint4 meta = make_uint4(slice, loc, (uint32_t)k, key / (uint32_t)(P.mtr * P.mtr));
+        reinterpret_cast<uint4 *>(dst)[1] = meta;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ scan
+// Exclusive prefix sum over uint32, three passes (tile sums, scan of tile sums, apply). 4096 per block.
+constexpr int SCAN_T = 256, SCAN_PER = 16, SCAN_TILE = SCAN_T * SCAN_PER;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t *warp_sums, uint32_t &total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = val;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t w = lane < (SCAN_T / 32) ? warp_sums[lane] : 0;
+        uint32_t winc = w;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        if (lane < (SCAN_T / 32)) warp_sums[lane] = winc - w;  // exclusive warp offsets
+        if (lane == 31) warp_sums[32] = winc;                   // block total
+    }
+    __syncthreads();
+    total = warp_sums[32];
+    return warp_sums[wid] + inc - val;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_tile_sums(const uint32_t *__restrict__ data, i64 n, uint32_t *__restrict__ sums) {
+    __shared__ uint32_t ws[33];
+    const i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_PER;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER; ++i) if (base + i < n) s += data[base + i];
+    uint32_t total;
+    block_exclusive_scan(s, ws, total);
+    if (threadIdx.x == 0) sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_sums(uint32_t *sums, i64 nb) {
+    __shared__ uint32_t ws[33];
+    uint32_t carry = 0;
+    for (i64 base = 0; base < nb; base += SCAN_T) {
+        const i64 i = base + threadIdx.x;
+        uint32_t v = i < nb ? sums[i] : 0, total;
+        uint32_t ex = block_exclusive_scan(v, ws, total);
+        if (i < nb) sums[i] = carry + ex;
+        carry += total;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(SCAN_T) scan_apply(uint32_t *__restrict__ data, i64 n, const uint32_t *__restrict__ sums) {
+    __shared__ uint32_t ws[33];
+    const i64 base = (i64)blockIdx.x * SCAN_TILE + (i64)threadIdx.x * SCAN_PER;
+    uint32_t v[SCAN_PER], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER; ++i) { v[i] = (base + i < n) ? data[base + i] : 0; s += v[i]; }
+    uint32_t total;
+    uint32_t ex = block_exclusive_scan(s, ws, total) + sums[blockIdx.x];
+#pragma unroll
+    for (int i = 0; i < SCAN_PER; ++i) { if (base + i < n) data[base + i] = ex; ex += v[i]; }
+}
+
+// ------------------------------------------------------------------------------------------ work items
+// After the scatter offs[k] is the END of bucket k. One thread per uv tile cuts the tile's records into
+// runs of at most CHUNK so that a dense tile is shared by many blocks.
+__global__ void __launch_bounds__(256) make_items_kernel(const uint32_t *__restrict__ offs, int ntiles, int mt_per_tile, WorkItem *__restrict__ items,
+                                                         uint32_t *__restrict__ counters, uint32_t max_items) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    const uint32_t begin = t == 0 ? 0u : offs[(i64)t * mt_per_tile - 1];
+    const uint32_t end = offs[(i64)t * mt_per_tile + mt_per_tile - 1];
+    if (end == begin) return;
+    atomicAdd(&counters[4], 1u);
+    const uint32_t n = (end - begin + CHUNK - 1) / CHUNK;
+    const uint32_t base = atomicAdd(&counters[0], n);
+    for (uint32_t c = 0; c < n && base + c < max_items; ++c) {
+        WorkItem it;
+        it.tile = (uint32_t)t;
+        it.begin = begin + c * CHUNK;
+        it.end = min(end, it.begin + CHUNK);
+        it.pad = 0;
+        items[base + c] = it;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ plan API
+void sk_plan_free(skagrid_plan *p) {
+    if (!p) return;
+    if (p->d_offs) cudaFree(p->d_offs);
+    if (p->d_rec) cudaFree(p->d_rec);
+    if (p->d_items) cudaFree(p->d_items);
+    if (p->d_counters) cudaFree(p->d_counters);
+    if (p->d_blocksums) cudaFree(p->d_blocksums);
+    delete p;
+}
+
+int sk_plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double *u, const double *v,
+                     const i64 *wbin, const double *vis, cudaStream_t st) {
+    if (count < 0 || count > p->capacity) return sk_fail(ctx, SKAGRID_EINVAL, "plan: count %lld exceeds capacity %lld", count, p->capacity);
+    if (count > 0 && (!u || !v)) return sk_fail(ctx, SKAGRID_EINVAL, "plan: u/v is NULL");
+    p->count = count;
+    p->has_vis = vis != nullptr;
+    const Geom &g = p->g;
+    const BinParams P = make_bin_params(g, p->slice_override);
+    SK_CUDA(ctx, cudaMemsetAsync(p->d_offs, 0, (size_t)(g.nkeys + 1) * sizeof(uint32_t), st));
+    SK_CUDA(ctx, cudaMemsetAsync(p->d_counters, 0, 16 * sizeof(uint32_t), st));
+    const int blocks = ctx->sm_count * 8;
+    if (count > 0) {
+        bin_hist_kernel<<<blocks, 256, 0, st>>>(P, count, u, v, wbin, p->d_offs, p->d_counters, ctx->d_flags);
+        SK_LAUNCH_CHECK(ctx);
+    }
+    const i64 n = g.nkeys + 1;
+    const i64 nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    scan_tile_sums<<<(unsigned)nb, SCAN_T, 0, st>>>(p->d_offs, n, p->d_blocksums);
+    SK_LAUNCH_CHECK(ctx);
+    scan_sums<<<1, SCAN_T, 0, st>>>(p->d_blocksums, nb);
+    SK_LAUNCH_CHECK(ctx);
+    scan_apply<<<(unsigned)nb, SCAN_T, 0, st>>>(p->d_offs, n, p->d_blocksums);
+    SK_LAUNCH_CHECK(ctx);
+    if (count > 0) {
+        bin_scatter_kernel<<<blocks, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
+        SK_LAUNCH_CHECK(ctx);
+    }
+    const int ntiles = g.ntx * g.nty;
+    make_items_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(p->d_offs, ntiles, g.MTR * g.MTR, p->d_items, p->d_counters, (uint32_t)p->max_items);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
+int sk_plan_alloc(skagrid_ctx *ctx, const skagrid_geom *geom, i64 capacity, int slice_override, skagrid_plan **out) {
+    *out = nullptr;
+    if (capacity < 0 || capacity >= (i64)0xFFFFFFF0ll) return sk_fail(ctx, SKAGRID_EINVAL, "plan: count %lld out of range", capacity);
+    skagrid_plan *p = new skagrid_plan();
+    memset(p, 0, sizeof *p);
+    int rc = sk_geom_init(ctx, geom, &p->g);
+    if (rc) { delete p; return rc; }
+    p->capacity = capacity > 0 ? capacity : 1;
+    p->slice_override = slice_override;
+    const Geom &g = p->g;
+    const i64 ntiles = (i64)g.ntx * g.nty;
+    p->max_items = p->capacity / CHUNK + ntiles + 1;
+    p->nblocksums = (g.nkeys + 1 + SCAN_TILE - 1) / SCAN_TILE;
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_offs, (size_t)(g.nkeys + 1) * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_rec, (size_t)p->capacity * sizeof(VisRec));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_items, (size_t)p->max_items * sizeof(WorkItem));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_counters, 16 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&p->d_blocksums, (size_t)(p->nblocksums + 1) * sizeof(uint32_t));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        sk_plan_free(p);
+        return sk_fail(ctx, SKAGRID_ENOMEM, "plan: device allocation failed for %lld visibilities, %lld buckets: %s", capacity, g.nkeys, cudaGetErrorString(e));
+    }
+    *out = p;
+    return SKAGRID_OK;
+}
+
+// Reads and clears the context's device error word (bit 0: a w-plane / oversampling / antenna index out of
+// range, bit 1: a visibility outside the weight grid).  Synchronises `st`.
+int sk_take_flags(skagrid_ctx *ctx, cudaStream_t st, uint32_t *flags) {
+    SK_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    SK_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t), st));
+    SK_CUDA(ctx, cudaStreamSynchronize(st));
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_dev_plan_create(skagrid_ctx *ctx, const skagrid_geom *geom, int64_t count, const double *u,
+                                       const double *v, const int64_t *wbin, const double *vis, int slice_override,
+                                       void *stream, skagrid_plan **out) {
+    if (!ctx || !out) return SKAGRID_EINVAL;
+    *out = nullptr;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    skagrid_plan *p = nullptr;
+    SK_TRY(sk_plan_alloc(ctx, geom, count, slice_override, &p));
+    cudaStream_t st = sk_stream(ctx, stream);
+    int rc = sk_plan_fill(ctx, p, count, u, v, (const i64 *)wbin, vis, st);
+    uint32_t flag = 0;
+    if (!rc) rc = sk_take_flags(ctx, st, &flag);
+    if (rc) { sk_plan_free(p); return rc; }
+    if (flag & 1u) { sk_plan_free(p); return sk_fail(ctx, SKAGRID_ERANGE, "plan: a w-plane index is outside [0,%lld)", (i64)geom->nw); }
+    *out = p;
+    return SKAGRID_OK;
+}
+
+extern "C" void skagrid_dev_plan_destroy(skagrid_ctx *ctx, skagrid_plan *plan) {
+    if (ctx) cudaSetDevice(ctx->device);
+    sk_plan_free(plan);
+}
+
+extern "C" int skagrid_dev_plan_update(skagrid_ctx *ctx, skagrid_plan *plan, int64_t count, const double *u,
+                                       const double *v, const int64_t *wbin, const double *vis, void *stream) {
+    if (!ctx || !plan) return SKAGRID_EINVAL;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sk_plan_fill(ctx, plan, count, u, v, (const i64 *)wbin, vis, sk_stream(ctx, stream));
+}
+
+extern "C" int skagrid_dev_plan_stats(skagrid_ctx *ctx, skagrid_plan *plan, void *stream, int64_t stats[5]) {
+    if (!ctx || !plan || !stats) return SKAGRID_EINVAL;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint32_t c[16];
+    cudaStream_t st = sk_stream(ctx, stream);
+    SK_CUDA(ctx, cudaMemcpyAsync(c, plan->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
+    SK_CUDA(ctx, cudaStreamSynchronize(st));
+    stats[0] = c[2]; stats[1] = c[3]; stats[2] = c[0]; stats[3] = (i64)plan->g.ntx * plan->g.nty; stats[4] = c[4];
+    return SKAGRID_OK;
+}
+
+// ------------------------------------------------------------------------------------------ public binning kernels
+__global__ void __launch_bounds__(256) frac_coord_kernel(i64 n, i64 qpx, i64 count, const double *__restrict__ p, i64 *__restrict__ fl,
+                                                         i64 *__restrict__ fr, int normalise) {
+    const double halfnf = (double)(n / 2), nf = (double)n, qpxf = (double)qpx, qpxfrac = 0.5 / (double)qpx;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+        i64 a, b;
+        frac_coord_one(p[k], halfnf, nf, qpxf, qpxfrac, qpx, normalise, a, b);
+        fl[k] = a; fr[k] = b;
+    }
+}
+
+int sk_frac_coord_dev(skagrid_ctx *ctx, i64 n, i64 qpx, i64 count, const double *p, i64 *fl, i64 *frac, int normalise, cudaStream_t st) {
+    if (count <= 0) return SKAGRID_OK;
+    const int blocks = (int)std::min<i64>((count + 255) / 256, (i64)ctx->sm_count * 16);
+    frac_coord_kernel<<<blocks, 256, 0, st>>>(n, qpx, count, p, fl, frac, normalise);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
+// findClosest, src/Gridding.hs:895-907, with the Q4 clamp (w above the last plane -> nw-1).
+__device__ __forceinline__ i64 find_closest_one(i64 len, const double *__restrict__ ws, double w) {
+    i64 mn = 0, mx = len;
+    while ((mx - mn) / 2 >= 1) {  // operands non-negative: C division == Haskell div
+        const i64 id = (mx + mn) / 2;
+        if (w > ws[id]) mn = id; else mx = id;
+    }
+    if (mx >= len) return mn;
+    return (fabs(w - ws[mn]) < fabs(w - ws[mx])) ? mn : mx;
+}
+
+__global__ void __launch_bounds__(256) find_closest_kernel(i64 len, const double *__restrict__ ws, i64 count, const double *__restrict__ w,
+                                                           i64 *__restrict__ out) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) out[k] = find_closest_one(len, ws, w[k]);
+}
+
+int sk_find_closest_dev(skagrid_ctx *ctx, i64 nw, const double *wbins, i64 count, const double *w, i64 *out, cudaStream_t st) {
+    if (count <= 0) return SKAGRID_OK;
+    if (nw <= 0) return sk_fail(ctx, SKAGRID_EINVAL, "find_closest: empty wbins");
+    const int blocks = (int)std::min<i64>((count + 255) / 256, (i64)ctx->sm_count * 16);
+    find_closest_kernel<<<blocks, 256, 0, st>>>(nw, wbins, count, w, out);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}

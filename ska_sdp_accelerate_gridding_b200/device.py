@@ -1,0 +1,121 @@
+"""Device-resident API: torch tensors as device memory, torch's current CUDA stream as the launch stream,
+libskagrid.so's `skagrid_dev_*` entry points for the arithmetic.  torch is plumbing only (allocation,
+streams, NCCL); no torch op touches the gridding arithmetic."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .context import Context, get_context
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t, dtype, name):
+    if t is None:
+        return
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA tensor of {dtype}")
+
+
+def context_for_current_device() -> Context:
+    return get_context(torch.cuda.current_device())
+
+
+def synth_vis(seed, first, count, n, support, nw, uniform=False, with_vis=True, ctx=None):
+    """SURVEY.md 8d synthetic SKA1-Low-shaped visibilities [first, first+count) -> (u, v, wbin, vis) on the device."""
+    ctx = ctx or context_for_current_device()
+    dev = torch.device("cuda", ctx.device)
+    u = torch.empty(count, dtype=torch.float64, device=dev)
+    v = torch.empty(count, dtype=torch.float64, device=dev)
+    wbin = torch.empty(count, dtype=torch.int64, device=dev)
+    vis = torch.empty(count, dtype=torch.complex128, device=dev) if with_vis else None
+    ctx.check(ctx.lib.skagrid_dev_synth_vis(ctx.h, seed, first, count, n, support, nw, int(uniform), _p(u), _p(v), _p(wbin), _p(vis), _stream()))
+    return u, v, wbin, vis
+
+
+def w_kernel_table(theta, ws, npixff, npixkern, qpx, conjugate=True, ctx=None):
+    """w_kernel (src/Gridding.hs:610-728) for every w in `ws`, built in device memory -> [nw,qpx,qpx,s,s]."""
+    ctx = ctx or context_for_current_device()
+    ws = np.ascontiguousarray(ws, dtype=np.float64)
+    out = torch.empty((ws.size, qpx, qpx, npixkern, npixkern), dtype=torch.complex128, device=torch.device("cuda", ctx.device))
+    ctx.check(ctx.lib.skagrid_dev_w_kernels(ctx.h, float(theta), ws.size, ws.ctypes.data, npixff, npixkern, qpx, int(conjugate), _p(out), _stream()))
+    return out
+
+
+class Plan:
+    """Bit-exact binning + uv-tile bucketing of one batch of visibilities (skagrid_dev_plan_*)."""
+
+    def __init__(self, height, width, table_shape, u, v, wbin=None, vis=None, rows=None, slice_override=False, ctx=None):
+        self.ctx = ctx or context_for_current_device()
+        if len(table_shape) == 4:
+            table_shape = (1,) + tuple(table_shape)
+        nw, qpx, qpx2, gh, gw = table_shape
+        if qpx != qpx2:
+            raise ValueError("kernel table must be [nw,qpx,qpx,gh,gw]")
+        row0, row1 = rows if rows is not None else (0, height)
+        self.geom = _lib.Geom(height, width, row0, row1, nw, qpx, gh, gw)
+        self.rows = (row0, row1)
+        self.width = width
+        _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(wbin, torch.int64, "wbin"); _chk(vis, torch.complex128, "vis")
+        self.count = int(u.numel())
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.skagrid_dev_plan_create(self.ctx.h, C.byref(self.geom), self.count, _p(u), _p(v), _p(wbin), _p(vis),
+                                                            int(slice_override), _stream(), C.byref(h)))
+        self.h = h
+
+    def update(self, u, v, wbin=None, vis=None):
+        _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(wbin, torch.int64, "wbin"); _chk(vis, torch.complex128, "vis")
+        self.ctx.check(self.ctx.lib.skagrid_dev_plan_update(self.ctx.h, self.h, int(u.numel()), _p(u), _p(v), _p(wbin), _p(vis), _stream()))
+        self.count = int(u.numel())
+
+    def stats(self):
+        out = (C.c_int64 * 5)()
+        self.ctx.check(self.ctx.lib.skagrid_dev_plan_stats(self.ctx.h, self.h, _stream(), C.byref(out)))
+        return dict(kept=out[0], dropped=out[1], work_items=out[2], tiles=out[3], nonempty_tiles=out[4])
+
+    def grid(self, table, grid, variant=0):
+        """grid[row0:row1] += sum vis_k * table[slice_k].  variant 0 tiled (+L1 prefetch), 1 atomic scatter, 2 tiled w/o prefetch."""
+        _chk(table, torch.complex128, "table"); _chk(grid, torch.complex128, "grid")
+        if grid.numel() != (self.rows[1] - self.rows[0]) * self.width:
+            raise ValueError("grid tensor does not match the plan's owned rows")
+        self.ctx.check(self.ctx.lib.skagrid_dev_grid(self.ctx.h, self.h, _p(table), _p(grid), int(variant), _stream()))
+
+    def degrid(self, table, grid, out=None):
+        _chk(table, torch.complex128, "table"); _chk(grid, torch.complex128, "grid")
+        if out is None:
+            out = torch.empty(self.count, dtype=torch.complex128, device=grid.device)
+        _chk(out, torch.complex128, "out")
+        self.ctx.check(self.ctx.lib.skagrid_dev_degrid(self.ctx.h, self.h, _p(table), _p(grid), _p(out), _stream()))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.ctx.lib.skagrid_dev_plan_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def grid_to_image(grid, want_image=True, ctx=None):
+    """In place on `grid` (n x n complex128 CUDA tensor): hermitian -> centred IFFT; returns (image or None, max tensor)."""
+    ctx = ctx or context_for_current_device()
+    _chk(grid, torch.complex128, "grid")
+    n = grid.shape[0]
+    img = torch.empty((n, n), dtype=torch.float64, device=grid.device) if want_image else None
+    mx = torch.empty(1, dtype=torch.float64, device=grid.device)
+    ctx.check(ctx.lib.skagrid_dev_grid_to_image(ctx.h, n, _p(grid), _p(img), _p(mx), _stream()))
+    return img, mx

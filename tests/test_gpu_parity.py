@@ -1,0 +1,354 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (host-pointer functions via the ctypes mirror of
+src/Gridding.hs, and the device-resident entry points), against the CPU oracle on the same seeded inputs.
+Integer / index results must be bit-exact; grids, images and visibilities within max-abs error <= 1e-10 of
+the peak (BASELINE.json north_star)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-10
+
+
+def rel_err(a, b):
+    peak = np.abs(b).max()
+    return np.abs(a - b).max() / (peak if peak > 0 else 1.0)
+
+
+@pytest.fixture(scope="module")
+def G():
+    from ska_sdp_accelerate_gridding_b200 import gridding
+    return gridding
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def _rand_c(rng, shape):
+    return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+
+def _t(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------------------ binning
+@pytest.mark.parametrize("n,qpx", [(2400, 8), (8192, 8), (32768, 8), (10, 1), (33, 4), (2400, 1)])
+def test_frac_coord_bit_exact(G, orc, n, qpx):
+    rng = np.random.default_rng(n + qpx)
+    p = np.concatenate([rng.uniform(-0.5, 0.5, 200000), [0.0, 0.25, -0.25, 0.4999999, -0.5, 1.0 / 3.0],
+                        (np.arange(-40, 40) + 0.5) / (n * qpx), np.arange(-40, 40) / (n * qpx * 2.0)])
+    for flags, norm in ((1, True), (0, False)):
+        fl, fr = G.frac_coord(n, qpx, p, flags=flags)
+        ofl, ofr = orc.frac_coord(n, qpx, p, normalise=norm)
+        assert np.array_equal(fl, ofl) and np.array_equal(fr, ofr)
+    q = p[::-1].copy()
+    x, xf, y, yf = G.frac_coords((n, n + 6), qpx, (p, q))
+    ox, oxf, oy, oyf = orc.frac_coords(n, n + 6, qpx, p, q)
+    assert np.array_equal(x, ox) and np.array_equal(xf, oxf) and np.array_equal(y, oy) and np.array_equal(yf, oyf)
+
+
+def test_find_closest_bit_exact(G, orc):
+    rng = np.random.default_rng(7)
+    for nw in (1, 2, 3, 37, 541):
+        ws = np.sort(rng.uniform(-3000, 3000, nw))
+        w = np.concatenate([rng.uniform(-3500, 3500, 50000), ws, (ws[:-1] + ws[1:]) / 2, [ws[-1] + 1.0, ws[0] - 1.0]])
+        assert np.array_equal(G.findClosest(ws, w), orc.find_closest(ws, w))
+
+
+def test_empty_inputs(G):
+    e = np.zeros(0)
+    fl, fr = G.frac_coord(16, 4, e)
+    assert fl.size == 0 and fr.size == 0
+    g = G.convgrid(np.ones((2, 2, 3, 3), complex), np.zeros((8, 8), complex), (e, e), np.zeros(0, complex))
+    assert not g.any()
+    assert G.convdegrid(np.ones((2, 2, 3, 3), complex), np.ones((8, 8), complex), (e, e)).size == 0
+
+
+# ------------------------------------------------------------------------------------------------ pre-steps
+def test_prestep_parity(G, orc):
+    from ska_sdp_accelerate_gridding_b200 import _lib
+    from ska_sdp_accelerate_gridding_b200 import image_dataset as D
+    rng = np.random.default_rng(11)
+    cnt, theta, lam = 50000, 0.01, 30000
+    u, v, w = (rng.uniform(-14000, 14000, cnt) for _ in range(3))
+    vis = _rand_c(rng, cnt)
+    ul = D.uvw_lambda(1.0e8, (u, v, w))
+    ol = orc.uvw_lambda(1.0e8, u, v, w)
+    assert all(np.array_equal(a, b) for a, b in zip(ul, ol))
+    (mu, mv, mw), mvis = G.mirror_uvw((u, v, w), vis)
+    ou, ov, ow, ovis = orc.mirror_uvw(u, v, w, vis)
+    assert np.array_equal(mu, ou) and np.array_equal(mv, ov) and np.array_equal(mw, ow) and np.array_equal(mvis, ovis)
+    wt = G.doweight(theta, lam, (u, v, w), vis)
+    assert np.array_equal(wt, orc.doweight(theta, lam, u, v, vis))
+    with pytest.raises(_lib.SkagridError):
+        G.doweight(theta, lam, (u * 100, v, w), vis)  # outside the weight grid
+
+
+def test_grid_simple_and_broken_numbers_golden(G, orc):
+    j = json.load(open(os.path.join(GOLD, "broken_numbers.json")))
+    # the permute (+) golden through the nearest-cell gridder: cell = n/2 + floor(0.5 + n p)  ->  p = (cell - 2) / 5
+    k = np.arange(10)
+    x, y = (2 * k) % 5, (3 * k + 1) % 5
+    val = (k + 5) + 1j
+    pu, pv = (x - 2) / 5.0, (y - 2) / 5.0
+    g = np.zeros((5, 5), complex)
+    for _ in range(2):
+        g = G.grid(g, (pu, pv), val)
+    assert np.array_equal(g, np.array(j["expected_re"]) + 1j * np.array(j["expected_im"]))
+    rng = np.random.default_rng(12)
+    u, v = rng.uniform(-0.5, 0.499, 30000), rng.uniform(-0.5, 0.499, 30000)
+    vis = _rand_c(rng, 30000)
+    a = G.grid(np.zeros((64, 64), complex), (u, v), vis)
+    assert rel_err(a, orc.grid_simple(np.zeros((64, 64), complex), u, v, vis)) < TOL
+    s = G.simple_imaging(0.01, 6400, (u * 6400, v * 6400, u), None, vis)
+    assert rel_err(s, orc.simple_imaging(0.01, 6400, u * 6400, v * 6400, u, vis)) < TOL
+
+
+# ------------------------------------------------------------------------------------------------ table gridders
+CASES = [
+    # n, s(h,w), qpx, nw, count, span   (span > 0.5: part of the footprints / visibilities fall off the grid)
+    (96, (7, 7), 4, 3, 500, 0.55),
+    (256, (15, 15), 8, 4, 20000, 0.5),
+    (200, (15, 15), 8, 1, 5000, 0.6),
+    (300, (31, 31), 8, 2, 3000, 0.52),
+    (128, (9, 9), 2, 2, 4000, 0.5),
+    (128, (13, 13), 4, 2, 4000, 0.5),
+    (160, (5, 11), 3, 2, 3000, 0.5),
+    (160, (33, 33), 2, 1, 600, 0.5),
+    (64, (1, 1), 1, 1, 1000, 0.5),
+    (260, (65, 65), 1, 1, 100, 0.45),
+]
+
+
+@pytest.mark.parametrize("n,s,qpx,nw,count,span", CASES)
+def test_convgrid2_and_degrid_parity(G, orc, n, s, qpx, nw, count, span):
+    rng = np.random.default_rng(n * 31 + s[0])
+    gcf = _rand_c(rng, (nw, qpx, qpx, s[0], s[1]))
+    u, v = rng.uniform(-span, span, count), rng.uniform(-span, span, count)
+    wb = rng.integers(0, nw, count)
+    vis = _rand_c(rng, count)
+    x, xf, y, yf = G.frac_coords((n, n), qpx, (u, v))
+    ox = orc.frac_coords(n, n, qpx, u, v)
+    assert all(np.array_equal(a, b) for a, b in zip((x, xf, y, yf), ox))
+    start = _rand_c(rng, (n, n))
+    g = G.convgrid2(gcf, start, (u, v), wb, vis)
+    og = orc.convgrid(gcf, start, u, v, vis, wbin=wb)
+    assert rel_err(g, og) < TOL
+    d = G.convdegrid2(gcf, og, (u, v), wb)
+    od = orc.convdegrid(gcf, og, u, v, wbin=wb)
+    assert rel_err(d, od) < TOL
+    if nw == 1:
+        assert rel_err(G.convgrid(gcf[0], start, (u, v), vis), og) < TOL
+        assert rel_err(G.convdegrid(gcf[0], og, (u, v)), od) < TOL
+
+
+def test_golden_random_case(G):
+    z = np.load(os.path.join(GOLD, "random_cases.npz"))
+    n = int(z["n"])
+    g = G.convgrid2(z["gcf"], np.zeros((n, n), complex), (z["u"], z["v"]), z["wbin"], z["vis"])
+    assert rel_err(g, z["grid"]) < TOL
+    d = G.convdegrid2(z["gcf"], z["grid"], (z["u"], z["v"]), z["wbin"])
+    assert rel_err(d, z["degrid"]) < TOL
+    x, xf, y, yf = G.frac_coords((n, n), 4, (z["u"], z["v"]))
+    assert np.array_equal(x, z["x"]) and np.array_equal(xf, z["xf"]) and np.array_equal(y, z["y"]) and np.array_equal(yf, z["yf"])
+
+
+def test_wbin_out_of_range_is_an_error(G):
+    from ska_sdp_accelerate_gridding_b200 import _lib
+    gcf = np.ones((2, 2, 2, 3, 3), complex)
+    with pytest.raises(_lib.SkagridError):
+        G.convgrid2(gcf, np.zeros((16, 16), complex), ([0.1], [0.1]), [2], [1 + 0j])
+
+
+def test_dense_tile_many_chunks_and_variants(orc):
+    """All visibilities in one uv tile (-> many work items flushing into the same cells) and the three gridder
+    variants (tiled with / without L1 prefetch, atomic scatter) agree with the oracle."""
+    import torch
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    rng = np.random.default_rng(99)
+    n, s, q, nw, cnt = 128, 15, 8, 2, 40000
+    gcf = _rand_c(rng, (nw, q, q, s, s))
+    u, v = rng.uniform(0.0, 20.0 / n, cnt), rng.uniform(0.0, 20.0 / n, cnt)
+    wb = rng.integers(0, nw, cnt)
+    vis = _rand_c(rng, cnt)
+    og = orc.convgrid(gcf, np.zeros((n, n), complex), u, v, vis, wbin=wb, parallel=True)
+    plan = dv.Plan(n, n, gcf.shape, _t(u), _t(v), _t(wb), _t(vis))
+    st = plan.stats()
+    assert st["kept"] == cnt and st["work_items"] >= cnt // 4096
+    for variant in (0, 1, 2):
+        grid = torch.zeros((n, n), dtype=torch.complex128, device="cuda")
+        plan.grid(_t(gcf), grid, variant=variant)
+        assert rel_err(grid.cpu().numpy(), og) < TOL, variant
+    d = plan.degrid(_t(gcf), _t(og)).cpu().numpy()
+    assert rel_err(d, orc.convdegrid(gcf, og, u, v, wbin=wb, parallel=True)) < TOL
+
+
+def test_row_slab_ownership(orc):
+    """uv-tile-sharded mode: two plans owning complementary row slabs reproduce the full grid exactly once."""
+    import torch
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    rng = np.random.default_rng(5)
+    n, s, q, nw, cnt = 192, 15, 4, 2, 20000
+    gcf = _rand_c(rng, (nw, q, q, s, s))
+    u, v = rng.uniform(-0.5, 0.5, cnt), rng.uniform(-0.5, 0.5, cnt)
+    wb = rng.integers(0, nw, cnt)
+    vis = _rand_c(rng, cnt)
+    og = orc.convgrid(gcf, np.zeros((n, n), complex), u, v, vis, wbin=wb)
+    g2 = _rand_c(rng, (n, n))
+    od = orc.convdegrid(gcf, g2, u, v, wbin=wb)
+    full = torch.zeros((n, n), dtype=torch.complex128, device="cuda")
+    dsum = torch.zeros(cnt, dtype=torch.complex128, device="cuda")
+    kept = 0
+    for rows in ((0, 70), (70, 192)):
+        plan = dv.Plan(n, n, gcf.shape, _t(u), _t(v), _t(wb), _t(vis), rows=rows)
+        kept += plan.stats()["kept"]
+        slab = torch.zeros((rows[1] - rows[0], n), dtype=torch.complex128, device="cuda")
+        plan.grid(_t(gcf), slab)
+        full[rows[0]:rows[1]] += slab
+        dsum += plan.degrid(_t(gcf), _t(g2[rows[0]:rows[1]]))  # partial sums over the owned rows
+    assert rel_err(full.cpu().numpy(), og) < TOL
+    assert rel_err(dsum.cpu().numpy(), od) < TOL
+    assert cnt <= kept <= cnt * 1.3  # only the footprints straddling row 70 are processed twice
+
+
+# ------------------------------------------------------------------------------------------------ AW path
+def test_convolve2d_and_aw_kernel(G, orc):
+    rng = np.random.default_rng(21)
+    for n in (3, 8, 15, 31):
+        a, b = _rand_c(rng, (n, n)), _rand_c(rng, (n, n))
+        assert rel_err(G.convolve2d(a, b), orc.convolve2d(a, b)) < 1e-12
+    nw, q, s, nant = 3, 4, 15, 5
+    wk, ak = _rand_c(rng, (nw, q, q, s, s)), _rand_c(rng, (nant, s, s))
+    cnt = 40
+    wb, yf, xf = rng.integers(0, nw, cnt), rng.integers(0, q, cnt), rng.integers(0, q, cnt)
+    a1, a2 = rng.integers(0, nant, cnt), rng.integers(0, nant, cnt)
+    out = G.aw_kernel_fn2(yf, xf, wk, ak, wb, a1, a2)
+    for k in range(cnt):
+        assert rel_err(out[k], orc.aw_kernel(wk[wb[k]], yf[k], xf[k], ak[a1[k]], ak[a2[k]])) < 1e-12
+
+
+def test_smalltest_fixture(G):
+    from tests.golden.make_golden import smalltest_inputs
+    wk, ak, uvw, idx, vis = smalltest_inputs()
+    stored = np.load(os.path.join(GOLD, "smalltest_oracle.npz"))
+    for fn in (G.convgrid3, G.convgrid4):
+        g = fn(wk, ak, np.zeros((10, 10), complex), (uvw[:, 0], uvw[:, 1], uvw[:, 2]), (idx[:, 0], idx[:, 1], idx[:, 2]), vis)
+        assert rel_err(g, stored["grid"]) < TOL
+        assert abs(abs(g[9, 6]) - 46.27454822566) < 1e-9
+
+
+def test_aw_gridding_end_to_end(G, orc):
+    from ska_sdp_accelerate_gridding_b200 import image_dataset as D
+    rng = np.random.default_rng(33)
+    theta, lam = 0.008, 30000   # N = 240
+    nw, q, s, nant, cnt = 5, 4, 15, 6, 3000
+    wk, ak = _rand_c(rng, (nw, q, q, s, s)) * 0.1, _rand_c(rng, (nant, s, s)) * 0.1
+    wbins = np.linspace(-400.0, 400.0, nw)
+    freq = 1.0e8
+    sc = 299792458.0 / freq
+    uvw_m = np.stack([rng.uniform(-12000, 12000, cnt) * sc, rng.uniform(-12000, 12000, cnt) * sc, rng.uniform(-380, 380, cnt) * sc], axis=1)
+    a1, a2 = rng.integers(0, nant, cnt), rng.integers(0, nant, cnt)
+    vis = _rand_c(rng, cnt)
+    mx, img, grd = D.aw_gridding_arrays(theta, lam, wk, wbins, ak, uvw_m, a1, a2, freq, vis, want_grid=True)
+    oimg, omx, ogrid = orc.aw_gridding(theta, lam, wk, wbins, ak, uvw_m[:, 0], uvw_m[:, 1], uvw_m[:, 2], a1, a2, freq, vis)
+    assert rel_err(grd, ogrid) < TOL
+    assert rel_err(img, oimg) < TOL
+    assert abs(mx - omx) <= TOL * abs(omx)
+    # aw_imaging alone, and its adjoint against the dot-product identity
+    u, v, w = orc.uvw_lambda(freq, uvw_m[:, 0], uvw_m[:, 1], uvw_m[:, 2])
+    g = G.aw_imaging(G.noArgs, G.noOtherArgs, theta, lam, wk, wbins, ak, (u, v, w), (a1, a2, None, None), vis)
+    assert rel_err(g, orc.aw_imaging(theta, lam, wk, wbins, ak, u, v, w, a1, a2, vis)) < TOL
+    wb = orc.find_closest(wbins, w)
+    g2 = _rand_c(rng, g.shape)
+    d = G.convdegrid3(wk, ak, g2, (u / lam, v / lam), (wb, a1, a2))
+    assert rel_err(d, orc.convdegrid_aw(wk, ak, g2, u / lam, v / lam, wb, a1, a2)) < TOL
+    lhs, rhs = np.vdot(g2, g), np.vdot(d, vis)
+    assert abs(lhs - rhs) < 1e-10 * abs(lhs)
+
+
+# ------------------------------------------------------------------------------------------------ grid -> image
+@pytest.mark.parametrize("n", [8, 9, 240, 255, 2400])
+def test_hermitian_fft_image(G, orc, n):
+    rng = np.random.default_rng(n)
+    g = _rand_c(rng, (n, n))
+    h = G.make_grid_hermitian(g)
+    assert rel_err(h, orc.make_grid_hermitian(g)) < 1e-15
+    assert rel_err(G.ifft(g), orc.ifft(g)) < 1e-12
+    if n <= 255:
+        assert rel_err(G.fft(g), orc.fft(g)) < 1e-12
+    img, mx = G.grid_to_image(g)
+    oimg = np.real(orc.ifft(orc.make_grid_hermitian(g)))
+    assert rel_err(img, oimg) < TOL and abs(mx - oimg.max()) <= TOL * abs(oimg.max())
+
+
+def test_w_kernel_and_w_cache_imaging(G, orc):
+    ko = G.KernelOptions(qpx=4, npixFF=64, npixKern=15, wstep=200)
+    ws = np.array([-400.0, 0.0, 250.0])
+    k = G.w_kernel(0.05, ws, ko)
+    for i, w in enumerate(ws):
+        assert rel_err(k[i], orc.w_kernel(0.05, w, 64, 15, 4)) < 1e-11
+    rng = np.random.default_rng(8)
+    cnt, theta, lam = 2000, 0.05, 4000  # N = 200
+    u, v, w = rng.uniform(-1800, 1800, cnt), rng.uniform(-1800, 1800, cnt), rng.uniform(-500, 500, cnt)
+    vis = _rand_c(rng, cnt)
+    g = G.w_cache_imaging(ko, G.noOtherArgs, theta, lam, (u, v, w), None, vis)
+    rw = (200 * (np.sign(w / 200) * np.floor(np.abs(w / 200) + 0.5))).astype(np.int64)
+    wmin = rw.min()
+    steps = (rw.max() - wmin) // 200 + 1
+    kern = np.stack([np.conj(orc.w_kernel(theta, float(i * 200 + wmin), 64, 15, 4)) for i in range(steps)])
+    og = orc.convgrid(kern, np.zeros((200, 200), complex), u / lam, v / lam, vis, wbin=(rw - wmin) // 200)
+    assert rel_err(g, og) < TOL
+
+
+def test_do_imaging(G, orc):
+    rng = np.random.default_rng(9)
+    cnt, theta, lam = 3000, 0.02, 6000  # N = 120
+    uvw = np.stack([rng.uniform(-2500, 2500, cnt), rng.uniform(-2500, 2500, cnt), rng.uniform(-100, 100, cnt)], axis=1)
+    vis = _rand_c(rng, cnt)
+    z = np.zeros(cnt)
+    drt, psf, pmax = G.do_imaging(theta, lam, uvw, z, z, z, 1e8, vis, G.simple_imaging)
+    odrt, opsf, opmax = orc.do_imaging(theta, lam, uvw[:, 0], uvw[:, 1], uvw[:, 2], vis, orc.simple_imaging)
+    assert rel_err(drt, odrt) < TOL and rel_err(psf, opsf) < TOL and abs(pmax - opmax) < TOL * abs(opmax)
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties
+def test_full_size_linearity_and_adjoint(G):
+    """BASELINE.json config-4 shape (8192^2 grid, S=15, Q=8, 32 w-planes) at 4e6 synthetic visibilities:
+    size-independent properties -- tiled == atomic scatter, sum(grid) == sum_k vis_k * sum(kernel_k) for
+    fully-inside footprints, <grid(v), g> == <v, degrid(g)>."""
+    import torch
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    n, s, q, nw, cnt = 8192, 15, 8, 32, 4_000_000
+    table = dv.w_kernel_table(0.01, np.linspace(-300.0, 300.0, nw), 128, s, q)
+    u, v, wb, vis = dv.synth_vis(20261018, 0, cnt, n, s, nw)
+    plan = dv.Plan(n, n, table.shape, u, v, wb, vis)
+    st = plan.stats()
+    assert st["kept"] == cnt and st["dropped"] == 0
+    g0 = torch.zeros((n, n), dtype=torch.complex128, device="cuda")
+    plan.grid(table, g0, variant=0)
+    g1 = torch.zeros((n, n), dtype=torch.complex128, device="cuda")
+    plan.grid(table, g1, variant=1)
+    peak = g1.abs().max().item()
+    assert (g0 - g1).abs().max().item() <= TOL * peak
+    # checksum: every footprint is inside the grid, so sum(grid) = sum_k vis_k * sum(table[slice_k])
+    _, xf = G.frac_coord(n, q, u.cpu().numpy())
+    _, yf = G.frac_coord(n, q, v.cpu().numpy())
+    ksum = table.sum(dim=(-1, -2)).reshape(-1)
+    sl = (wb * q + _t(yf)) * q + _t(xf)
+    expect = (vis * ksum[sl]).sum().item()
+    got = g0.sum().item()
+    assert abs(got - expect) <= 1e-9 * max(abs(expect), peak)
+    g2 = torch.randn((n, n), dtype=torch.float64, device="cuda").to(torch.complex128)
+    d = plan.degrid(table, g2)
+    lhs = (g2.conj() * g0).sum().item()
+    rhs = (d.conj() * vis).sum().item()
+    assert abs(lhs - rhs) <= 1e-9 * abs(lhs)
