@@ -176,7 +176,8 @@ int skagrid_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *
 
 /* ================================================================== device-resident API
  * All pointers are DEVICE pointers on ctx's device; `stream` is a cudaStream_t passed as void*
- * (NULL = the context's own stream).  Nothing here synchronises the host except where stated. */
+ * (NULL = the CUDA legacy default stream).  Work is ordered on that stream only; nothing here
+ * synchronises the host except where stated. */
 
 typedef struct skagrid_geom {
     int64_t height, width;   /* full grid size (binning uses these) */

@@ -121,7 +121,9 @@ int sk_fail(skagrid_ctx *ctx, int code, const char *fmt, ...);
 
 // named, growable device scratch (never shrinks; contents undefined after a grow)
 int sk_scratch(skagrid_ctx *ctx, const char *name, size_t bytes, void **out);
-static inline cudaStream_t sk_stream(skagrid_ctx *ctx, void *s) { return s ? (cudaStream_t)s : ctx->stream; }
+// device-resident API: the caller's stream as is; NULL is the CUDA (legacy) default stream, which is what
+// torch uses unless told otherwise -- NOT the context's private stream, or launches would race the caller's work
+static inline cudaStream_t sk_stream(skagrid_ctx *ctx, void *s) { (void)ctx; return (cudaStream_t)s; }
 
 // ---------------------------------------------------------------------------------------------
 // internal device-pointer entry points implemented across the TUs (all asynchronous on `st`)
