@@ -21,8 +21,9 @@ typedef unsigned long long u64;
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) VisRec {
     double re, im;       // visibility (0 for degrid-only plans)
-    uint32_t slice;      // kernel-table slice: (wbin*qpx + yf)*qpx + xf, or the visibility index (AW)
-    uint32_t loc;        // ly << 8 | lx : footprint origin inside the tile (0..TILE-1 each)
+    uint32_t kbase;      // (slice * gh*gw - (dy*gw + dx)) mod 2^32, slice = (wbin*qpx + yf)*qpx + xf or the visibility index (AW):
+                         // table element of tap (i,j) of this visibility = kbase + (dy+i)*gw + (dx+j)
+    uint32_t loc;        // one-hot(dy*MT + dx) << 16 | ly << 8 | lx: footprint origin inside the tile (0..TILE-1) and inside its micro-tile
     uint32_t index;      // position of the visibility in the caller's arrays (degrid output slot)
     uint32_t tile;       // uv tile ty * ntx + tx (lets a record be placed on the grid without its work item)
 };
@@ -47,7 +48,7 @@ struct Geom {
     i64 nw, qpx, gh, gw;
     int ntx, nty;        // tiles per dimension
     int R;               // register region edge: 16, 32 or 64 (0: shape not supported by the tiled kernels)
-    int MT;              // micro-tile edge: 2, 4 or 8
+    int MT;              // micro-tile edge: 2 or 4
     int MTR;             // micro-tiles per tile row = TILE / MT
     int SG;              // shared-memory subgrid edge = TILE - 1 + max(gh, gw)
     i64 nkeys;           // ntx * nty * MTR * MTR

@@ -15,7 +15,9 @@
 //    residue per visibility, accumulates it in REGISTERS while the micro-tile stays the same, and folds
 //    the registers into its own shared-memory cells when it changes -- no atomics, no barriers, no bank
 //    conflicts in the hot loop;
-//  * the kernel taps are 128-bit loads; the 16 threads of a row read 16 consecutive taps of the slice;
+//  * the kernel taps are 128-bit loads; the 16 threads of a row read 16 consecutive taps of the slice; the
+//    loop is software-pipelined (records two ahead, taps one ahead) so the L2 latency of the tap loads is
+//    covered by the FMAs of the previous visibility;
 //  * at the end of the item the subgrid is added to the grid in HBM/L2 with fp64 RED (no return value).
 //    Dense tiles are split over many blocks for load balance, which is why the flush is a reduction and
 //    not a plain store; its share of the runtime is small (one flush per <= 4096 visibilities).
@@ -37,133 +39,182 @@ struct GridArgs {
     int ntx;
     int width, nrows; // grid width, owned rows
     int queue;        // index into counters of this launch's queue head
-    int prefetch;     // issue L1 prefetches of upcoming kernel slices
 };
 
-__device__ __forceinline__ double2 ldg2(const double2 *p) {
-    return __ldg(p);
-}
-
-__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ double2 ldg2(const double2 *p) { return __ldg(p); }
 
 __device__ __forceinline__ void red_add(double *addr, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
 
+// Per-thread state of one micro-tile: where the thread's residues sit inside the R x R region.
+template <int C>
+struct MtState {
+    uint32_t key;                  // loc & mtkey_mask of the micro-tile (0xFFFFFFFF: none)
+    int toff[C][C];                // tap offset roty*gw + rotx of the thread's (a,b) residue
+    uint32_t vmask[C][C];          // bit 16 + dy*MT+dx set: residue (a,b) has a valid tap for a footprint at (dy,dx)
+    int cell[C][C];                // shared-memory cell of residue (a,b)
+};
+
+template <int R, int C>
+__device__ __forceinline__ void mt_setup(MtState<C> &S, uint32_t key, int ty, int tx, const GridArgs &A, int mt) {
+    S.key = key;
+    const int mx = (int)(key & 255u), my = (int)((key >> 8) & 255u);
+    int roty[C], rotx[C];
+    uint32_t ym[C], xm[C];
+#pragma unroll
+    for (int a = 0; a < C; ++a) {
+        roty[a] = (ty + 16 * a - my) & (R - 1);
+        rotx[a] = (tx + 16 * a - mx) & (R - 1);
+        ym[a] = 0; xm[a] = 0;
+        for (int d = 0; d < mt; ++d) {
+            if ((unsigned)(roty[a] - d) < (unsigned)A.gh) ym[a] |= 1u << d;
+            if ((unsigned)(rotx[a] - d) < (unsigned)A.gw) xm[a] |= 1u << d;
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < C; ++a)
+#pragma unroll
+        for (int b = 0; b < C; ++b) {
+            S.toff[a][b] = roty[a] * A.gw + rotx[b];
+            S.cell[a][b] = (my + roty[a]) * A.SG + mx + rotx[b];
+            uint32_t m = 0;
+            for (int d = 0; d < mt; ++d)
+                if ((ym[a] >> d) & 1u) m |= xm[b] << (d * mt);
+            S.vmask[a][b] = m << 16;  // lines up with the one-hot (dy*MT+dx) field of VisRec::loc
+        }
+}
+
+constexpr int REC_BATCH = GRID_THREADS;  // records staged in shared memory per batch (one per thread)
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int R>
-__global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 3 : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
+__global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 4 : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
     constexpr int C = R / 16;  // residues per thread per dimension
     extern __shared__ double2 sg[];
+    __shared__ __align__(16) uint4 s_rec[2][REC_BATCH * 2];  // double-buffered record batches (32 B each)
     __shared__ uint32_t s_item;
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int ncell = A.SG * A.SG;
     const uint32_t n_items = A.counters[0];
-    const int slice_lines = (A.s2 * 16 + 127) / 128;
-    constexpr int PD = 12;  // prefetch distance in records
+    const int mt = -A.mt_mask;  // micro-tile edge
+    const uint32_t mtkey_mask = (uint32_t)(A.mt_mask & 255) * 0x0101u;
+    const uint4 *recq = reinterpret_cast<const uint4 *>(A.rec);
 
     for (;;) {
         if (tid == 0) s_item = atomicAdd(&A.counters[A.queue], 1u);
         __syncthreads();
         const uint32_t item = s_item;
         if (item >= n_items) break;
-        for (int c = tid; c < ncell; c += GRID_THREADS) sg[c] = make_double2(0.0, 0.0);
         const WorkItem it = A.items[item];
-        __syncthreads();
+        const uint32_t nrec = it.end - it.begin;
+        const uint32_t nbatch = (nrec + REC_BATCH - 1) / REC_BATCH;
+        // stage batch 0 (asynchronously) while the subgrid is zeroed
+        if ((uint32_t)tid < nrec) {
+            cp_async16(&s_rec[0][2 * tid], recq + 2 * (size_t)(it.begin + tid));
+            cp_async16(&s_rec[0][2 * tid + 1], recq + 2 * (size_t)(it.begin + tid) + 1);
+        }
+        cp_async_commit();
+        for (int c = tid; c < ncell; c += GRID_THREADS) sg[c] = make_double2(0.0, 0.0);
 
         double2 acc[C][C];
-        int roty[C], rotx[C];
+        int cell_cur[C][C];
+        MtState<C> S;  // micro-tile state of the record whose taps were requested last
+        S.key = 0xFFFFFFFFu;
 #pragma unroll
-        for (int a = 0; a < C; ++a) {
-            roty[a] = 0; rotx[a] = 0;
+        for (int a = 0; a < C; ++a)
 #pragma unroll
-            for (int b = 0; b < C; ++b) acc[a][b] = make_double2(0.0, 0.0);
-        }
-        int cur_mx = -1, cur_my = -1;
+            for (int b = 0; b < C; ++b) { acc[a][b] = make_double2(0.0, 0.0); cell_cur[a][b] = 0; S.cell[a][b] = 0; S.toff[a][b] = 0; S.vmask[a][b] = 0; }
 
-        // software pipeline: the record of iteration r+1 is loaded while r is processed
-        const VisRec *rp = A.rec + it.begin;
-        double2 vis = ldg2(reinterpret_cast<const double2 *>(rp));
-        uint4 meta = __ldg(reinterpret_cast<const uint4 *>(rp) + 1);
-        uint32_t pf_slice = 0xFFFFFFFFu;
-
-        for (uint32_t r = it.begin; r < it.end; ++r) {
-            const uint32_t rn = (r + 1 < it.end) ? r + 1 : r;
-            const double2 vis_n = ldg2(reinterpret_cast<const double2 *>(A.rec + rn));
-            const uint4 meta_n = __ldg(reinterpret_cast<const uint4 *>(A.rec + rn) + 1);
-
-            if (A.prefetch && ((r & 7u) == (uint32_t)warp)) {
-                // this warp prefetches the kernel slice of a record PD ahead; the slice id it uses was
-                // loaded one turn (8 records) earlier so the prefetch never waits on that load
-                if (pf_slice != 0xFFFFFFFFu && lane < slice_lines)
-                    prefetch_l1(reinterpret_cast<const char *>(A.table + (size_t)pf_slice * A.s2) + lane * 128);
-                const uint32_t rpf = r + PD + 8;
-                pf_slice = rpf < it.end ? __ldg(&A.rec[rpf].slice) : 0xFFFFFFFFu;
-            }
-
-            const int lx = (int)(meta.y & 255u), ly = (int)(meta.y >> 8);
-            const int mx = lx & A.mt_mask, my = ly & A.mt_mask;
-            if (mx != cur_mx || my != cur_my) {  // warp-uniform: all threads walk the same records
-                if (cur_mx >= 0) {
-#pragma unroll
-                    for (int a = 0; a < C; ++a)
-#pragma unroll
-                        for (int b = 0; b < C; ++b) {
-                            if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
-                                double2 *cell = sg + (cur_my + roty[a]) * A.SG + cur_mx + rotx[b];
-                                double2 t = *cell;
-                                t.x += acc[a][b].x; t.y += acc[a][b].y;
-                                *cell = t;
-                                acc[a][b] = make_double2(0.0, 0.0);
-                            }
-                        }
-                }
-                cur_mx = mx; cur_my = my;
-#pragma unroll
-                for (int a = 0; a < C; ++a) {
-                    roty[a] = (ty + 16 * a - my) & (R - 1);
-                    rotx[a] = (tx + 16 * a - mx) & (R - 1);
-                }
-            }
-            const int dy = ly - my, dx = lx - mx;
-            const double2 *kp = A.table + (size_t)meta.x * A.s2;
-            double2 k[C][C];
-            bool ok[C][C];
-#pragma unroll
-            for (int a = 0; a < C; ++a) {
-                const int i = roty[a] - dy;
-#pragma unroll
-                for (int b = 0; b < C; ++b) {
-                    const int j = rotx[b] - dx;
-                    ok[a][b] = (unsigned)i < (unsigned)A.gh && (unsigned)j < (unsigned)A.gw;
-                    k[a][b] = make_double2(0.0, 0.0);
-                    if (ok[a][b]) k[a][b] = ldg2(kp + i * A.gw + j);
-                }
-            }
+        // request the taps of staged record `j` into k / remember where its products go
+        auto issue = [&](const uint4 *buf, uint32_t j, double2 (&k)[C][C], int (&cell)[C][C], bool &sw) {
+            const uint2 m = *reinterpret_cast<const uint2 *>(&buf[2 * j + 1]);  // kbase, loc (broadcast read)
+            const uint32_t key = m.y & mtkey_mask;
+            sw = key != S.key;
+            if (sw) mt_setup<R, C>(S, key, ty, tx, A, mt);  // warp-uniform
 #pragma unroll
             for (int a = 0; a < C; ++a)
 #pragma unroll
                 for (int b = 0; b < C; ++b) {
-                    // (vr + i vi)(kr + i ki); a zero tap (invalid cell) adds +0
+                    cell[a][b] = S.cell[a][b];
+                    k[a][b] = make_double2(0.0, 0.0);
+                    if (S.vmask[a][b] & m.y) k[a][b] = ldg2(A.table + (uint32_t)(m.x + (uint32_t)S.toff[a][b]));
+                }
+        };
+        // acc += vis_j * k; a micro-tile switch first folds the registers into the thread's own subgrid cells
+        auto consume = [&](const uint4 *buf, uint32_t j, const double2 (&k)[C][C], const int (&cell)[C][C], bool sw) {
+            const double2 vis = *reinterpret_cast<const double2 *>(&buf[2 * j]);
+#pragma unroll
+            for (int a = 0; a < C; ++a)
+#pragma unroll
+                for (int b = 0; b < C; ++b) {
+                    if (sw) {
+                        if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
+                            double2 t = sg[cell_cur[a][b]];
+                            t.x += acc[a][b].x; t.y += acc[a][b].y;
+                            sg[cell_cur[a][b]] = t;
+                            acc[a][b] = make_double2(0.0, 0.0);
+                        }
+                        cell_cur[a][b] = cell[a][b];
+                    }
+                    // (vr + i vi)(kr + i ki); an invalid cell has a zero tap and adds +0
                     acc[a][b].x = fma(vis.x, k[a][b].x, acc[a][b].x);
                     acc[a][b].x = fma(-vis.y, k[a][b].y, acc[a][b].x);
                     acc[a][b].y = fma(vis.x, k[a][b].y, acc[a][b].y);
                     acc[a][b].y = fma(vis.y, k[a][b].x, acc[a][b].y);
                 }
-            vis = vis_n; meta = meta_n;
-        }
-        if (cur_mx >= 0) {
-#pragma unroll
-            for (int a = 0; a < C; ++a)
-#pragma unroll
-                for (int b = 0; b < C; ++b) {
-                    if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
-                        double2 *cell = sg + (cur_my + roty[a]) * A.SG + cur_mx + rotx[b];
-                        double2 t = *cell;
-                        t.x += acc[a][b].x; t.y += acc[a][b].y;
-                        *cell = t;
-                    }
+        };
+
+        for (uint32_t bi = 0; bi < nbatch; ++bi) {
+            const uint32_t base = bi * REC_BATCH;
+            const uint32_t m = min((uint32_t)REC_BATCH, nrec - base);
+            // stage batch bi+1 into the other buffer (its previous contents were consumed before the barrier
+            // that ended iteration bi-1)
+            if (bi + 1 < nbatch) {
+                const uint32_t nb = base + REC_BATCH + tid;
+                if (nb < nrec) {
+                    cp_async16(&s_rec[(bi + 1) & 1][2 * tid], recq + 2 * (size_t)(it.begin + nb));
+                    cp_async16(&s_rec[(bi + 1) & 1][2 * tid + 1], recq + 2 * (size_t)(it.begin + nb) + 1);
                 }
+            }
+            cp_async_commit();
+            cp_async_wait<1>();   // batch bi has landed (for this thread); the barrier publishes it block-wide
+            __syncthreads();      // (first iteration: also orders the subgrid zeroing before any fold)
+            const uint4 *buf = s_rec[bi & 1];
+
+            // two tap-register sets in ping-pong: the taps of record j+1 are requested before the FMAs of
+            // record j issue, so each warp keeps two 128-bit tap loads per residue in flight
+            double2 kA[C][C], kB[C][C];
+            int cA[C][C], cB[C][C];
+            bool swA, swB;
+            issue(buf, 0, kA, cA, swA);
+            uint32_t j = 0;
+            for (; j + 1 < m; j += 2) {
+                issue(buf, j + 1, kB, cB, swB);
+                consume(buf, j, kA, cA, swA);
+                if (j + 2 < m) issue(buf, j + 2, kA, cA, swA);
+                consume(buf, j + 1, kB, cB, swB);
+            }
+            if (j < m) consume(buf, j, kA, cA, swA);
+            __syncthreads();  // every warp is done with buf before it is refilled
         }
+#pragma unroll
+        for (int a = 0; a < C; ++a)
+#pragma unroll
+            for (int b = 0; b < C; ++b) {
+                if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
+                    double2 t = sg[cell_cur[a][b]];
+                    t.x += acc[a][b].x; t.y += acc[a][b].y;
+                    sg[cell_cur[a][b]] = t;
+                }
+            }
         __syncthreads();
 
         // subgrid -> grid.  Cells outside the owned rows / the grid are dropped (fixoutofbounds).
@@ -180,6 +231,7 @@ __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 3 : (R == 32 ? 2 : 1)
                 red_add(g + 1, v.y);
             }
         }
+        cp_async_wait<0>();
         // the next iteration's first barrier orders these reads before the subgrid is zeroed again
     }
 }
@@ -194,53 +246,65 @@ __global__ void __launch_bounds__(256) grid_atomic_kernel(const GridArgs A) {
         const int i = t / A.gw, j = t - i * A.gw;
         const double2 vis = ldg2(reinterpret_cast<const double2 *>(A.rec + r));
         const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(A.rec + r) + 1);
-        const int lx = (int)(meta.y & 255u), ly = (int)(meta.y >> 8);
+        const int lx = (int)(meta.y & 255u), ly = (int)((meta.y >> 8) & 255u);
+        const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
         const int tyi = (int)(meta.w / (uint32_t)A.ntx), txi = (int)(meta.w % (uint32_t)A.ntx);
         const int gx = txi * TILE + lx - (A.gw - 1) + j, gy = tyi * TILE + ly - (A.gh - 1) + i;
         if ((unsigned)gx >= (unsigned)A.width || (unsigned)gy >= (unsigned)A.nrows) continue;
-        const double2 k = ldg2(A.table + (size_t)meta.x * A.s2 + t);
+        const double2 k = ldg2(A.table + (uint32_t)(meta.x + dy * (uint32_t)A.gw + dx + (uint32_t)t));
         double *g = reinterpret_cast<double *>(A.grid + (size_t)gy * A.width + gx);
         red_add(g, vis.x * k.x - vis.y * k.y);
         red_add(g + 1, vis.x * k.y + vis.y * k.x);
     }
 }
 
-// Degridder: the adjoint gather, one warp per visibility, lanes over taps, shuffle reduction.
+// Degridder: the adjoint gather.  Half a warp per visibility: lane j of the half-warp walks column j (+16, +32..)
+// of the footprint row by row, so the kernel taps and the grid cells are both contiguous 16-byte loads; the
+// partial sums are combined with four shuffle steps.
 //   vis_out[index] = sum_{i,j} conj(table[slice][i,j]) * grid[y0 + i, x0 + j]
-// Records are in tile order, so the warps of a block read the same few KB of the grid (L1/L2 hits) and
-// the slice is one contiguous, coalesced stream.
+// Records are in tile order, so the warps of a block read the same few KB of the grid (L1/L2 hits).
 __global__ void __launch_bounds__(256) degrid_warp_kernel(const GridArgs A) {
-    const int lane = threadIdx.x & 31;
-    const i64 warp0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    const int hl = threadIdx.x & 15;
+    const i64 hw0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const i64 nhw = ((i64)gridDim.x * blockDim.x) >> 4;
     const i64 count = (i64)A.counters[2];
-    for (i64 r = warp0; r < count; r += nwarps) {
-        const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(A.rec + r) + 1);
-        const int lx = (int)(meta.y & 255u), ly = (int)(meta.y >> 8);
-        const int tyi = (int)(meta.w / (uint32_t)A.ntx), txi = (int)(meta.w % (uint32_t)A.ntx);
-        const int gx0 = txi * TILE + lx - (A.gw - 1), gy0 = tyi * TILE + ly - (A.gh - 1);
-        const double2 *kp = A.table + (size_t)meta.x * A.s2;
+    const i64 rounds = (count + nhw - 1) / nhw;
+    for (i64 it = 0; it < rounds; ++it) {
+        const i64 r = it * nhw + hw0;   // both halves of a warp stay in the loop together (shuffles below)
+        const bool live = r < count;
         double ar = 0.0, ai = 0.0;
-        int i = lane / A.gw, j = lane - i * A.gw;
-        const int di = 32 / A.gw, dj = 32 - di * A.gw;
-        for (int t = lane; t < A.s2; t += 32) {
-            const int gx = gx0 + j, gy = gy0 + i;
-            if ((unsigned)gx < (unsigned)A.width && (unsigned)gy < (unsigned)A.nrows) {
-                const double2 k = ldg2(kp + t);
-                const double2 g = ldg2(A.grid + (size_t)gy * A.width + gx);
-                // conj(k) * g
-                ar = fma(k.x, g.x, ar); ar = fma(k.y, g.y, ar);
-                ai = fma(k.x, g.y, ai); ai = fma(-k.y, g.x, ai);
+        uint32_t out_index = 0;
+        if (live) {
+            const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(A.rec + r) + 1);
+            out_index = meta.z;
+            const int lx = (int)(meta.y & 255u), ly = (int)((meta.y >> 8) & 255u);
+            const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
+            const int tyi = (int)(meta.w / (uint32_t)A.ntx), txi = (int)(meta.w % (uint32_t)A.ntx);
+            const int gx0 = txi * TILE + lx - (A.gw - 1), gy0 = tyi * TILE + ly - (A.gh - 1);
+            const uint32_t kslice = meta.x + dy * (uint32_t)A.gw + dx;
+            const int i0 = max(0, -gy0), i1 = min(A.gh, A.nrows - gy0);
+            for (int j = hl; j < A.gw; j += 16) {
+                const int gx = gx0 + j;
+                if ((unsigned)gx >= (unsigned)A.width) continue;
+                const double2 *kp = A.table + (uint32_t)(kslice + (uint32_t)(i0 * A.gw + j));
+                const double2 *gp = A.grid + (size_t)(gy0 + i0) * A.width + gx;
+#pragma unroll 5
+                for (int i = i0; i < i1; ++i) {
+                    const double2 k = ldg2(kp);
+                    const double2 g = ldg2(gp);
+                    // conj(k) * g
+                    ar = fma(k.x, g.x, ar); ar = fma(k.y, g.y, ar);
+                    ai = fma(k.x, g.y, ai); ai = fma(-k.y, g.x, ai);
+                    kp += A.gw; gp += A.width;
+                }
             }
-            i += di; j += dj;
-            if (j >= A.gw) { j -= A.gw; ++i; }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
+        for (int o = 8; o > 0; o >>= 1) {
             ar += __shfl_xor_sync(0xffffffffu, ar, o);
             ai += __shfl_xor_sync(0xffffffffu, ai, o);
         }
-        if (lane == 0) A.vis_out[meta.z] = make_double2(ar, ai);
+        if (live && hl == 0) A.vis_out[out_index] = make_double2(ar, ai);
     }
 }
 
@@ -255,7 +319,7 @@ static GridArgs make_args(skagrid_plan *plan, const double *table, double *grid)
     A.mt_mask = ~(g.MT - 1);
     A.SG = g.SG; A.ntx = g.ntx;
     A.width = (int)g.width; A.nrows = (int)(g.row1 - g.row0);
-    A.queue = 1; A.prefetch = 0;
+    A.queue = 1;
     return A;
 }
 
@@ -288,7 +352,6 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
         SK_LAUNCH_CHECK(ctx);
         return SKAGRID_OK;
     }
-    A.prefetch = (variant == 2) ? 0 : 1;
     SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 1, 0, sizeof(uint32_t), st));
     if (R == 16) return launch_tiled<16>(ctx, A, st);
     if (R == 32) return launch_tiled<32>(ctx, A, st);

@@ -30,7 +30,7 @@ static BinParams make_bin_params(const Geom &g, int slice_override) {
     p.qpx = g.qpx; p.width = g.width; p.height = g.height; p.row0 = g.row0; p.row1 = g.row1;
     p.gh = g.gh; p.gw = g.gw; p.halfgh = g.gh / 2; p.halfgw = g.gw / 2; p.nw = g.nw;
     p.ntx = g.ntx; p.nty = g.nty; p.normalise = g.normalise; p.slice_override = slice_override;
-    p.mt_shift = g.MT == 8 ? 3 : (g.MT == 4 ? 2 : 1); p.mtr = g.MTR;
+    p.mt_shift = g.MT == 4 ? 2 : 1; p.mtr = g.MTR;
     return p;
 }
 
@@ -46,17 +46,18 @@ int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, Geom *g) {
     const i64 ntx = (in->width + in->gw - 1 + TILE - 1) / TILE;
     const i64 nty = ((in->row1 - in->row0) + in->gh - 1 + TILE - 1) / TILE;
     // register region / micro-tile of the tiled kernels: smallest R in {16,32,64} with R >= S+1, then the
-    // largest power-of-two micro-tile (<= 8) whose footprints still fit: MT - 1 + S <= R
+    // largest power-of-two micro-tile (<= 4, so that (dy,dx) fits a 16-bit one-hot) whose footprints still fit:
+    // MT - 1 + S <= R
     const i64 smax = in->gh > in->gw ? in->gh : in->gw;
     g->R = smax <= 15 ? 16 : (smax <= 31 ? 32 : (smax <= 63 ? 64 : 0));
     const int rr = g->R ? g->R : 64;
     g->MT = 2;
-    while (g->MT < 8 && g->MT * 2 - 1 + smax <= rr) g->MT *= 2;
+    while (g->MT < 4 && g->MT * 2 - 1 + smax <= rr) g->MT *= 2;
     g->MTR = TILE / g->MT;
     g->SG = TILE - g->MT + rr;
     const i64 nkeys = ntx * nty * g->MTR * g->MTR;
     if (nkeys >= (i64)0xFFFFFFF0ll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: grid too large for 32-bit bucket keys");
-    if (in->nw * in->qpx * in->qpx >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel table has too many slices");
+    if (in->nw * in->qpx * in->qpx * in->gh * in->gw >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel table has more than 2^32 taps");
     g->ntx = (int)ntx; g->nty = (int)nty; g->nkeys = nkeys; g->normalise = 1;
     return SKAGRID_OK;
 }
@@ -81,7 +82,10 @@ __device__ __forceinline__ bool bin_vis(const BinParams &P, double pu, double pv
     const int tx = (int)(oxs / TILE), ty = (int)(oys / TILE);
     const int lx = (int)(oxs % TILE), ly = (int)(oys % TILE);
     const uint32_t mt = (uint32_t)((ly >> P.mt_shift) * P.mtr + (lx >> P.mt_shift));
-    loc = ((uint32_t)ly << 8) | (uint32_t)lx;
+    const uint32_t mtm = (1u << P.mt_shift) - 1u, dx = (uint32_t)lx & mtm, dy = (uint32_t)ly & mtm;
+    loc = (0x10000u << ((dy << P.mt_shift) | dx)) | ((uint32_t)ly << 8) | (uint32_t)lx;
+    // element offset of tap (-dy, -dx) of the slice, modulo 2^32: the gridder adds its per-thread tap offset
+    slice = slice * (uint32_t)(P.gh * P.gw) - (dy * (uint32_t)P.gw + dx);
     key = (uint32_t)(ty * P.ntx + tx) * (uint32_t)(P.mtr * P.mtr) + mt;
     return true;
 }
@@ -230,6 +234,7 @@ void sk_plan_free(skagrid_plan *p) {
 int sk_plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double *u, const double *v,
                      const i64 *wbin, const double *vis, cudaStream_t st) {
     if (count < 0 || count > p->capacity) return sk_fail(ctx, SKAGRID_EINVAL, "plan: count %lld exceeds capacity %lld", count, p->capacity);
+    if (p->slice_override && count * p->g.gh * p->g.gw >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "plan: per-visibility kernel table has more than 2^32 taps");
     if (count > 0 && (!u || !v)) return sk_fail(ctx, SKAGRID_EINVAL, "plan: u/v is NULL");
     p->count = count;
     p->has_vis = vis != nullptr;
