@@ -24,6 +24,8 @@
 //
 // Variant 1 is the literal `permute (+)`: one thread per (visibility, tap) with a global atomic; it is the
 // cross-check of the tiled kernel and the path for kernel shapes the tiled kernel does not cover.
+#include <cstdlib>
+
 #include "common.cuh"
 
 struct GridArgs {
@@ -56,8 +58,8 @@ struct MtState {
     int cell[C][C];                // shared-memory cell of residue (a,b)
 };
 
-template <int R, int C>
-__device__ __forceinline__ void mt_setup(MtState<C> &S, uint32_t key, int ty, int tx, const GridArgs &A, int mt) {
+template <int R, int C, int MT>
+__device__ __forceinline__ void mt_setup(MtState<C> &S, uint32_t key, int ty, int tx, const GridArgs &A) {
     S.key = key;
     const int mx = (int)(key & 255u), my = (int)((key >> 8) & 255u);
     int roty[C], rotx[C];
@@ -67,7 +69,8 @@ __device__ __forceinline__ void mt_setup(MtState<C> &S, uint32_t key, int ty, in
         roty[a] = (ty + 16 * a - my) & (R - 1);
         rotx[a] = (tx + 16 * a - mx) & (R - 1);
         ym[a] = 0; xm[a] = 0;
-        for (int d = 0; d < mt; ++d) {
+#pragma unroll
+        for (int d = 0; d < MT; ++d) {
             if ((unsigned)(roty[a] - d) < (unsigned)A.gh) ym[a] |= 1u << d;
             if ((unsigned)(rotx[a] - d) < (unsigned)A.gw) xm[a] |= 1u << d;
         }
@@ -79,8 +82,9 @@ __device__ __forceinline__ void mt_setup(MtState<C> &S, uint32_t key, int ty, in
             S.toff[a][b] = roty[a] * A.gw + rotx[b];
             S.cell[a][b] = (my + roty[a]) * A.SG + mx + rotx[b];
             uint32_t m = 0;
-            for (int d = 0; d < mt; ++d)
-                if ((ym[a] >> d) & 1u) m |= xm[b] << (d * mt);
+#pragma unroll
+            for (int d = 0; d < MT; ++d)
+                if ((ym[a] >> d) & 1u) m |= xm[b] << (d * MT);
             S.vmask[a][b] = m << 16;  // lines up with the one-hot (dy*MT+dx) field of VisRec::loc
         }
 }
@@ -95,7 +99,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int R>
+template <int R, int MT>
 __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 4 : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
     constexpr int C = R / 16;  // residues per thread per dimension
     extern __shared__ double2 sg[];
@@ -104,8 +108,7 @@ __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 4 : (R == 32 ? 2 : 1)
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
     const int ncell = A.SG * A.SG;
     const uint32_t n_items = A.counters[0];
-    const int mt = -A.mt_mask;  // micro-tile edge
-    const uint32_t mtkey_mask = (uint32_t)(A.mt_mask & 255) * 0x0101u;
+    constexpr uint32_t mtkey_mask = (uint32_t)(~(MT - 1) & 255) * 0x0101u;
     const uint4 *recq = reinterpret_cast<const uint4 *>(A.rec);
 
     for (;;) {
@@ -133,37 +136,47 @@ __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 4 : (R == 32 ? 2 : 1)
 #pragma unroll
             for (int b = 0; b < C; ++b) { acc[a][b] = make_double2(0.0, 0.0); cell_cur[a][b] = 0; S.cell[a][b] = 0; S.toff[a][b] = 0; S.vmask[a][b] = 0; }
 
-        // request the taps of staged record `j` into k / remember where its products go
-        auto issue = [&](const uint4 *buf, uint32_t j, double2 (&k)[C][C], int (&cell)[C][C], bool &sw) {
+        // request the taps of staged record `j` into k; a record that starts a new micro-tile re-derives the
+        // thread's tap offsets and leaves `pending` set: the registers must be folded before it is consumed
+        bool pending = false;
+        auto issue = [&](const uint4 *buf, uint32_t j, double2 (&k)[C][C]) {
             const uint2 m = *reinterpret_cast<const uint2 *>(&buf[2 * j + 1]);  // kbase, loc (broadcast read)
             const uint32_t key = m.y & mtkey_mask;
-            sw = key != S.key;
-            if (sw) mt_setup<R, C>(S, key, ty, tx, A, mt);  // warp-uniform
+            if (key != S.key) {  // warp-uniform
+                mt_setup<R, C, MT>(S, key, ty, tx, A);
+                pending = true;
+            }
 #pragma unroll
             for (int a = 0; a < C; ++a)
 #pragma unroll
                 for (int b = 0; b < C; ++b) {
-                    cell[a][b] = S.cell[a][b];
                     k[a][b] = make_double2(0.0, 0.0);
                     if (S.vmask[a][b] & m.y) k[a][b] = ldg2(A.table + (uint32_t)(m.x + (uint32_t)S.toff[a][b]));
                 }
         };
-        // acc += vis_j * k; a micro-tile switch first folds the registers into the thread's own subgrid cells
-        auto consume = [&](const uint4 *buf, uint32_t j, const double2 (&k)[C][C], const int (&cell)[C][C], bool sw) {
+        // fold the register accumulators into the thread's own subgrid cells and retarget them
+        auto fold = [&]() {
+#pragma unroll
+            for (int a = 0; a < C; ++a)
+#pragma unroll
+                for (int b = 0; b < C; ++b) {
+                    if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
+                        double2 t = sg[cell_cur[a][b]];
+                        t.x += acc[a][b].x; t.y += acc[a][b].y;
+                        sg[cell_cur[a][b]] = t;
+                        acc[a][b] = make_double2(0.0, 0.0);
+                    }
+                    cell_cur[a][b] = S.cell[a][b];
+                }
+            pending = false;
+        };
+        // acc += vis_j * k
+        auto consume = [&](const uint4 *buf, uint32_t j, const double2 (&k)[C][C]) {
             const double2 vis = *reinterpret_cast<const double2 *>(&buf[2 * j]);
 #pragma unroll
             for (int a = 0; a < C; ++a)
 #pragma unroll
                 for (int b = 0; b < C; ++b) {
-                    if (sw) {
-                        if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
-                            double2 t = sg[cell_cur[a][b]];
-                            t.x += acc[a][b].x; t.y += acc[a][b].y;
-                            sg[cell_cur[a][b]] = t;
-                            acc[a][b] = make_double2(0.0, 0.0);
-                        }
-                        cell_cur[a][b] = cell[a][b];
-                    }
                     // (vr + i vi)(kr + i ki); an invalid cell has a zero tap and adds +0
                     acc[a][b].x = fma(vis.x, k[a][b].x, acc[a][b].x);
                     acc[a][b].x = fma(-vis.y, k[a][b].y, acc[a][b].x);
@@ -190,19 +203,22 @@ __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 4 : (R == 32 ? 2 : 1)
             const uint4 *buf = s_rec[bi & 1];
 
             // two tap-register sets in ping-pong: the taps of record j+1 are requested before the FMAs of
-            // record j issue, so each warp keeps two 128-bit tap loads per residue in flight
+            // record j issue, so each warp keeps two 128-bit tap loads per residue in flight.  Order matters:
+            // issue(j+1) may set `pending` (j+1 opens a new micro-tile); the fold must come after consume(j)
+            // and before consume(j+1), while S still describes record j+1.
             double2 kA[C][C], kB[C][C];
-            int cA[C][C], cB[C][C];
-            bool swA, swB;
-            issue(buf, 0, kA, cA, swA);
+            issue(buf, 0, kA);
+            if (pending) fold();
             uint32_t j = 0;
             for (; j + 1 < m; j += 2) {
-                issue(buf, j + 1, kB, cB, swB);
-                consume(buf, j, kA, cA, swA);
-                if (j + 2 < m) issue(buf, j + 2, kA, cA, swA);
-                consume(buf, j + 1, kB, cB, swB);
+                issue(buf, j + 1, kB);
+                consume(buf, j, kA);
+                if (pending) fold();
+                if (j + 2 < m) issue(buf, j + 2, kA);
+                consume(buf, j + 1, kB);
+                if (pending) fold();
             }
-            if (j < m) consume(buf, j, kA, cA, swA);
+            if (j < m) consume(buf, j, kA);
             __syncthreads();  // every warp is done with buf before it is refilled
         }
 #pragma unroll
@@ -263,6 +279,7 @@ __global__ void __launch_bounds__(256) grid_atomic_kernel(const GridArgs A) {
 // partial sums are combined with four shuffle steps.
 //   vis_out[index] = sum_{i,j} conj(table[slice][i,j]) * grid[y0 + i, x0 + j]
 // Records are in tile order, so the warps of a block read the same few KB of the grid (L1/L2 hits).
+template <int UNROLL>
 __global__ void __launch_bounds__(256) degrid_warp_kernel(const GridArgs A) {
     const int hl = threadIdx.x & 15;
     const i64 hw0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
@@ -288,7 +305,7 @@ __global__ void __launch_bounds__(256) degrid_warp_kernel(const GridArgs A) {
                 if ((unsigned)gx >= (unsigned)A.width) continue;
                 const double2 *kp = A.table + (uint32_t)(kslice + (uint32_t)(i0 * A.gw + j));
                 const double2 *gp = A.grid + (size_t)(gy0 + i0) * A.width + gx;
-#pragma unroll 5
+#pragma unroll UNROLL
                 for (int i = i0; i < i1; ++i) {
                     const double2 k = ldg2(kp);
                     const double2 g = ldg2(gp);
@@ -308,6 +325,64 @@ __global__ void __launch_bounds__(256) degrid_warp_kernel(const GridArgs A) {
     }
 }
 
+// Degridder, small supports (gh*gw <= 32*M, M <= 8): one warp per visibility, lane l owns taps l, l+32, ...
+// of the slice, so the M tap loads of a warp are one contiguous, fully coalesced stream; the matching grid
+// cells are M loads at per-lane offsets that do not depend on the visibility and are computed once.  All 2M
+// loads of a visibility are issued before the first FMA (memory-level parallelism instead of occupancy).
+template <int M>
+__global__ void __launch_bounds__(256) degrid_lin_kernel(const GridArgs A) {
+    const int lane = threadIdx.x & 31;
+    const i64 warp0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
+    const i64 count = (i64)A.counters[2];
+    int ti[M], tj[M], goff[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+        const int t = lane + 32 * m;
+        ti[m] = t < A.s2 ? t / A.gw : -1;
+        tj[m] = t < A.s2 ? t - ti[m] * A.gw : 0;
+        goff[m] = ti[m] * A.width + tj[m];
+    }
+    for (i64 r = warp0; r < count; r += nwarps) {
+        const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(A.rec + r) + 1);
+        const int lx = (int)(meta.y & 255u), ly = (int)((meta.y >> 8) & 255u);
+        const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
+        const int tyi = (int)(meta.w / (uint32_t)A.ntx), txi = (int)(meta.w % (uint32_t)A.ntx);
+        const int gx0 = txi * TILE + lx - (A.gw - 1), gy0 = tyi * TILE + ly - (A.gh - 1);
+        const double2 *kp = A.table + (uint32_t)(meta.x + dy * (uint32_t)A.gw + dx) + lane;
+        const double2 *gp = A.grid + ((i64)gy0 * A.width + gx0);
+        const bool interior = gx0 >= 0 && gy0 >= 0 && gx0 + A.gw <= A.width && gy0 + A.gh <= A.nrows;  // warp-uniform
+        double2 k[M], g[M];
+        if (interior) {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                k[m] = make_double2(0.0, 0.0); g[m] = make_double2(0.0, 0.0);
+                if (ti[m] >= 0) { k[m] = ldg2(kp + 32 * m); g[m] = ldg2(gp + goff[m]); }
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                k[m] = make_double2(0.0, 0.0); g[m] = make_double2(0.0, 0.0);
+                if (ti[m] >= 0 && (unsigned)(gx0 + tj[m]) < (unsigned)A.width && (unsigned)(gy0 + ti[m]) < (unsigned)A.nrows) {
+                    k[m] = ldg2(kp + 32 * m); g[m] = ldg2(gp + goff[m]);
+                }
+            }
+        }
+        double ar = 0.0, ai = 0.0;
+#pragma unroll
+        for (int m = 0; m < M; ++m) {  // conj(k) * g
+            ar = fma(k[m].x, g[m].x, ar); ar = fma(k[m].y, g[m].y, ar);
+            ai = fma(k[m].x, g[m].y, ai); ai = fma(-k[m].y, g[m].x, ai);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ar += __shfl_xor_sync(0xffffffffu, ar, o);
+            ai += __shfl_xor_sync(0xffffffffu, ai, o);
+        }
+        if (lane == 0) A.vis_out[meta.z] = make_double2(ar, ai);
+    }
+}
+
 static GridArgs make_args(skagrid_plan *plan, const double *table, double *grid) {
     const Geom &g = plan->g;
     GridArgs A;
@@ -323,18 +398,18 @@ static GridArgs make_args(skagrid_plan *plan, const double *table, double *grid)
     return A;
 }
 
-template <int R>
+template <int R, int MT>
 static int launch_tiled(skagrid_ctx *ctx, const GridArgs &A, cudaStream_t st) {
     const size_t smem = (size_t)A.SG * A.SG * sizeof(double2);
     static bool configured = false;
     if (!configured) {
-        SK_CUDA(ctx, cudaFuncSetAttribute(grid_tiled_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SK_CUDA(ctx, cudaFuncSetAttribute(grid_tiled_kernel<R, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     int per_sm = 0;
-    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_tiled_kernel<R>, GRID_THREADS, smem));
+    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_tiled_kernel<R, MT>, GRID_THREADS, smem));
     if (per_sm < 1) return sk_fail(ctx, SKAGRID_ECUDA, "tiled gridder does not fit on an SM (smem %zu)", smem);
-    grid_tiled_kernel<R><<<ctx->sm_count * per_sm, GRID_THREADS, smem, st>>>(A);
+    grid_tiled_kernel<R, MT><<<ctx->sm_count * per_sm, GRID_THREADS, smem, st>>>(A);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
@@ -353,9 +428,10 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
         return SKAGRID_OK;
     }
     SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 1, 0, sizeof(uint32_t), st));
-    if (R == 16) return launch_tiled<16>(ctx, A, st);
-    if (R == 32) return launch_tiled<32>(ctx, A, st);
-    return launch_tiled<64>(ctx, A, st);
+    const int MT = plan->g.MT;
+    if (R == 16) return MT == 2 ? launch_tiled<16, 2>(ctx, A, st) : launch_tiled<16, 4>(ctx, A, st);
+    if (R == 32) return MT == 2 ? launch_tiled<32, 2>(ctx, A, st) : launch_tiled<32, 4>(ctx, A, st);
+    return MT == 2 ? launch_tiled<64, 2>(ctx, A, st) : launch_tiled<64, 4>(ctx, A, st);
 }
 
 extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, const double *grid, double *vis_out,
@@ -368,7 +444,13 @@ extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const do
     SK_CUDA(ctx, cudaMemsetAsync(vis_out, 0, (size_t)plan->count * sizeof(double2), st));
     GridArgs A = make_args(plan, table, const_cast<double *>(grid));
     A.vis_out = reinterpret_cast<double2 *>(vis_out);
-    degrid_warp_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(A);
+    static const int variant = getenv("SKAGRID_DEGRID_VARIANT") ? atoi(getenv("SKAGRID_DEGRID_VARIANT")) : 0;  // tuning experiments
+    const int taps = A.s2;
+    if (variant == 2 && taps <= 256) degrid_lin_kernel<8><<<ctx->sm_count * 8, 256, 0, st>>>(A);
+    else if (variant == 1) degrid_warp_kernel<16><<<ctx->sm_count * 8, 256, 0, st>>>(A);
+    else if (variant == 3) degrid_warp_kernel<15><<<ctx->sm_count * 16, 256, 0, st>>>(A);
+    else if (variant == 4) degrid_warp_kernel<5><<<ctx->sm_count * 8, 256, 0, st>>>(A);
+    else degrid_warp_kernel<15><<<ctx->sm_count * 8, 256, 0, st>>>(A);  // measured on B200 (S=15): unroll 15 -> 2.9e9 vis/s, 5 -> 2.1e9
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
