@@ -219,6 +219,9 @@ int skagrid_dev_synth_vis(skagrid_ctx *ctx, uint64_t seed, int64_t first, int64_
                           int64_t support, int64_t nw, int uniform, double *u, double *v,
                           int64_t *wbin, double *vis, void *stream);
 
+/* frac_coord (src/Gridding.hs:126-140) on device arrays. */
+int skagrid_dev_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, int64_t count, const double *d_p,
+                           int64_t *d_fl, int64_t *d_frac, int flags, void *stream);
 /* w_kernel table built directly into device memory (w values on the host). */
 int skagrid_dev_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *w_host, int64_t npixff,
                           int64_t npixkern, int64_t qpx, int conjugate, double *d_out, void *stream);

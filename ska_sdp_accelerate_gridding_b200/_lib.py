@@ -62,6 +62,7 @@ _SIGS = {
     "skagrid_dev_grid_to_image": [vp, i64, vp, vp, vp, vp],
     "skagrid_dev_synth_vis": [vp, C.c_uint64, i64, i64, i64, i64, i64, ip, vp, vp, vp, vp, vp],
     "skagrid_dev_w_kernels": [vp, dbl, i64, vp, i64, i64, i64, ip, vp, vp],
+    "skagrid_dev_frac_coord": [vp, i64, i64, i64, vp, vp, vp, ip, vp],
 }
 _RESTYPES = {
     "skagrid_destroy": None,

@@ -613,3 +613,14 @@ extern "C" int skagrid_dev_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw,
     NEED(ctx, nw > 0 && w_host && d_out, "dev_w_kernels: NULL pointer or nw <= 0");
     return sk_w_kernels_dev(ctx, theta, nw, w_host, npixff, npixkern, qpx, conjugate, d_out, sk_stream(ctx, stream));
 }
+
+// Device-resident binning (used by the uv-tile-sharded router: the owner of a visibility is an integer function
+// of its bit-exact y cell).
+extern "C" int skagrid_dev_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, int64_t count, const double *d_p, int64_t *d_fl,
+                                      int64_t *d_frac, int flags, void *stream) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, n > 0 && qpx > 0 && count >= 0, "dev_frac_coord: n, qpx must be positive");
+    if (count == 0) return SKAGRID_OK;
+    NEED(ctx, d_p && d_fl && d_frac, "dev_frac_coord: NULL pointer");
+    return sk_frac_coord_dev(ctx, n, qpx, count, d_p, (i64 *)d_fl, (i64 *)d_frac, flags & SKAGRID_FRAC_NORMALISE, sk_stream(ctx, stream));
+}

@@ -43,6 +43,16 @@ def synth_vis(seed, first, count, n, support, nw, uniform=False, with_vis=True, 
     return u, v, wbin, vis
 
 
+def frac_coord(n, qpx, p, normalise=True, ctx=None):
+    """Bit-exact frac_coord (src/Gridding.hs:126-140) of a CUDA float64 tensor -> (fl, frac) int64 CUDA tensors."""
+    ctx = ctx or context_for_current_device()
+    _chk(p, torch.float64, "p")
+    fl = torch.empty(p.shape, dtype=torch.int64, device=p.device)
+    fr = torch.empty(p.shape, dtype=torch.int64, device=p.device)
+    ctx.check(ctx.lib.skagrid_dev_frac_coord(ctx.h, n, qpx, p.numel(), _p(p), _p(fl), _p(fr), int(normalise), _stream()))
+    return fl, fr
+
+
 def w_kernel_table(theta, ws, npixff, npixkern, qpx, conjugate=True, ctx=None):
     """w_kernel (src/Gridding.hs:610-728) for every w in `ws`, built in device memory -> [nw,qpx,qpx,s,s]."""
     ctx = ctx or context_for_current_device()

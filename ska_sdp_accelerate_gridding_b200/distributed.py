@@ -1,0 +1,149 @@
+"""Multi-GPU partitioning of the gridding hot path: one process per GPU, torch.distributed (NCCL over
+NVLink 5 / NVSwitch on the B200 box; gloo in the CPU tests of the host logic).
+
+Two modes, both from BASELINE.json:
+  * visibility-sharded (config 4): every rank grids a contiguous slice of the visibilities into a full local
+    grid; the grids are summed with one NCCL (all-)reduce.  Gridding is linear in the visibilities
+    (`permute (+)`, src/Gridding.hs:377), so the result differs from the 1-GPU grid only by summation order.
+    Degridding replicates the grid and shards the visibilities: no collective afterwards.
+  * uv-tile-sharded (config 5): rank g owns grid rows [bounds[g], bounds[g+1]); every visibility is routed
+    (all-to-all) to each owner its footprint rows intersect (at most two when a slab is taller than the
+    kernel) and each owner clips taps to its slab -- the same rule as fixoutofbounds (src/Gridding.hs:883-891).
+    No grid reduction.
+
+The routing/partition logic here is integer-only and backend-agnostic (it runs on CPU tensors under gloo in
+tests/test_distributed.py); the gridding itself is done by `device.Plan` on CUDA tensors.
+"""
+from __future__ import annotations
+
+from typing import Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(count: int, rank: int, world: int):
+    """Contiguous, balanced slice [first, first+n) of `count` items for `rank` (first ranks get the remainder)."""
+    base, rem = divmod(int(count), int(world))
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def slab_bounds(height: int, world: int, align: int = 32):
+    """Row slabs of the uv-tile-sharded mode: world+1 increasing bounds, interior ones aligned to the uv tile."""
+    bounds = [0]
+    for g in range(1, world):
+        b = (height * g // world) // align * align
+        bounds.append(max(b, bounds[-1]))
+    bounds.append(height)
+    return bounds
+
+
+def owners_of_rows(y0: torch.Tensor, gh: int, bounds: Sequence[int]):
+    """For footprints covering rows [y0, y0+gh): first and last owning rank (clamped to the grid).  Integer only.
+    Returns (lo, hi, on_grid)."""
+    b = torch.as_tensor(list(bounds[1:-1]), dtype=torch.int64, device=y0.device)
+    height = bounds[-1]
+    first = torch.clamp(y0, 0, height - 1)
+    last = torch.clamp(y0 + gh - 1, 0, height - 1)
+    on_grid = (y0 + gh > 0) & (y0 < height)
+    lo = torch.bucketize(first, b, right=True)
+    hi = torch.bucketize(last, b, right=True)
+    return lo, hi, on_grid
+
+
+def route_by_rows(y0: torch.Tensor, gh: int, bounds: Sequence[int], payload: Sequence[torch.Tensor], group=None):
+    """All-to-all of per-visibility payload tensors (each [count, ...]) to the ranks owning their footprint rows.
+    Returns the received payload tensors (concatenated over source ranks, in source-rank order) and the
+    per-source receive counts."""
+    world = dist.get_world_size(group)
+    lo, hi, on_grid = owners_of_rows(y0, gh, bounds)
+    send_idx = []
+    for g in range(world):
+        sel = on_grid & (lo <= g) & (hi >= g)
+        send_idx.append(torch.nonzero(sel, as_tuple=False).reshape(-1))
+    send_counts = torch.tensor([int(i.numel()) for i in send_idx], dtype=torch.int64, device=y0.device)
+    recv_counts = torch.empty_like(send_counts)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    order = torch.cat(send_idx)
+    in_splits = [int(x) for x in send_counts.tolist()]
+    out_splits = [int(x) for x in recv_counts.tolist()]
+    received = []
+    for t in payload:
+        src = t.index_select(0, order).contiguous()
+        as_real = torch.view_as_real(src) if src.is_complex() else src
+        out = torch.empty((sum(out_splits),) + tuple(as_real.shape[1:]), dtype=as_real.dtype, device=as_real.device)
+        dist.all_to_all_single(out, as_real, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+        received.append(torch.view_as_complex(out) if src.is_complex() else out)
+    return received, out_splits
+
+
+def allreduce_grid(grid: torch.Tensor, group=None, dst: int | None = None):
+    """Sum the per-rank grids in place (complex128 viewed as 2 x float64).  dst=None: all-reduce, else reduce to dst."""
+    real = torch.view_as_real(grid) if grid.is_complex() else grid
+    if dst is None:
+        dist.all_reduce(real, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.reduce(real, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return grid
+
+
+class VisShardedGridder:
+    """Visibility-sharded gridding / degridding on CUDA tensors (config 4)."""
+
+    def __init__(self, height, width, table, group=None):
+        self.h, self.w, self.table, self.group = height, width, table, group
+        self.plan = None
+
+    def _plan(self, u, v, wbin, vis):
+        from . import device as dv
+        if self.plan is None or self.plan.count < u.numel():
+            self.plan = dv.Plan(self.h, self.w, self.table.shape, u, v, wbin, vis)
+        else:
+            self.plan.update(u, v, wbin, vis)
+        return self.plan
+
+    def grid(self, u, v, wbin, vis, out=None, dst=None):
+        """Grids this rank's visibilities and sums over ranks.  Returns the full grid (on every rank, or on dst)."""
+        if out is None:
+            out = torch.zeros((self.h, self.w), dtype=torch.complex128, device=u.device)
+        self._plan(u, v, wbin, vis).grid(self.table, out)
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            allreduce_grid(out, self.group, dst)
+        return out
+
+    def degrid(self, grid, u, v, wbin):
+        """Every rank holds the full (model) grid; each degrids its own visibilities."""
+        return self._plan(u, v, wbin, None).degrid(self.table, grid)
+
+
+class TileShardedGridder:
+    """uv-tile-sharded gridding on CUDA tensors (config 5): this rank owns rows [bounds[rank], bounds[rank+1])."""
+
+    def __init__(self, height, width, table, group=None):
+        self.h, self.w, self.table, self.group = height, width, table, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bounds = slab_bounds(height, self.world)
+        self.rows = (self.bounds[self.rank], self.bounds[self.rank + 1])
+
+    def route(self, u, v, wbin, vis):
+        from . import device as dv
+        gh = self.table.shape[-2]
+        qpx = self.table.shape[-3]
+        y, _ = dv.frac_coord(self.h, qpx, v)
+        if self.world == 1:
+            return (u, v, wbin, vis), [u.numel()]
+        return route_by_rows(y - gh // 2, gh, self.bounds, (u, v, wbin, vis), self.group)
+
+    def grid(self, u, v, wbin, vis, out=None):
+        """Routes, then grids into this rank's slab [rows, width] (no reduction)."""
+        from . import device as dv
+        (ru, rv, rwb, rvis), _ = self.route(u, v, wbin, vis)
+        if out is None:
+            out = torch.zeros((self.rows[1] - self.rows[0], self.w), dtype=torch.complex128, device=u.device)
+        if ru.numel() > 0:
+            plan = dv.Plan(self.h, self.w, self.table.shape, ru, rv, rwb, rvis, rows=self.rows)
+            plan.grid(self.table, out)
+            plan.close()
+        return out

@@ -1,0 +1,111 @@
+"""Host-side logic of the two multi-GPU modes on CPU: world_size-2 gloo process groups.  The gridding inside
+each rank is done by the CPU oracle here (the CUDA path needs a GPU); what is tested is the partitioning,
+the owner computation, the all-to-all routing and the reduction."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ska_sdp_accelerate_gridding_b200 import distributed as D
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _problem():
+    rng = np.random.default_rng(77)
+    n, s, q, nw, cnt = 160, 15, 4, 2, 3000
+    gcf = rng.standard_normal((nw, q, q, s, s)) + 1j * rng.standard_normal((nw, q, q, s, s))
+    u, v = rng.uniform(-0.55, 0.55, cnt), rng.uniform(-0.55, 0.55, cnt)
+    wb = rng.integers(0, nw, cnt)
+    vis = rng.standard_normal(cnt) + 1j * rng.standard_normal(cnt)
+    return n, s, q, gcf, u, v, wb, vis
+
+
+def _worker(rank, world, port, mode, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as orc
+        n, s, q, gcf, u, v, wb, vis = _problem()
+        full = orc.convgrid(gcf, np.zeros((n, n), complex), u, v, vis, wbin=wb)
+        first, cnt = D.shard_range(len(u), rank, world)
+        sl = slice(first, first + cnt)
+        if mode == "vis":
+            local = orc.convgrid(gcf, np.zeros((n, n), complex), u[sl], v[sl], vis[sl], wbin=wb[sl])
+            g = torch.from_numpy(local)
+            D.allreduce_grid(g)
+            err = np.abs(g.numpy() - full).max() / np.abs(full).max()
+            ret[rank] = ("ok", float(err), cnt)
+        else:
+            bounds = D.slab_bounds(n, world)
+            y, _ = orc.frac_coord(n, q, v[sl])
+            y0 = torch.from_numpy(y - s // 2)
+            payload = (torch.from_numpy(u[sl].copy()), torch.from_numpy(v[sl].copy()), torch.from_numpy(wb[sl].copy()),
+                       torch.from_numpy(vis[sl].copy()))
+            (ru, rv, rwb, rvis), splits = D.route_by_rows(y0, s, bounds, payload)
+            r0, r1 = bounds[rank], bounds[rank + 1]
+            # every received footprint intersects the owned slab, and nothing that does was left behind
+            ry, _ = orc.frac_coord(n, q, rv.numpy())
+            assert ((ry - s // 2 + s > r0) & (ry - s // 2 < r1)).all()
+            ay, _ = orc.frac_coord(n, q, v)
+            expected = int(((ay - s // 2 + s > r0) & (ay - s // 2 < r1)).sum())
+            assert ru.numel() == expected, (ru.numel(), expected)
+            # grid the routed visibilities, clip to the slab, compare with the same rows of the full grid
+            g = orc.convgrid(gcf, np.zeros((n, n), complex), ru.numpy(), rv.numpy(), rvis.numpy(), wbin=rwb.numpy())
+            err = np.abs(g[r0:r1] - full[r0:r1]).max() / np.abs(full).max()
+            ret[rank] = ("ok", float(err), int(ru.numel()))
+    except Exception as e:  # pragma: no cover
+        ret[rank] = ("fail", repr(e), 0)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode", ["vis", "tile"])
+def test_two_rank_gloo(mode):
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, mode, ret), nprocs=world, join=True)
+    assert len(ret) == world
+    for r in range(world):
+        status, err, cnt = ret[r]
+        assert status == "ok", err
+        assert err < 1e-12
+    if mode == "vis":
+        assert sum(ret[r][2] for r in range(world)) == 3000
+    else:
+        assert sum(ret[r][2] for r in range(world)) >= 2600  # some footprints straddle the slab boundary, some fall off the grid
+
+
+def test_shard_range_and_bounds():
+    for count in (0, 1, 7, 100, 12345):
+        for world in (1, 2, 3, 8):
+            spans = [D.shard_range(count, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and sum(n for _, n in spans) == count
+            for (f0, n0), (f1, _) in zip(spans, spans[1:]):
+                assert f0 + n0 == f1
+            assert max(n for _, n in spans) - min(n for _, n in spans) <= 1
+    b = D.slab_bounds(32768, 8)
+    assert b[0] == 0 and b[-1] == 32768 and all(x % 32 == 0 for x in b) and all(b[i] < b[i + 1] for i in range(8))
+    assert D.slab_bounds(100, 3) == [0, 32, 64, 100]
+
+
+def test_owners_of_rows():
+    bounds = [0, 32, 64, 100]
+    y0 = torch.tensor([-20, -15, -14, 0, 17, 18, 31, 50, 63, 85, 99, 100, 120])
+    lo, hi, on = D.owners_of_rows(y0, 15, bounds)
+    assert on.tolist() == [False, False, True, True, True, True, True, True, True, True, True, False, False]
+    assert lo.tolist()[2:11] == [0, 0, 0, 0, 0, 1, 1, 2, 2]
+    assert hi.tolist()[2:11] == [0, 0, 0, 1, 1, 2, 2, 2, 2]

@@ -352,3 +352,36 @@ def test_full_size_linearity_and_adjoint(G):
     lhs = (g2.conj() * g0).sum().item()
     rhs = (d.conj() * vis).sum().item()
     assert abs(lhs - rhs) <= 1e-9 * abs(lhs)
+
+
+# ------------------------------------------------------------------------------------------------ sharding modes
+def test_tile_sharded_single_rank_and_device_frac_coord(orc):
+    import torch
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    from ska_sdp_accelerate_gridding_b200 import distributed as D
+    rng = np.random.default_rng(41)
+    n, s, q, nw, cnt = 256, 15, 8, 2, 10000
+    gcf = _rand_c(rng, (nw, q, q, s, s))
+    u, v = rng.uniform(-0.5, 0.5, cnt), rng.uniform(-0.5, 0.5, cnt)
+    wb = rng.integers(0, nw, cnt)
+    vis = _rand_c(rng, cnt)
+    fl, fr = dv.frac_coord(n, q, _t(v))
+    ofl, ofr = orc.frac_coord(n, q, v)
+    assert np.array_equal(fl.cpu().numpy(), ofl) and np.array_equal(fr.cpu().numpy(), ofr)
+    ts = D.TileShardedGridder(n, n, _t(gcf))
+    g = ts.grid(_t(u), _t(v), _t(wb), _t(vis)).cpu().numpy()
+    assert rel_err(g, orc.convgrid(gcf, np.zeros((n, n), complex), u, v, vis, wbin=wb)) < TOL
+    vs = D.VisShardedGridder(n, n, _t(gcf))
+    assert rel_err(vs.grid(_t(u), _t(v), _t(wb), _t(vis)).cpu().numpy(), g) < TOL
+
+
+def test_two_gpu_torchrun_if_available():
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29511", os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
