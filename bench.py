@@ -240,11 +240,13 @@ def main():
     alg_bytes = BYTES_PER_VIS * V + 16 * N_GRID * N_GRID + table.numel() * 16
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "grid_tiled_kernel<16>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "bound": "hbm", "kernel": "grid_tiled_kernel<16,2>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
-        "note": "compulsory-byte accounting (64 B/vis + 16 N^2 + table); the tiled gridder is bound on-chip (L2->SM kernel taps, FP64), see DESIGN.md",
+        "note": "compulsory-byte accounting (64 B/vis + 16 N^2 + table); the tiled gridder is bound by L2->SM kernel-tap traffic (3.7 KB/vis), see DESIGN.md 4.2 and the l2_taps entry",
         "fp64": {"achieved_tflops": FLOP_PER_VIS * V / (kern_ms * 1e-3) / 1e12, "peak_tflops_measured": fp64_peak,
                  "frac": FLOP_PER_VIS * V / (kern_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None},
+        "l2_taps": {"achieved_tbs": 16.0 * SUPPORT * SUPPORT * V / (kern_ms * 1e-3) / 1e12, "practical_peak_tbs": 6300 * 1.965e9 / 1e12,
+                    "frac": 16.0 * SUPPORT * SUPPORT * V / (kern_ms * 1e-3) / (6300 * 1.965e9), "note": "kernel taps streamed L2->SM (16 B x S^2 per visibility) vs the ~6.3 KB/clk LTS cap of B300_MICROARCH.md at 1965 MHz"},
         "hbm_update_equiv": {"achieved": UPD_BYTES_PER_VIS * V / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak,
                              "frac": UPD_BYTES_PER_VIS * V / (kern_ms * 1e-3) / 1e9 / hbm_peak},
     }

@@ -42,6 +42,11 @@ def convertAndSort(names):
     return [vals[i] for i in order], [names[i] for i in order]
 
 
+def _fmt(x):
+    """Haskell `printf "%f"` on a Double prints the shortest digits that round-trip (0.008 -> "0.008")."""
+    return np.format_float_positional(float(x), trim="-")
+
+
 def _members(store, prefix):
     pre = prefix.rstrip("/") + "/"
     out = []
@@ -55,7 +60,7 @@ def _members(store, prefix):
 
 def getWKernels(store, theta):
     """src/ImageDataset.hs:136-148: stack /wkern/<theta>/<w>/kern in numeric w order -> (wkernels, wbins)."""
-    base = "/wkern/%s" % (("%f" % theta).rstrip("0"))
+    base = "/wkern/%s" % _fmt(theta)
     ws, names = convertAndSort(_members(store, base))
     kerns = np.stack([c128(store["%s/%s/kern" % (base, n)]) for n in names])
     return kerns, np.array(ws, np.float64)
@@ -63,7 +68,7 @@ def getWKernels(store, theta):
 
 def getAKernels(store, theta, t0, f0):
     """src/ImageDataset.hs:108-133: per antenna (numeric order) the kernel of the closest time and frequency."""
-    base = "/akern/%s" % (("%f" % theta).rstrip("0"))
+    base = "/akern/%s" % _fmt(theta)
     _, ants = convertAndSort(_members(store, base))
     ts, tnames = convertAndSort(_members(store, "%s/%s" % (base, ants[0])))
     tname = tnames[findClosestList(ts, t0)]
