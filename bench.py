@@ -36,6 +36,7 @@ UPD_BYTES_PER_VIS = 64 + 16 * SUPPORT * SUPPORT      # grid-update-equivalent ac
 
 
 def parse():
+    global N_GRID, SUPPORT, NW, FLOP_PER_VIS, UPD_BYTES_PER_VIS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -48,7 +49,16 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-vis", type=float, default=None, help="visibilities per e2e step (default: --vis)")
     ap.add_argument("--cpu-sample", type=float, default=4e6)
-    return ap.parse_args()
+    ap.add_argument("--grid", type=int, default=N_GRID, help="grid side (config 4: 8192; config 5: 32768)")
+    ap.add_argument("--support", type=int, default=SUPPORT, help="kernel support (config 4: 15; config 5: 31)")
+    ap.add_argument("--nw", type=int, default=NW, help="w-planes in the kernel table")
+    ap.add_argument("--mode", default="vis", choices=["vis", "tile"],
+                    help="vis: visibility-sharded + all-reduce (config 4, the headline); tile: uv-tile-sharded + routing (config 5, gridding only)")
+    args = ap.parse_args()
+    N_GRID, SUPPORT, NW = args.grid, args.support, args.nw
+    FLOP_PER_VIS = 8 * SUPPORT * SUPPORT
+    UPD_BYTES_PER_VIS = 64 + 16 * SUPPORT * SUPPORT
+    return args
 
 
 class ClockSampler:
@@ -144,6 +154,67 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------------ GPU arm
+def run_tile_mode(args, rank, world, dev, ctx, table, u, v, wb, vis):
+    """Config 5 shape: uv-tile-sharded gridding.  step = owner computation + all-to-all routing + bin/bucket +
+    tiled gridder into the owned row slab; no grid reduction.  value = visibilities gridded per second."""
+    import torch
+    import torch.distributed as dist
+    from ska_sdp_accelerate_gridding_b200 import distributed as D
+    V = int(args.vis)
+    ts = D.TileShardedGridder(N_GRID, N_GRID, table)
+    slab = torch.zeros((ts.rows[1] - ts.rows[0], N_GRID), dtype=torch.complex128, device=dev)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    kept = [0]
+
+    def step():
+        (ru, rv, rwb, rvis), _ = ts.route(u, v, wb, vis)
+        slab.zero_()
+        kept[0] = int(ru.numel())
+        if ru.numel():
+            from ska_sdp_accelerate_gridding_b200 import device as dv
+            plan = dv.Plan(N_GRID, N_GRID, table.shape, ru, rv, rwb, rvis, rows=ts.rows)
+            plan.grid(table, slab)
+            plan.close()
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    l0 = ctx.launch_count
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(args.steps):
+        step()
+    t1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = t0.elapsed_time(t1)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        k = torch.tensor([kept[0]], dtype=torch.int64, device=dev)
+        dist.all_reduce(k)
+        kept[0] = int(k.item())
+    ms_per_step = ms / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": "visibilities/sec gridded (uv-tile-sharded)", "value": world * V / (ms_per_step * 1e-3), "unit": "vis/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"config 5 shape: {N_GRID}^2 c128 grid, support {SUPPORT}, oversampling {QPX}, {NW} w-planes, uv-tile-sharded "
+                                   "(row slabs, all-to-all routing, no grid reduce)", "vis_per_gpu_per_step": V, "routed_records": kept[0],
+                       "step": "owners (bit-exact y cell) -> all-to-all -> bin+bucket -> tiled gridder into the owned slab"},
+            "gpu_launches": int(ctx.launch_count - l0), "clocks": clocks, "e2e": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -168,6 +239,9 @@ def main():
 
     table = dv.w_kernel_table(THETA, np.linspace(-WMAX, WMAX, NW), NPIXFF, SUPPORT, QPX)
     u, v, wb, vis = dv.synth_vis(SEED, rank * V, V, N_GRID, SUPPORT, NW, uniform=args.uniform)
+    if args.mode == "tile":
+        run_tile_mode(args, rank, world, dev, ctx, table, u, v, wb, vis)
+        return
     grid = torch.zeros((N_GRID, N_GRID), dtype=torch.complex128, device=dev)
     vis_out = torch.empty(V, dtype=torch.complex128, device=dev)
     plan = dv.Plan(N_GRID, N_GRID, table.shape, u, v, wb, vis)
@@ -286,9 +360,14 @@ def main():
         del u, v, wb, vis, vis_out, grid
         torch.cuda.empty_cache()
 
+        # conv_imaging2 takes uvw in wavelengths and divides by lam itself (src/Gridding.hs:115-124): theta*lam = N_GRID
+        E2E_THETA, E2E_LAM = 0.01, N_GRID * 100
+        hu_wl, hv_wl = (hu * float(E2E_LAM)).pin_memory(), (hv * float(E2E_LAM)).pin_memory()
+        nu_wl, nv_wl = hu_wl.numpy(), hv_wl.numpy()
+
         def e2e_step():
-            ngrid.fill(0)
-            ctx.check(lib.skagrid_convgrid2(h, NW, QPX, SUPPORT, SUPPORT, p(ntab), N_GRID, N_GRID, p(ngrid), Ve, p(nu), p(nv), p(nwb), p(nvis)))
+            ctx.check(lib.skagrid_conv_imaging2(h, NW, QPX, SUPPORT, SUPPORT, p(ntab), E2E_THETA, E2E_LAM, Ve, p(nu_wl), p(nv_wl), p(nu_wl),
+                                                p(nwb), p(nvis), p(ngrid)))
             ctx.check(lib.skagrid_grid_to_image(h, N_GRID, p(ngrid), None, p(hmax)))
             ctx.check(lib.skagrid_convdegrid2(h, NW, QPX, SUPPORT, SUPPORT, p(ntab), N_GRID, N_GRID, p(ngrid), Ve, p(nu), p(nv), p(nwb), p(nout)))
 
@@ -308,8 +387,8 @@ def main():
             te = float(t.item())
         grid_b = N_GRID * N_GRID * 16
         out["e2e"] = {"value": world * Ve / te, "unit": "vis/s", "ms_per_step": te * 1e3, "vis_per_gpu_per_step": Ve,
-                      "h2d_bytes_per_step": int(Ve * 64 + Ve * 48 + 3 * grid_b + 2 * ntab.nbytes), "d2h_bytes_per_step": int(Ve * 16 + grid_b + 8),
-                      "api": "skagrid_convgrid2 + skagrid_grid_to_image + skagrid_convdegrid2 (host pointers, pinned)"}
+                      "h2d_bytes_per_step": int(Ve * 40 + Ve * 24 + 2 * grid_b + 2 * ntab.nbytes), "d2h_bytes_per_step": int(Ve * 16 + grid_b + 8),
+                      "api": "skagrid_conv_imaging2 (vis -> grid) + skagrid_grid_to_image (grid -> max) + skagrid_convdegrid2 (grid -> vis), host pointers, pinned"}
     else:
         out["e2e"] = None
 

@@ -155,6 +155,11 @@ int skagrid_simple_imaging(skagrid_ctx *ctx, double theta, int64_t lam, int64_t 
 int skagrid_conv_imaging(skagrid_ctx *ctx, int64_t qpx, int64_t gh, int64_t gw, const double *gcf,
                          double theta, int64_t lam, int64_t count, const double *u, const double *v,
                          const double *w, const double *vis, double *grid_out);
+/* conv_imaging with a w-indexed table [nw,qpx,qpx,gh,gw] + wbin: the last step of w_cache_imaging
+ * (src/Gridding.hs:421-449: zero grid, p = uvw/lam, convgrid2). */
+int skagrid_conv_imaging2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw, const double *gcf,
+                          double theta, int64_t lam, int64_t count, const double *u, const double *v,
+                          const double *w, const int64_t *wbin, const double *vis, double *grid_out);
 int skagrid_aw_imaging(skagrid_ctx *ctx, double theta, int64_t lam, int64_t nw, int64_t qpx, int64_t s,
                        const double *wkerns, const double *wbins, int64_t nant, const double *akerns,
                        int64_t count, const double *u, const double *v, const double *w,

@@ -50,6 +50,7 @@ _SIGS = {
     "skagrid_grid_to_image": [vp, i64, vp, vp, vp],
     "skagrid_simple_imaging": [vp, dbl, i64, i64, vp, vp, vp, vp, vp],
     "skagrid_conv_imaging": [vp, i64, i64, i64, vp, dbl, i64, i64, vp, vp, vp, vp, vp],
+    "skagrid_conv_imaging2": [vp, i64, i64, i64, i64, vp, dbl, i64, i64, vp, vp, vp, vp, vp, vp],
     "skagrid_aw_imaging": [vp, dbl, i64, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp],
     "skagrid_aw_gridding": [vp, dbl, i64, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp],
     "skagrid_w_kernels": [vp, dbl, i64, vp, i64, i64, i64, ip, vp],

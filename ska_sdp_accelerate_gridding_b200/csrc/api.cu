@@ -52,6 +52,26 @@ static int check_flags(skagrid_ctx *ctx, const char *what) {
     return SKAGRID_OK;
 }
 
+// The host-pointer functions keep ONE plan alive in the context (cudaMalloc/cudaFree of its ~0.5 GB of buckets and
+// records per call would cost more than the gridding of a small batch); it is reused when the geometry matches.
+static int plan_acquire(skagrid_ctx *ctx, const skagrid_geom *geom, i64 capacity, int slice_override, skagrid_plan **out) {
+    skagrid_plan *p = ctx->cached_plan;
+    if (p) {
+        const Geom &g = p->g;
+        const bool same = g.height == geom->height && g.width == geom->width && g.row0 == geom->row0 && g.row1 == geom->row1 &&
+                          g.nw == geom->nw && g.qpx == geom->qpx && g.gh == geom->gh && g.gw == geom->gw &&
+                          p->slice_override == slice_override && p->capacity >= capacity;
+        if (same) { *out = p; return SKAGRID_OK; }
+        sk_plan_free(p);
+        ctx->cached_plan = nullptr;
+    }
+    SK_TRY(sk_plan_alloc(ctx, geom, capacity, slice_override, &p));
+    ctx->cached_plan = p;
+    *out = p;
+    return SKAGRID_OK;
+}
+static void plan_release(skagrid_ctx *, skagrid_plan *) {}  // stays cached; freed by skagrid_destroy
+
 #define NEED(ctx, cond, what) \
     do { if (!(cond)) return sk_fail((ctx), SKAGRID_EINVAL, "%s", (what)); } while (0)
 
@@ -159,11 +179,11 @@ extern "C" int skagrid_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int
 //   degrid == 0: d_grid[row0:row1] += sum vis_k * d_table[slice_k]      (vis is the input)
 //   degrid != 0: vis_out[k] = sum conj(d_table[slice_k]) * d_grid[...]  (vis_out is the output, host)
 static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double *d_table, double *d_grid, i64 count, const double *u,
-                        const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid) {
+                        const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam = 0.0) {
     if (count <= 0) return SKAGRID_OK;
     const i64 chunk = std::min<i64>(count, VIS_CHUNK);
     skagrid_plan *plan = nullptr;
-    SK_TRY(sk_plan_alloc(ctx, geom, chunk, 0, &plan));
+    SK_TRY(plan_acquire(ctx, geom, chunk, 0, &plan));
     double *du[2], *dv[2], *dvis[2];
     i64 *dwb[2] = {nullptr, nullptr};
     int rc = SKAGRID_OK;
@@ -174,7 +194,7 @@ static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double
         if (!rc && wbin) rc = sk_scratch(ctx, nwb, (size_t)chunk * 8, (void **)&dwb[b]);
         if (!rc) rc = sk_scratch(ctx, nvis, (size_t)chunk * 16, (void **)&dvis[b]);
     }
-    if (rc) { sk_plan_free(plan); return rc; }
+    if (rc) { plan_release(ctx, plan); return rc; }
     cudaError_t e = cudaSuccess;
     // the copy stream must not overwrite scratch that earlier work on the compute stream still uses
     e = cudaEventRecord(ctx->ev_done[0], ctx->stream);
@@ -191,6 +211,12 @@ static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0);
         if (e != cudaSuccess) break;
+        if (lam > 0.0) {  // div3 (src/Gridding.hs:838-839) on u and v; w does not enter the table gridders
+            void *dscr;
+            rc = sk_scratch(ctx, "st_wscr", (size_t)chunk * 8, &dscr);
+            if (!rc) { cudaMemsetAsync(dscr, 0, (size_t)n * 8, ctx->stream); rc = sk_scale3_dev(ctx, n, du[b], dv[b], (double *)dscr, lam, 1, ctx->stream); }
+            if (rc) break;
+        }
         rc = sk_plan_fill(ctx, plan, n, du[b], dv[b], wbin ? dwb[b] : nullptr, degrid ? nullptr : dvis[b], ctx->stream);
         if (!rc) {
             if (degrid) {
@@ -205,7 +231,7 @@ static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     else cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
-    sk_plan_free(plan);
+    plan_release(ctx, plan);
     if (rc) return rc;
     if (e != cudaSuccess) return sk_fail(ctx, SKAGRID_ECUDA, "table gridder: %s", cudaGetErrorString(e));
     return SKAGRID_OK;
@@ -288,7 +314,7 @@ static int aw_core_dev(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 s, const double *d
     const i64 chunk = std::min<i64>(count, AW_CHUNK);
     skagrid_geom geom = {height, width, 0, height, 1, qpx, s, s};  // slice_override: the table has one slice per visibility
     skagrid_plan *plan = nullptr;
-    SK_TRY(sk_plan_alloc(ctx, &geom, chunk, 1, &plan));
+    SK_TRY(plan_acquire(ctx, &geom, chunk, 1, &plan));
     void *dx, *dxf, *dy, *dyf, *dk;
     int rc = sk_scratch(ctx, "aw_x", (size_t)chunk * 8, &dx);
     if (!rc) rc = sk_scratch(ctx, "aw_xf", (size_t)chunk * 8, &dxf);
@@ -308,7 +334,7 @@ static int aw_core_dev(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 s, const double *d
         }
     }
     cudaStreamSynchronize(ctx->stream);
-    sk_plan_free(plan);
+    plan_release(ctx, plan);
     return rc;
 }
 
@@ -508,15 +534,39 @@ extern "C" int skagrid_conv_imaging(skagrid_ctx *ctx, int64_t qpx, int64_t gh, i
         SK_TRY(sk_scale3_dev(ctx, count, du, dv, (double *)dscr, (double)lam, 1, ctx->stream));
         skagrid_geom geom = {n, n, 0, n, 1, qpx, gh, gw};
         skagrid_plan *plan = nullptr;
-        SK_TRY(sk_plan_alloc(ctx, &geom, count, 0, &plan));
+        SK_TRY(plan_acquire(ctx, &geom, count, 0, &plan));
         int rc = sk_plan_fill(ctx, plan, count, du, dv, nullptr, (double *)dvis, ctx->stream);
         if (!rc) rc = skagrid_dev_grid(ctx, plan, (double *)dtab, (double *)dgrid, 0, ctx->stream);
         cudaStreamSynchronize(ctx->stream);
-        sk_plan_free(plan);
+        plan_release(ctx, plan);
         SK_TRY(rc);
     }
     SK_TRY(down(ctx, grid_out, dgrid, (size_t)(n * n) * 16));
     return t.finish();
+}
+
+// conv_imaging with a w-indexed table: the 5-D analogue of conv_imaging (src/Gridding.hs:115-124) and the last step of
+// w_cache_imaging (:421-449): zero grid of side round(theta*lam), p = uvw/lam, convgrid2.  Nothing but the
+// visibilities and the table goes up, only the grid comes back.
+extern "C" int skagrid_conv_imaging2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, double theta,
+                                     int64_t lam, int64_t count, const double *u, const double *v, const double *w, const int64_t *wbin,
+                                     const double *vis, double *grid_out) {
+    SK_TRY(enter(ctx));
+    const i64 n = grid_side(theta, lam);
+    SK_TRY(check_table_args(ctx, nw, qpx, gh, gw, n, n, count));
+    NEED(ctx, gcf && grid_out, "conv_imaging2: NULL kernel or grid");
+    if (count > 0) NEED(ctx, u && v && wbin && vis, "conv_imaging2: NULL visibility array");
+    (void)w;
+    Timer t(ctx);
+    void *dgrid, *dtab;
+    SK_TRY(up(ctx, "tab", gcf, (size_t)(nw * qpx * qpx * gh * gw) * 16, &dtab));
+    SK_TRY(sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid));
+    SK_CUDA(ctx, cudaMemsetAsync(dgrid, 0, (size_t)(n * n) * 16, ctx->stream));
+    skagrid_geom geom = {n, n, 0, n, nw, qpx, gh, gw};
+    SK_TRY(stream_table(ctx, &geom, (double *)dtab, (double *)dgrid, count, u, v, wbin, vis, nullptr, 0, (double)lam));
+    SK_TRY(down(ctx, grid_out, dgrid, (size_t)(n * n) * 16));
+    SK_TRY(t.finish());
+    return check_flags(ctx, "conv_imaging2");
 }
 
 // aw_imaging on device-resident inputs: p = uvw/lam (in place), wbin = findClosest wbins w (w in wavelengths,

@@ -90,6 +90,7 @@ struct skagrid_ctx {
     std::map<std::string, DevBuf> pool;   // named scratch buffers, grown on demand, freed at destroy
     std::map<i64, cufftHandle> fft_plans; // n -> Z2Z n x n plan
     std::map<i64, DevBuf> fft_work;
+    skagrid_plan *cached_plan = nullptr;  // plan kept between host-pointer calls (api.cu plan_acquire)
 };
 
 // ---------------------------------------------------------------------------------------------

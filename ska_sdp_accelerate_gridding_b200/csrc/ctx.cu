@@ -76,6 +76,7 @@ extern "C" void skagrid_destroy(skagrid_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->cached_plan) { sk_plan_free(ctx->cached_plan); ctx->cached_plan = nullptr; }
     for (auto &kv : ctx->fft_plans) cufftDestroy(kv.second);
     for (auto &kv : ctx->fft_work) if (kv.second.p) cudaFree(kv.second.p);
     for (auto &kv : ctx->pool) if (kv.second.p) cudaFree(kv.second.p);

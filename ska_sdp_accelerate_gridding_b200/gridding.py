@@ -329,6 +329,21 @@ def conv_imaging(kv, theta, lam, uvw, src, vis, ctx=None):
     return out
 
 
+def conv_imaging2(kv, theta, lam, uvw, wbin, vis, ctx=None):
+    """5-D analogue of conv_imaging (src/Gridding.hs:115-124) = the last step of w_cache_imaging (:421-449):
+    zero grid, p = uvw/lam, convgrid2 with the w-plane index per visibility."""
+    ctx = ctx or get_context()
+    kv = c128(kv)
+    u, v, w = _uvw(uvw)
+    vis, wbin = c128(vis), int64(wbin)
+    n = _grid_side(theta, lam)
+    nw, qpx, _, gh, gw = kv.shape
+    out = np.empty((n, n), np.complex128)
+    ctx.check(ctx.lib.skagrid_conv_imaging2(ctx.h, nw, qpx, gh, gw, ptr(kv), float(theta), int(lam), u.size, ptr(u), ptr(v), ptr(w), ptr(wbin),
+                                            ptr(vis), ptr(out)))
+    return out
+
+
 def _round_half_away(x):
     return np.sign(x) * np.floor(np.abs(x) + 0.5)
 
@@ -346,9 +361,7 @@ def w_cache_imaging(kernops: KernelOptions, otargs: OtherImagingArgs, theta, lam
     wbins = (rounded - wmin) // wstep
     ws = np.array([float(i * wstep + wmin) for i in range(steps)])
     kernels = w_kernel(theta, ws, kernops, conjugate=True, ctx=ctx)
-    n = _grid_side(theta, lam)
-    lamf = float(lam)
-    return convgrid2(kernels, np.zeros((n, n), np.complex128), (u / lamf, v / lamf), wbins, vis, ctx=ctx)
+    return conv_imaging2(kernels, theta, lam, (u, v, w), wbins, vis, ctx=ctx)
 
 
 def aw_imaging(kernops, otargs, theta, lam, wkernels, wbins, akernels, uvw, src, vis, ctx=None):
