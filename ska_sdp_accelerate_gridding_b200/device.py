@@ -78,6 +78,7 @@ class Plan:
         self.width = width
         _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(wbin, torch.int64, "wbin"); _chk(vis, torch.complex128, "vis")
         self.count = int(u.numel())
+        self.capacity = max(self.count, 1)
         h = C.c_void_p()
         self.ctx.check(self.ctx.lib.skagrid_dev_plan_create(self.ctx.h, C.byref(self.geom), self.count, _p(u), _p(v), _p(wbin), _p(vis),
                                                             int(slice_override), _stream(), C.byref(h)))

@@ -39,6 +39,24 @@ def slab_bounds(height: int, world: int, align: int = 32):
     return bounds
 
 
+def balanced_slab_bounds(row_hist: torch.Tensor, world: int):
+    """Row slabs holding (nearly) equal numbers of visibilities: bounds at the k/world quantiles of the per-row
+    histogram of footprint-centre rows (already summed over ranks).  SKA1-Low uv coverage is core-dominated and
+    mirrored to v >= 0, so equal-height slabs would leave half of the GPUs idle.  Integer only; every slab has at
+    least one row."""
+    height = int(row_hist.numel())
+    cum = torch.cumsum(row_hist.to(torch.int64), 0)
+    total = int(cum[-1].item())
+    bounds = [0]
+    for g in range(1, world):
+        target = (total * g) // world
+        b = int(torch.searchsorted(cum, torch.tensor([target], dtype=torch.int64, device=cum.device), right=True).item())
+        b = min(max(b, bounds[-1] + 1), height - (world - g))
+        bounds.append(b)
+    bounds.append(height)
+    return bounds
+
+
 def owners_of_rows(y0: torch.Tensor, gh: int, bounds: Sequence[int]):
     """For footprints covering rows [y0, y0+gh): first and last owning rank (clamped to the grid).  Integer only.
     Returns (lo, hi, on_grid)."""
@@ -124,8 +142,21 @@ class TileShardedGridder:
         self.h, self.w, self.table, self.group = height, width, table, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
-        self.bounds = slab_bounds(height, self.world)
+        self.set_bounds(slab_bounds(height, self.world))
+
+    def set_bounds(self, bounds):
+        self.bounds = [int(b) for b in bounds]
         self.rows = (self.bounds[self.rank], self.bounds[self.rank + 1])
+
+    def balance(self, v):
+        """Choose the slab bounds from this data set's uv coverage (collective): equal visibility counts per rank."""
+        from . import device as dv
+        y, _ = dv.frac_coord(self.h, self.table.shape[-3], v)
+        hist = torch.bincount(torch.clamp(y, 0, self.h - 1), minlength=self.h)
+        if self.world > 1:
+            dist.all_reduce(hist, group=self.group)
+        self.set_bounds(balanced_slab_bounds(hist, self.world))
+        return self.bounds
 
     def route(self, u, v, wbin, vis):
         from . import device as dv
@@ -140,10 +171,16 @@ class TileShardedGridder:
         """Routes, then grids into this rank's slab [rows, width] (no reduction)."""
         from . import device as dv
         (ru, rv, rwb, rvis), _ = self.route(u, v, wbin, vis)
+        self.last_routed = int(ru.numel())
         if out is None:
             out = torch.zeros((self.rows[1] - self.rows[0], self.w), dtype=torch.complex128, device=u.device)
         if ru.numel() > 0:
-            plan = dv.Plan(self.h, self.w, self.table.shape, ru, rv, rwb, rvis, rows=self.rows)
+            plan = getattr(self, "_plan", None)
+            if plan is None or plan.capacity < ru.numel() or plan.rows != self.rows:
+                if plan is not None:
+                    plan.close()
+                self._plan = plan = dv.Plan(self.h, self.w, self.table.shape, ru, rv, rwb, rvis, rows=self.rows)
+            else:
+                plan.update(ru, rv, rwb, rvis)
             plan.grid(self.table, out)
-            plan.close()
         return out

@@ -109,3 +109,17 @@ def test_owners_of_rows():
     assert on.tolist() == [False, False, True, True, True, True, True, True, True, True, True, False, False]
     assert lo.tolist()[2:11] == [0, 0, 0, 0, 0, 1, 1, 2, 2]
     assert hi.tolist()[2:11] == [0, 0, 0, 1, 1, 2, 2, 2, 2]
+
+
+def test_balanced_slab_bounds():
+    hist = torch.zeros(1000, dtype=torch.int64)
+    hist[500:520] = 100          # dense core
+    hist[520:1000] = 1
+    b = D.balanced_slab_bounds(hist, 4)
+    assert b[0] == 0 and b[-1] == 1000 and all(b[i] < b[i + 1] for i in range(4))
+    counts = [int(hist[b[i]:b[i + 1]].sum()) for i in range(4)]
+    assert max(counts) - min(counts) <= 200          # within two rows of the densest region
+    # degenerate: everything in one row still yields valid, strictly increasing bounds
+    h2 = torch.zeros(64, dtype=torch.int64); h2[10] = 5
+    b2 = D.balanced_slab_bounds(h2, 8)
+    assert b2[0] == 0 and b2[-1] == 64 and all(b2[i] < b2[i + 1] for i in range(8))
