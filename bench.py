@@ -308,10 +308,17 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     alg_bytes = BYTES_PER_VIS * V + 16 * N_GRID * N_GRID + table.numel() * 16
+    traffic = None   # dram__bytes_read+write of the gridder per launch, from the committed ncu capture of this workload
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_v5_traffic.json")
+    if os.path.exists(tpath) and N_GRID == 8192 and SUPPORT == 15 and not args.uniform and args.variant == 0:
+        tj = json.load(open(tpath))
+        if int(tj.get("vis_per_launch", 0)) == V:
+            k = tj["grid_tiled_kernel<16,2>"]
+            traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": "grid_tiled_kernel<16,2>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "traffic": None, "peak_source": peak_src, "kernel_ms": kern_ms,
+        "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "kernel_ms": kern_ms,
         "note": "compulsory-byte accounting (64 B/vis + 16 N^2 + table); the tiled gridder is bound by L2->SM kernel-tap traffic (3.7 KB/vis), see DESIGN.md 4.2 and the l2_taps entry",
         "fp64": {"achieved_tflops": FLOP_PER_VIS * V / (kern_ms * 1e-3) / 1e12, "peak_tflops_measured": fp64_peak,
                  "frac": FLOP_PER_VIS * V / (kern_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None},
