@@ -342,9 +342,9 @@ void orc_make_grid_hermitian(i64 n, const double *g, double *out) {
 /* ===========================================================================
  * CPU BASELINE (bench.py cpu_baseline / --impl reference): the same convgrid2 semantics,
  * parallelised over disjoint grid row bands so no atomics are needed (BASELINE.md section 4,
- * variant 1).  Binning is done once up front; each thread scans all visibilities and applies
- * only the taps that land in its row band.  Results equal orc_convgrid2 up to summation order
- * (per-cell order is identical: visibility order), so in practice bit-identical.
+ * variant 1).  Binning is done once up front; the visibilities are listed per row band (in
+ * visibility order) and the bands are claimed dynamically by the threads.  Per-cell summation
+ * order is visibility order, as in orc_convgrid2, so the result is bit-identical to it.
  * ========================================================================= */
 int orc_num_threads(void) {
 #ifdef _OPENMP
@@ -359,21 +359,39 @@ void orc_convgrid2_omp(i64 nw, i64 qpx, i64 gh, i64 gw, const double *gcf, i64 h
                        const double *vis, int normalise) {
     (void)nw;
     const i64 halfgh = fdiv(gh, 2), halfgw = fdiv(gw, 2);
-    i64 *xs = (i64 *)malloc((size_t)cnt * 4 * sizeof(i64));
+    i64 *xs = (i64 *)malloc((size_t)(cnt > 0 ? cnt : 1) * 4 * sizeof(i64));
     i64 *xfs = xs + cnt, *ys = xfs + cnt, *yfs = ys + cnt;
     orc_frac_coord(w, qpx, cnt, u, xs, xfs, normalise);
     orc_frac_coord(h, qpx, cnt, v, ys, yfs, normalise);
-#pragma omp parallel
-    {
-#ifdef _OPENMP
-        const int nt = omp_get_num_threads(), tid = omp_get_thread_num();
-#else
-        const int nt = 1, tid = 0;
-#endif
-        const i64 r0 = h * tid / nt, r1 = h * (tid + 1) / nt;
-        for (i64 k = 0; k < cnt; ++k) {
+    /* row bands (many more than threads, claimed dynamically: the uv coverage is core-dominated); every band
+     * gets the list of visibilities whose footprint rows intersect it, in visibility order */
+    const i64 nb = (i64)orc_num_threads() * 16 < h ? (i64)orc_num_threads() * 16 : (h > 0 ? h : 1);
+    i64 *start = (i64 *)calloc((size_t)nb + 1, sizeof(i64));
+#define BAND_OF(r) ((((r) + 1) * nb - 1) / h) /* largest b with h*b/nb <= r */
+    for (i64 k = 0; k < cnt; ++k) {
+        i64 y0 = ys[k] - halfgh, y1 = y0 + gh - 1;
+        if (y1 < 0 || y0 >= h) continue;
+        if (y0 < 0) y0 = 0;
+        if (y1 >= h) y1 = h - 1;
+        for (i64 b = BAND_OF(y0); b <= BAND_OF(y1); ++b) start[b + 1]++;
+    }
+    for (i64 b = 0; b < nb; ++b) start[b + 1] += start[b];
+    i64 *list = (i64 *)malloc((size_t)(start[nb] > 0 ? start[nb] : 1) * sizeof(i64));
+    i64 *fill = (i64 *)malloc((size_t)nb * sizeof(i64));
+    memcpy(fill, start, (size_t)nb * sizeof(i64));
+    for (i64 k = 0; k < cnt; ++k) {
+        i64 y0 = ys[k] - halfgh, y1 = y0 + gh - 1;
+        if (y1 < 0 || y0 >= h) continue;
+        if (y0 < 0) y0 = 0;
+        if (y1 >= h) y1 = h - 1;
+        for (i64 b = BAND_OF(y0); b <= BAND_OF(y1); ++b) list[fill[b]++] = k;
+    }
+#pragma omp parallel for schedule(dynamic, 1)
+    for (i64 b = 0; b < nb; ++b) {
+        const i64 r0 = h * b / nb, r1 = h * (b + 1) / nb;
+        for (i64 q = start[b]; q < start[b + 1]; ++q) {
+            const i64 k = list[q];
             const i64 y0 = ys[k] - halfgh;
-            if (y0 >= r1 || y0 + gh <= r0) continue;
             const i64 wb = wbin ? wbin[k] : 0;
             const double *kern = gcf + 2 * ((((wb * qpx) + yfs[k]) * qpx + xfs[k]) * gh * gw);
             const double vr = vis[2 * k], vi = vis[2 * k + 1];
@@ -390,7 +408,8 @@ void orc_convgrid2_omp(i64 nw, i64 qpx, i64 gh, i64 gw, const double *gcf, i64 h
             }
         }
     }
-    free(xs);
+#undef BAND_OF
+    free(fill); free(list); free(start); free(xs);
 }
 
 void orc_convdegrid2_omp(i64 nw, i64 qpx, i64 gh, i64 gw, const double *gcf, i64 h, i64 w,
