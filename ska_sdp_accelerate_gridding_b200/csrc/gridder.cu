@@ -325,61 +325,68 @@ __global__ void __launch_bounds__(256) degrid_warp_kernel(const GridArgs A) {
     }
 }
 
-// Degridder, small supports (gh*gw <= 32*M, M <= 8): one warp per visibility, lane l owns taps l, l+32, ...
-// of the slice, so the M tap loads of a warp are one contiguous, fully coalesced stream; the matching grid
-// cells are M loads at per-lane offsets that do not depend on the visibility and are computed once.  All 2M
-// loads of a visibility are issued before the first FMA (memory-level parallelism instead of occupancy).
-template <int M>
-__global__ void __launch_bounds__(256) degrid_lin_kernel(const GridArgs A) {
-    const int lane = threadIdx.x & 31;
-    const i64 warp0 = ((i64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const i64 nwarps = ((i64)gridDim.x * blockDim.x) >> 5;
-    const i64 count = (i64)A.counters[2];
-    int ti[M], tj[M], goff[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        const int t = lane + 32 * m;
-        ti[m] = t < A.s2 ? t / A.gw : -1;
-        tj[m] = t < A.s2 ? t - ti[m] * A.gw : 0;
-        goff[m] = ti[m] * A.width + tj[m];
-    }
-    for (i64 r = warp0; r < count; r += nwarps) {
-        const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(A.rec + r) + 1);
-        const int lx = (int)(meta.y & 255u), ly = (int)((meta.y >> 8) & 255u);
-        const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
-        const int tyi = (int)(meta.w / (uint32_t)A.ntx), txi = (int)(meta.w % (uint32_t)A.ntx);
-        const int gx0 = txi * TILE + lx - (A.gw - 1), gy0 = tyi * TILE + ly - (A.gh - 1);
-        const double2 *kp = A.table + (uint32_t)(meta.x + dy * (uint32_t)A.gw + dx) + lane;
-        const double2 *gp = A.grid + ((i64)gy0 * A.width + gx0);
-        const bool interior = gx0 >= 0 && gy0 >= 0 && gx0 + A.gw <= A.width && gy0 + A.gh <= A.nrows;  // warp-uniform
-        double2 k[M], g[M];
-        if (interior) {
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                k[m] = make_double2(0.0, 0.0); g[m] = make_double2(0.0, 0.0);
-                if (ti[m] >= 0) { k[m] = ldg2(kp + 32 * m); g[m] = ldg2(gp + goff[m]); }
-            }
-        } else {
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                k[m] = make_double2(0.0, 0.0); g[m] = make_double2(0.0, 0.0);
-                if (ti[m] >= 0 && (unsigned)(gx0 + tj[m]) < (unsigned)A.width && (unsigned)(gy0 + ti[m]) < (unsigned)A.nrows) {
-                    k[m] = ldg2(kp + 32 * m); g[m] = ldg2(gp + goff[m]);
+// Degridder, tiled: a persistent block pulls the same work items as the gridder, stages the item's subgrid
+// (TILE-1+S)^2 from the grid into shared memory once (zero outside the owned rows / the grid, so the hot loop has no
+// bounds checks), then its 16 half-warps take the item's records round-robin.  Grid cells are then conflict-free
+// 128-bit shared-memory loads (two wavefronts per 15-lane row instead of three unaligned L1 lines); only the kernel
+// taps still come from L2.
+template <int UNROLL>
+__global__ void __launch_bounds__(GRID_THREADS, 4) degrid_tile_kernel(const GridArgs A) {
+    extern __shared__ double2 sg[];
+    __shared__ uint32_t s_item;
+    const int tid = threadIdx.x, hl = tid & 15, hw = tid >> 4;
+    const int SGW = TILE - 1 + A.gw, SGH = TILE - 1 + A.gh;  // staged region (pitch SGW)
+    const uint32_t n_items = A.counters[0];
+    for (;;) {
+        __syncthreads();  // all half-warps are done with the previous subgrid
+        if (tid == 0) s_item = atomicAdd(&A.counters[A.queue], 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_items) break;
+        const WorkItem it = A.items[item];
+        const int tyi = (int)(it.tile / (uint32_t)A.ntx), txi = (int)(it.tile % (uint32_t)A.ntx);
+        const int gx0 = txi * TILE - (A.gw - 1), gy0 = tyi * TILE - (A.gh - 1);
+        for (int c = tid; c < SGW * SGH; c += GRID_THREADS) {
+            const int cy = c / SGW, cx = c - cy * SGW;
+            const int gx = gx0 + cx, gy = gy0 + cy;
+            double2 v = make_double2(0.0, 0.0);
+            if ((unsigned)gx < (unsigned)A.width && (unsigned)gy < (unsigned)A.nrows) v = ldg2(A.grid + (size_t)gy * A.width + gx);
+            sg[c] = v;
+        }
+        __syncthreads();
+        const uint32_t nrec = it.end - it.begin;
+        const uint32_t rounds = (nrec + 15u) / 16u;
+        for (uint32_t q = 0; q < rounds; ++q) {
+            const uint32_t r = q * 16u + (uint32_t)hw;  // both halves of a warp stay in the loop (shuffles below)
+            const bool live = r < nrec;
+            double ar = 0.0, ai = 0.0;
+            uint32_t out_index = 0;
+            if (live) {
+                const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(A.rec + it.begin + r) + 1);
+                out_index = meta.z;
+                const int lx = (int)(meta.y & 255u), ly = (int)((meta.y >> 8) & 255u);
+                const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
+                const uint32_t kslice = meta.x + dy * (uint32_t)A.gw + dx;
+                for (int j = hl; j < A.gw; j += 16) {
+                    const double2 *kp = A.table + (uint32_t)(kslice + (uint32_t)j);
+                    const double2 *gp = sg + ly * SGW + lx + j;
+#pragma unroll UNROLL
+                    for (int i = 0; i < A.gh; ++i) {
+                        const double2 k = ldg2(kp);
+                        const double2 g = *gp;
+                        ar = fma(k.x, g.x, ar); ar = fma(k.y, g.y, ar);   // conj(k) * g
+                        ai = fma(k.x, g.y, ai); ai = fma(-k.y, g.x, ai);
+                        kp += A.gw; gp += SGW;
+                    }
                 }
             }
-        }
-        double ar = 0.0, ai = 0.0;
 #pragma unroll
-        for (int m = 0; m < M; ++m) {  // conj(k) * g
-            ar = fma(k[m].x, g[m].x, ar); ar = fma(k[m].y, g[m].y, ar);
-            ai = fma(k[m].x, g[m].y, ai); ai = fma(-k[m].y, g[m].x, ai);
+            for (int o = 8; o > 0; o >>= 1) {
+                ar += __shfl_xor_sync(0xffffffffu, ar, o);
+                ai += __shfl_xor_sync(0xffffffffu, ai, o);
+            }
+            if (live && hl == 0) A.vis_out[out_index] = make_double2(ar, ai);
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            ar += __shfl_xor_sync(0xffffffffu, ar, o);
-            ai += __shfl_xor_sync(0xffffffffu, ai, o);
-        }
-        if (lane == 0) A.vis_out[meta.z] = make_double2(ar, ai);
     }
 }
 
@@ -444,13 +451,21 @@ extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const do
     SK_CUDA(ctx, cudaMemsetAsync(vis_out, 0, (size_t)plan->count * sizeof(double2), st));
     GridArgs A = make_args(plan, table, const_cast<double *>(grid));
     A.vis_out = reinterpret_cast<double2 *>(vis_out);
-    static const int variant = getenv("SKAGRID_DEGRID_VARIANT") ? atoi(getenv("SKAGRID_DEGRID_VARIANT")) : 0;  // tuning experiments
-    const int taps = A.s2;
-    if (variant == 2 && taps <= 256) degrid_lin_kernel<8><<<ctx->sm_count * 8, 256, 0, st>>>(A);
-    else if (variant == 1) degrid_warp_kernel<16><<<ctx->sm_count * 8, 256, 0, st>>>(A);
-    else if (variant == 3) degrid_warp_kernel<15><<<ctx->sm_count * 16, 256, 0, st>>>(A);
-    else if (variant == 4) degrid_warp_kernel<5><<<ctx->sm_count * 8, 256, 0, st>>>(A);
-    else degrid_warp_kernel<15><<<ctx->sm_count * 8, 256, 0, st>>>(A);  // measured on B200 (S=15): unroll 15 -> 2.9e9 vis/s, 5 -> 2.1e9
+    // SKAGRID_DEGRID_VARIANT=1 selects the untiled kernel (A/B measurements; B200, S=15: tiled 28.6 ms, untiled 35.1 ms per 1e8)
+    static const int variant = getenv("SKAGRID_DEGRID_VARIANT") ? atoi(getenv("SKAGRID_DEGRID_VARIANT")) : 0;
+    const size_t tile_smem = (size_t)(TILE - 1 + A.gw) * (TILE - 1 + A.gh) * sizeof(double2);
+    if (variant != 1 && tile_smem <= 200 * 1024) {
+        A.queue = 5;
+        SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 5, 0, sizeof(uint32_t), st));
+        static bool configured = false;
+        if (!configured) { SK_CUDA(ctx, cudaFuncSetAttribute(degrid_tile_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+        int per_sm = 0;
+        SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_tile_kernel<15>, GRID_THREADS, tile_smem));
+        if (per_sm < 1) per_sm = 1;
+        degrid_tile_kernel<15><<<ctx->sm_count * per_sm, GRID_THREADS, tile_smem, st>>>(A);
+    } else {
+        degrid_warp_kernel<15><<<ctx->sm_count * 8, 256, 0, st>>>(A);  // unroll 15 -> 2.9e9 vis/s, unroll 5 -> 2.1e9 (B200, S=15)
+    }
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
