@@ -89,7 +89,7 @@ __device__ __forceinline__ void mt_setup(MtState<C> &S, uint32_t key, int ty, in
         }
 }
 
-constexpr int REC_BATCH = 128;  // records staged in shared memory per batch (threads 0..127 load one each)
+constexpr int REC_BATCH = 48;   // records staged in shared memory per batch (threads 0..127 load one each)
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -100,7 +100,7 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int R, int MT>
-__global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 5 : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
+__global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 6 : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
     constexpr int C = R / 16;  // residues per thread per dimension
     extern __shared__ double2 sg[];
     __shared__ __align__(16) uint4 s_rec[2][REC_BATCH * 2];  // double-buffered record batches (32 B each)
