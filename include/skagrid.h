@@ -71,6 +71,9 @@ double skagrid_last_device_ms(const skagrid_ctx *ctx);
 int64_t skagrid_launch_count(const skagrid_ctx *ctx);
 /* Measures the FP64 FMA peak of the device with a register-resident DFMA loop (TFLOP/s). */
 int skagrid_measure_fp64_tflops(skagrid_ctx *ctx, double *tflops);
+/* Measures the L2 -> SM read bandwidth (TB/s) with 128-bit L2-only loads over a `bytes`-sized, L2-resident buffer:
+ * the ceiling of the tiled gridder / degridder, whose kernel taps stream from an L2-resident table. */
+int skagrid_measure_l2_read_tbs(skagrid_ctx *ctx, int64_t bytes, double *tbs);
 
 /* ------------------------------------------------------------------ binning (bit-exact)
  * frac_coord  src/Gridding.hs:126-140, frac_coords :142-151 (x,xf from u with width; y,yf from v with height) */
@@ -208,7 +211,8 @@ int skagrid_dev_plan_stats(skagrid_ctx *ctx, skagrid_plan *plan, void *stream, i
 
 /* grid[row0:row1, :] += sum over the plan's visibilities of vis_k * table[slice_k].
  * variant: 0 = tiled shared-memory gridder (default), 1 = one-thread-per-tap global-atomic gridder
- * (the literal `permute (+)`; baseline and cross-check). */
+ * (the literal `permute (+)`; baseline and cross-check), 2 = tiled gridder with two instead of three
+ * kernel-tap loads in flight per thread (A/B measurements). */
 int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, double *grid,
                      int variant, void *stream);
 /* vis_out[k] = sum conj(table[slice_k][i,j]) * grid[...] for the plan's visibilities (others = 0). */

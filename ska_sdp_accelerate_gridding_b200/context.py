@@ -51,6 +51,13 @@ class Context:
         return out.value
 
 
+
+    def l2_read_tbs(self, nbytes: int = 8 << 20) -> float:
+        out = C.c_double()
+        self.check(self.lib.skagrid_measure_l2_read_tbs(self.h, int(nbytes), C.byref(out)))
+        return out.value
+
+
 def get_context(device: int | None = None) -> Context:
     if device is None:
         device = 0

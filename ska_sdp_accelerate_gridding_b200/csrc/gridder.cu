@@ -99,7 +99,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int R, int MT>
+template <int R, int MT, int DEPTH>
 __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 6 : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
     constexpr int C = R / 16;  // residues per thread per dimension
     extern __shared__ double2 sg[];
@@ -136,52 +136,44 @@ __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 6 : (R == 32 ? 2 : 1)
 #pragma unroll
             for (int b = 0; b < C; ++b) { acc[a][b] = make_double2(0.0, 0.0); cell_cur[a][b] = 0; S.cell[a][b] = 0; S.toff[a][b] = 0; S.vmask[a][b] = 0; }
 
-        // request the taps of staged record `j` into k; a record that starts a new micro-tile re-derives the
-        // thread's tap offsets and leaves `pending` set: the registers must be folded before it is consumed
-        bool pending = false;
-        auto issue = [&](const uint4 *buf, uint32_t j, double2 (&k)[C][C]) {
+        // A tap slot: the taps of one staged record in flight, where its products go and whether it opens a new
+        // micro-tile (then the registers are folded before it is consumed).
+        struct Slot { double2 k[C][C]; int cell[C][C]; bool sw; };
+        auto issue = [&](const uint4 *buf, uint32_t j, Slot &s) {
             const uint2 m = *reinterpret_cast<const uint2 *>(&buf[2 * j + 1]);  // kbase, loc (broadcast read)
             const uint32_t key = m.y & mtkey_mask;
-            if (key != S.key) {  // warp-uniform
-                mt_setup<R, C, MT>(S, key, ty, tx, A);
-                pending = true;
-            }
+            s.sw = key != S.key;
+            if (s.sw) mt_setup<R, C, MT>(S, key, ty, tx, A);  // warp-uniform
 #pragma unroll
             for (int a = 0; a < C; ++a)
 #pragma unroll
                 for (int b = 0; b < C; ++b) {
-                    k[a][b] = make_double2(0.0, 0.0);
-                    if (S.vmask[a][b] & m.y) k[a][b] = ldg2(A.table + (uint32_t)(m.x + (uint32_t)S.toff[a][b]));
+                    s.cell[a][b] = S.cell[a][b];
+                    s.k[a][b] = make_double2(0.0, 0.0);
+                    if (S.vmask[a][b] & m.y) s.k[a][b] = ldg2(A.table + (uint32_t)(m.x + (uint32_t)S.toff[a][b]));
                 }
-        };
-        // fold the register accumulators into the thread's own subgrid cells and retarget them
-        auto fold = [&]() {
-#pragma unroll
-            for (int a = 0; a < C; ++a)
-#pragma unroll
-                for (int b = 0; b < C; ++b) {
-                    if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
-                        double2 t = sg[cell_cur[a][b]];
-                        t.x += acc[a][b].x; t.y += acc[a][b].y;
-                        sg[cell_cur[a][b]] = t;
-                        acc[a][b] = make_double2(0.0, 0.0);
-                    }
-                    cell_cur[a][b] = S.cell[a][b];
-                }
-            pending = false;
         };
         // acc += vis_j * k
-        auto consume = [&](const uint4 *buf, uint32_t j, const double2 (&k)[C][C]) {
+        auto consume = [&](const uint4 *buf, uint32_t j, const Slot &s) {
             const double2 vis = *reinterpret_cast<const double2 *>(&buf[2 * j]);
 #pragma unroll
             for (int a = 0; a < C; ++a)
 #pragma unroll
                 for (int b = 0; b < C; ++b) {
+                    if (s.sw) {  // fold the register accumulator into the thread's own subgrid cell and retarget it
+                        if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
+                            double2 t = sg[cell_cur[a][b]];
+                            t.x += acc[a][b].x; t.y += acc[a][b].y;
+                            sg[cell_cur[a][b]] = t;
+                            acc[a][b] = make_double2(0.0, 0.0);
+                        }
+                        cell_cur[a][b] = s.cell[a][b];
+                    }
                     // (vr + i vi)(kr + i ki); an invalid cell has a zero tap and adds +0
-                    acc[a][b].x = fma(vis.x, k[a][b].x, acc[a][b].x);
-                    acc[a][b].x = fma(-vis.y, k[a][b].y, acc[a][b].x);
-                    acc[a][b].y = fma(vis.x, k[a][b].y, acc[a][b].y);
-                    acc[a][b].y = fma(vis.y, k[a][b].x, acc[a][b].y);
+                    acc[a][b].x = fma(vis.x, s.k[a][b].x, acc[a][b].x);
+                    acc[a][b].x = fma(-vis.y, s.k[a][b].y, acc[a][b].x);
+                    acc[a][b].y = fma(vis.x, s.k[a][b].y, acc[a][b].y);
+                    acc[a][b].y = fma(vis.y, s.k[a][b].x, acc[a][b].y);
                 }
         };
 
@@ -202,23 +194,35 @@ __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 6 : (R == 32 ? 2 : 1)
             __syncthreads();      // (first iteration: also orders the subgrid zeroing before any fold)
             const uint4 *buf = s_rec[bi & 1];
 
-            // two tap-register sets in ping-pong: the taps of record j+1 are requested before the FMAs of
-            // record j issue, so each warp keeps two 128-bit tap loads per residue in flight.  Order matters:
-            // issue(j+1) may set `pending` (j+1 opens a new micro-tile); the fold must come after consume(j)
-            // and before consume(j+1), while S still describes record j+1.
-            double2 kA[C][C], kB[C][C];
-            issue(buf, 0, kA);
-            if (pending) fold();
-            uint32_t j = 0;
-            for (; j + 1 < m; j += 2) {
-                issue(buf, j + 1, kB);
-                consume(buf, j, kA);
-                if (pending) fold();
-                if (j + 2 < m) issue(buf, j + 2, kA);
-                consume(buf, j + 1, kB);
-                if (pending) fold();
+            // DEPTH tap slots in rotation: the taps of records j+1 .. j+DEPTH-1 are requested before the FMAs of
+            // record j issue, so each warp keeps DEPTH 128-bit tap loads per residue in flight.
+            if constexpr (DEPTH == 2) {
+                Slot s0, s1;
+                issue(buf, 0, s0);
+                uint32_t j = 0;
+                for (; j + 1 < m; j += 2) {
+                    issue(buf, j + 1, s1);
+                    consume(buf, j, s0);
+                    if (j + 2 < m) issue(buf, j + 2, s0);
+                    consume(buf, j + 1, s1);
+                }
+                if (j < m) consume(buf, j, s0);
+            } else {
+                Slot s0, s1, s2;
+                issue(buf, 0, s0);
+                if (m > 1) issue(buf, 1, s1);
+                uint32_t j = 0;
+                for (; j + 2 < m; j += 3) {
+                    issue(buf, j + 2, s2);
+                    consume(buf, j, s0);
+                    if (j + 3 < m) issue(buf, j + 3, s0);
+                    consume(buf, j + 1, s1);
+                    if (j + 4 < m) issue(buf, j + 4, s1);
+                    consume(buf, j + 2, s2);
+                }
+                if (j < m) consume(buf, j, s0);
+                if (j + 1 < m) consume(buf, j + 1, s1);
             }
-            if (j < m) consume(buf, j, kA);
             __syncthreads();  // every warp is done with buf before it is refilled
         }
 #pragma unroll
@@ -405,18 +409,18 @@ static GridArgs make_args(skagrid_plan *plan, const double *table, double *grid)
     return A;
 }
 
-template <int R, int MT>
+template <int R, int MT, int DEPTH>
 static int launch_tiled(skagrid_ctx *ctx, const GridArgs &A, cudaStream_t st) {
     const size_t smem = (size_t)A.SG * A.SG * sizeof(double2);
     static bool configured = false;
     if (!configured) {
-        SK_CUDA(ctx, cudaFuncSetAttribute(grid_tiled_kernel<R, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SK_CUDA(ctx, cudaFuncSetAttribute(grid_tiled_kernel<R, MT, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     int per_sm = 0;
-    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_tiled_kernel<R, MT>, GRID_THREADS, smem));
+    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_tiled_kernel<R, MT, DEPTH>, GRID_THREADS, smem));
     if (per_sm < 1) return sk_fail(ctx, SKAGRID_ECUDA, "tiled gridder does not fit on an SM (smem %zu)", smem);
-    grid_tiled_kernel<R, MT><<<ctx->sm_count * per_sm, GRID_THREADS, smem, st>>>(A);
+    grid_tiled_kernel<R, MT, DEPTH><<<ctx->sm_count * per_sm, GRID_THREADS, smem, st>>>(A);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
@@ -436,9 +440,13 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
     }
     SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 1, 0, sizeof(uint32_t), st));
     const int MT = plan->g.MT;
-    if (R == 16) return MT == 2 ? launch_tiled<16, 2>(ctx, A, st) : launch_tiled<16, 4>(ctx, A, st);
-    if (R == 32) return MT == 2 ? launch_tiled<32, 2>(ctx, A, st) : launch_tiled<32, 4>(ctx, A, st);
-    return MT == 2 ? launch_tiled<64, 2>(ctx, A, st) : launch_tiled<64, 4>(ctx, A, st);
+    if (R == 16) {
+        // three tap slots in flight (B200, S=15, 1e8 visibilities: 27.1 ms; two slots (variant 2): 27.6 ms)
+        if (variant == 2) return MT == 2 ? launch_tiled<16, 2, 2>(ctx, A, st) : launch_tiled<16, 4, 2>(ctx, A, st);
+        return MT == 2 ? launch_tiled<16, 2, 3>(ctx, A, st) : launch_tiled<16, 4, 3>(ctx, A, st);
+    }
+    if (R == 32) return MT == 2 ? launch_tiled<32, 2, 2>(ctx, A, st) : launch_tiled<32, 4, 2>(ctx, A, st);
+    return MT == 2 ? launch_tiled<64, 2, 2>(ctx, A, st) : launch_tiled<64, 4, 2>(ctx, A, st);
 }
 
 extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, const double *grid, double *vis_out,

@@ -95,7 +95,7 @@ class Plan:
         return dict(kept=out[0], dropped=out[1], work_items=out[2], tiles=out[3], nonempty_tiles=out[4])
 
     def grid(self, table, grid, variant=0):
-        """grid[row0:row1] += sum vis_k * table[slice_k].  variant 0 tiled (+L1 prefetch), 1 atomic scatter, 2 tiled w/o prefetch."""
+        """grid[row0:row1] += sum vis_k * table[slice_k].  variant 0 tiled, 1 atomic scatter (literal permute (+)), 2 tiled with a shallower tap pipeline."""
         _chk(table, torch.complex128, "table"); _chk(grid, torch.complex128, "grid")
         if grid.numel() != (self.rows[1] - self.rows[0]) * self.width:
             raise ValueError("grid tensor does not match the plan's owned rows")
