@@ -21,8 +21,8 @@ typedef unsigned long long u64;
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) VisRec {
     double re, im;       // visibility (0 for degrid-only plans)
-    uint32_t kbase;      // (slice * gh*gw - (dy*gw + dx)) mod 2^32, slice = (wbin*qpx + yf)*qpx + xf or the visibility index (AW):
-                         // table element of tap (i,j) of this visibility = kbase + (dy+i)*gw + (dx+j)
+    uint32_t kbase;      // (slice * gh*kpitch - (dy*kpitch + dx)) mod 2^32, slice = (wbin*qpx + yf)*qpx + xf or the visibility index (AW):
+                         // padded-table element of tap (i,j) of this visibility = kbase + (dy+i)*kpitch + (dx+j)
     uint32_t loc;        // one-hot(dy*MT + dx) << 16 | ly << 8 | lx: footprint origin inside the tile (0..TILE-1) and inside its micro-tile
     uint32_t index;      // position of the visibility in the caller's arrays (degrid output slot)
     uint32_t tile;       // uv tile ty * ntx + tx (lets a record be placed on the grid without its work item)
@@ -50,7 +50,9 @@ struct Geom {
     int R;               // register region edge: 16, 32 or 64 (0: shape not supported by the tiled kernels)
     int MT;              // micro-tile edge: 2 or 4
     int MTR;             // micro-tiles per tile row = TILE / MT
-    int SG;              // shared-memory subgrid edge = TILE - 1 + max(gh, gw)
+    int SG;              // shared-memory subgrid edge = TILE - MT + R
+    int kpitch;          // row pitch (taps) of the padded copy of the kernel table the kernels read: gw rounded up to 16
+                         // (rows start on 256-byte boundaries: a 15-tap row is 2 L1 lines instead of up to 3); gw if R == 0
     i64 nkeys;           // ntx * nty * MTR * MTR
     int normalise;
 };
@@ -70,6 +72,8 @@ struct skagrid_plan {
     uint32_t *d_counters;
     uint32_t *d_blocksums;  // scan scratch
     i64 nblocksums;
+    double2 *d_table;       // padded copy of the kernel table (refreshed by every grid / degrid call), lazily allocated
+    size_t table_bytes;
 };
 
 struct DevBuf {

@@ -36,6 +36,7 @@ struct GridArgs {
     double2 *grid;    // points at the first owned row
     double2 *vis_out; // degridder output
     int gh, gw, s2;
+    int kpitch;       // row pitch (taps) of the padded kernel table; a slice is gh * kpitch taps
     int mt_mask;      // ~(MT - 1)
     int SG;           // subgrid edge (= pitch)
     int ntx;
@@ -50,36 +51,42 @@ __device__ __forceinline__ void red_add(double *addr, double v) {
 }
 
 // Per-thread state of one micro-tile: where the thread's residues sit inside the R x R region.
-template <int C>
+template <int CY, int CX>
 struct MtState {
     uint32_t key;                  // loc & mtkey_mask of the micro-tile (0xFFFFFFFF: none)
-    int toff[C][C];                // tap offset roty*gw + rotx of the thread's (a,b) residue
-    uint32_t vmask[C][C];          // bit 16 + dy*MT+dx set: residue (a,b) has a valid tap for a footprint at (dy,dx)
-    int cell[C][C];                // shared-memory cell of residue (a,b)
+    int toff[CY][CX];              // tap offset roty*kpitch + rotx of the thread's (a,b) residue
+    uint32_t vmask[CY][CX];        // bit 16 + dy*MT+dx set: residue (a,b) has a valid tap for a footprint at (dy,dx)
+    int cell[CY][CX];              // shared-memory cell of residue (a,b)
 };
 
-template <int R, int C, int MT>
-__device__ __forceinline__ void mt_setup(MtState<C> &S, uint32_t key, int ty, int tx, const GridArgs &A) {
+template <int R, int CY, int CX, int MT>
+__device__ __forceinline__ void mt_setup(MtState<CY, CX> &S, uint32_t key, int ty, int tx, const GridArgs &A) {
+    constexpr int TY = R / CY;  // thread rows of the block
     S.key = key;
     const int mx = (int)(key & 255u), my = (int)((key >> 8) & 255u);
-    int roty[C], rotx[C];
-    uint32_t ym[C], xm[C];
+    int roty[CY], rotx[CX];
+    uint32_t ym[CY], xm[CX];
 #pragma unroll
-    for (int a = 0; a < C; ++a) {
-        roty[a] = (ty + 16 * a - my) & (R - 1);
-        rotx[a] = (tx + 16 * a - mx) & (R - 1);
-        ym[a] = 0; xm[a] = 0;
+    for (int a = 0; a < CY; ++a) {
+        roty[a] = (ty + TY * a - my) & (R - 1);
+        ym[a] = 0;
 #pragma unroll
-        for (int d = 0; d < MT; ++d) {
+        for (int d = 0; d < MT; ++d)
             if ((unsigned)(roty[a] - d) < (unsigned)A.gh) ym[a] |= 1u << d;
-            if ((unsigned)(rotx[a] - d) < (unsigned)A.gw) xm[a] |= 1u << d;
-        }
     }
 #pragma unroll
-    for (int a = 0; a < C; ++a)
+    for (int b = 0; b < CX; ++b) {
+        rotx[b] = (tx + 16 * b - mx) & (R - 1);
+        xm[b] = 0;
 #pragma unroll
-        for (int b = 0; b < C; ++b) {
-            S.toff[a][b] = roty[a] * A.gw + rotx[b];
+        for (int d = 0; d < MT; ++d)
+            if ((unsigned)(rotx[b] - d) < (unsigned)A.gw) xm[b] |= 1u << d;
+    }
+#pragma unroll
+    for (int a = 0; a < CY; ++a)
+#pragma unroll
+        for (int b = 0; b < CX; ++b) {
+            S.toff[a][b] = roty[a] * A.kpitch + rotx[b];
             S.cell[a][b] = (my + roty[a]) * A.SG + mx + rotx[b];
             uint32_t m = 0;
 #pragma unroll
@@ -99,9 +106,13 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int R, int MT, int DEPTH>
-__global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 6 : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
-    constexpr int C = R / 16;  // residues per thread per dimension
+// TY thread rows x 16 thread columns; a thread owns CY x CX = (R/TY) x (R/16) residues.  Fewer, fatter threads
+// (TY = 8 for R = 16) halve the per-visibility bookkeeping (record decode, broadcast shared-memory reads, loop
+// control), which matters because the kernel is bound by the L1/shared-memory data pipe and the issue slots.
+template <int R, int MT, int DEPTH, int TY>
+__global__ void __launch_bounds__(16 * TY, (R == 16 ? 6 : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
+    constexpr int CY = R / TY, CX = R / 16;  // residues per thread
+    constexpr int NT = 16 * TY;              // threads per block
     extern __shared__ double2 sg[];
     __shared__ __align__(16) uint4 s_rec[2][REC_BATCH * 2];  // double-buffered record batches (32 B each)
     __shared__ uint32_t s_item;
@@ -125,29 +136,29 @@ __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 6 : (R == 32 ? 2 : 1)
             cp_async16(&s_rec[0][2 * tid + 1], recq + 2 * (size_t)(it.begin + tid) + 1);
         }
         cp_async_commit();
-        for (int c = tid; c < ncell; c += GRID_THREADS) sg[c] = make_double2(0.0, 0.0);
+        for (int c = tid; c < ncell; c += NT) sg[c] = make_double2(0.0, 0.0);
 
-        double2 acc[C][C];
-        int cell_cur[C][C];
-        MtState<C> S;  // micro-tile state of the record whose taps were requested last
+        double2 acc[CY][CX];
+        int cell_cur[CY][CX];
+        MtState<CY, CX> S;  // micro-tile state of the record whose taps were requested last
         S.key = 0xFFFFFFFFu;
 #pragma unroll
-        for (int a = 0; a < C; ++a)
+        for (int a = 0; a < CY; ++a)
 #pragma unroll
-            for (int b = 0; b < C; ++b) { acc[a][b] = make_double2(0.0, 0.0); cell_cur[a][b] = 0; S.cell[a][b] = 0; S.toff[a][b] = 0; S.vmask[a][b] = 0; }
+            for (int b = 0; b < CX; ++b) { acc[a][b] = make_double2(0.0, 0.0); cell_cur[a][b] = 0; S.cell[a][b] = 0; S.toff[a][b] = 0; S.vmask[a][b] = 0; }
 
         // A tap slot: the taps of one staged record in flight, where its products go and whether it opens a new
         // micro-tile (then the registers are folded before it is consumed).
-        struct Slot { double2 k[C][C]; int cell[C][C]; bool sw; };
+        struct Slot { double2 k[CY][CX]; int cell[CY][CX]; bool sw; };
         auto issue = [&](const uint4 *buf, uint32_t j, Slot &s) {
             const uint2 m = *reinterpret_cast<const uint2 *>(&buf[2 * j + 1]);  // kbase, loc (broadcast read)
             const uint32_t key = m.y & mtkey_mask;
             s.sw = key != S.key;
-            if (s.sw) mt_setup<R, C, MT>(S, key, ty, tx, A);  // warp-uniform
+            if (s.sw) mt_setup<R, CY, CX, MT>(S, key, ty, tx, A);  // warp-uniform
 #pragma unroll
-            for (int a = 0; a < C; ++a)
+            for (int a = 0; a < CY; ++a)
 #pragma unroll
-                for (int b = 0; b < C; ++b) {
+                for (int b = 0; b < CX; ++b) {
                     s.cell[a][b] = S.cell[a][b];
                     s.k[a][b] = make_double2(0.0, 0.0);
                     if (S.vmask[a][b] & m.y) s.k[a][b] = ldg2(A.table + (uint32_t)(m.x + (uint32_t)S.toff[a][b]));
@@ -157,9 +168,9 @@ __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 6 : (R == 32 ? 2 : 1)
         auto consume = [&](const uint4 *buf, uint32_t j, const Slot &s) {
             const double2 vis = *reinterpret_cast<const double2 *>(&buf[2 * j]);
 #pragma unroll
-            for (int a = 0; a < C; ++a)
+            for (int a = 0; a < CY; ++a)
 #pragma unroll
-                for (int b = 0; b < C; ++b) {
+                for (int b = 0; b < CX; ++b) {
                     if (s.sw) {  // fold the register accumulator into the thread's own subgrid cell and retarget it
                         if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
                             double2 t = sg[cell_cur[a][b]];
@@ -226,9 +237,9 @@ __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 6 : (R == 32 ? 2 : 1)
             __syncthreads();  // every warp is done with buf before it is refilled
         }
 #pragma unroll
-        for (int a = 0; a < C; ++a)
+        for (int a = 0; a < CY; ++a)
 #pragma unroll
-            for (int b = 0; b < C; ++b) {
+            for (int b = 0; b < CX; ++b) {
                 if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
                     double2 t = sg[cell_cur[a][b]];
                     t.x += acc[a][b].x; t.y += acc[a][b].y;
@@ -240,7 +251,7 @@ __global__ void __launch_bounds__(GRID_THREADS, (R == 16 ? 6 : (R == 32 ? 2 : 1)
         // subgrid -> grid.  Cells outside the owned rows / the grid are dropped (fixoutofbounds).
         const int tyi = (int)(it.tile / (uint32_t)A.ntx), txi = (int)(it.tile % (uint32_t)A.ntx);
         const int gx0 = txi * TILE - (A.gw - 1), gy0 = tyi * TILE - (A.gh - 1);
-        for (int c = tid; c < ncell; c += GRID_THREADS) {
+        for (int c = tid; c < ncell; c += NT) {
             const double2 v = sg[c];
             if (v.x == 0.0 && v.y == 0.0) continue;
             const int cy = c / A.SG, cx = c - cy * A.SG;
@@ -271,7 +282,7 @@ __global__ void __launch_bounds__(256) grid_atomic_kernel(const GridArgs A) {
         const int tyi = (int)(meta.w / (uint32_t)A.ntx), txi = (int)(meta.w % (uint32_t)A.ntx);
         const int gx = txi * TILE + lx - (A.gw - 1) + j, gy = tyi * TILE + ly - (A.gh - 1) + i;
         if ((unsigned)gx >= (unsigned)A.width || (unsigned)gy >= (unsigned)A.nrows) continue;
-        const double2 k = ldg2(A.table + (uint32_t)(meta.x + dy * (uint32_t)A.gw + dx + (uint32_t)t));
+        const double2 k = ldg2(A.table + (uint32_t)(meta.x + (dy + (uint32_t)i) * (uint32_t)A.kpitch + dx + (uint32_t)j));
         double *g = reinterpret_cast<double *>(A.grid + (size_t)gy * A.width + gx);
         red_add(g, vis.x * k.x - vis.y * k.y);
         red_add(g + 1, vis.x * k.y + vis.y * k.x);
@@ -302,12 +313,12 @@ __global__ void __launch_bounds__(256) degrid_warp_kernel(const GridArgs A) {
             const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
             const int tyi = (int)(meta.w / (uint32_t)A.ntx), txi = (int)(meta.w % (uint32_t)A.ntx);
             const int gx0 = txi * TILE + lx - (A.gw - 1), gy0 = tyi * TILE + ly - (A.gh - 1);
-            const uint32_t kslice = meta.x + dy * (uint32_t)A.gw + dx;
+            const uint32_t kslice = meta.x + dy * (uint32_t)A.kpitch + dx;
             const int i0 = max(0, -gy0), i1 = min(A.gh, A.nrows - gy0);
             for (int j = hl; j < A.gw; j += 16) {
                 const int gx = gx0 + j;
                 if ((unsigned)gx >= (unsigned)A.width) continue;
-                const double2 *kp = A.table + (uint32_t)(kslice + (uint32_t)(i0 * A.gw + j));
+                const double2 *kp = A.table + (uint32_t)(kslice + (uint32_t)(i0 * A.kpitch + j));
                 const double2 *gp = A.grid + (size_t)(gy0 + i0) * A.width + gx;
 #pragma unroll UNROLL
                 for (int i = i0; i < i1; ++i) {
@@ -316,7 +327,7 @@ __global__ void __launch_bounds__(256) degrid_warp_kernel(const GridArgs A) {
                     // conj(k) * g
                     ar = fma(k.x, g.x, ar); ar = fma(k.y, g.y, ar);
                     ai = fma(k.x, g.y, ai); ai = fma(-k.y, g.x, ai);
-                    kp += A.gw; gp += A.width;
+                    kp += A.kpitch; gp += A.width;
                 }
             }
         }
@@ -370,7 +381,7 @@ __global__ void __launch_bounds__(GRID_THREADS, 4) degrid_tile_kernel(const Grid
                 out_index = meta.z;
                 const int lx = (int)(meta.y & 255u), ly = (int)((meta.y >> 8) & 255u);
                 const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
-                const uint32_t kslice = meta.x + dy * (uint32_t)A.gw + dx;
+                const uint32_t kslice = meta.x + dy * (uint32_t)A.kpitch + dx;
                 for (int j = hl; j < A.gw; j += 16) {
                     const double2 *kp = A.table + (uint32_t)(kslice + (uint32_t)j);
                     const double2 *gp = sg + ly * SGW + lx + j;
@@ -380,7 +391,7 @@ __global__ void __launch_bounds__(GRID_THREADS, 4) degrid_tile_kernel(const Grid
                         const double2 g = *gp;
                         ar = fma(k.x, g.x, ar); ar = fma(k.y, g.y, ar);   // conj(k) * g
                         ai = fma(k.x, g.y, ai); ai = fma(-k.y, g.x, ai);
-                        kp += A.gw; gp += SGW;
+                        kp += A.kpitch; gp += SGW;
                     }
                 }
             }
@@ -394,6 +405,43 @@ __global__ void __launch_bounds__(GRID_THREADS, 4) degrid_tile_kernel(const Grid
     }
 }
 
+// Padded copy of the caller's kernel table: [slice][gh][kpitch], zero in the pad columns.  A few MB for a w-kernel
+// table (microseconds), one S x S kernel per visibility on the AW path.
+__global__ void __launch_bounds__(256) pad_table_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, i64 nslices, int gh, int gw,
+                                                        int kpitch) {
+    const i64 total = nslices * gh * kpitch;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += stride) {
+        const int j = (int)(c % kpitch);
+        const i64 row = c / kpitch;  // slice * gh + i
+        out[c] = j < gw ? in[row * gw + j] : make_double2(0.0, 0.0);
+    }
+}
+
+static int prepare_table(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, cudaStream_t st, const double **out) {
+    const Geom &g = plan->g;
+    if (g.kpitch == (int)g.gw) { *out = table; return SKAGRID_OK; }
+    const i64 nslices = plan->slice_override ? plan->count : g.nw * g.qpx * g.qpx;
+    const i64 cap_slices = plan->slice_override ? plan->capacity : nslices;
+    const size_t need = (size_t)(cap_slices * g.gh * g.kpitch) * sizeof(double2);
+    if (plan->table_bytes < need) {
+        if (plan->d_table) { SK_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(plan->d_table); plan->d_table = nullptr; plan->table_bytes = 0; }
+        if (cudaMalloc(&plan->d_table, need) != cudaSuccess) {
+            cudaGetLastError();
+            return sk_fail(ctx, SKAGRID_ENOMEM, "padded kernel table: %zu bytes", need);
+        }
+        plan->table_bytes = need;
+    }
+    if (nslices > 0) {
+        i64 b = (nslices * g.gh * g.kpitch + 255) / 256;
+        if (b > (i64)ctx->sm_count * 16) b = (i64)ctx->sm_count * 16;
+        pad_table_kernel<<<(unsigned)b, 256, 0, st>>>(reinterpret_cast<const double2 *>(table), plan->d_table, nslices, (int)g.gh, (int)g.gw, g.kpitch);
+        SK_LAUNCH_CHECK(ctx);
+    }
+    *out = reinterpret_cast<const double *>(plan->d_table);
+    return SKAGRID_OK;
+}
+
 static GridArgs make_args(skagrid_plan *plan, const double *table, double *grid) {
     const Geom &g = plan->g;
     GridArgs A;
@@ -402,6 +450,7 @@ static GridArgs make_args(skagrid_plan *plan, const double *table, double *grid)
     A.grid = reinterpret_cast<double2 *>(grid);
     A.vis_out = nullptr;
     A.gh = (int)g.gh; A.gw = (int)g.gw; A.s2 = (int)(g.gh * g.gw);
+    A.kpitch = g.kpitch;
     A.mt_mask = ~(g.MT - 1);
     A.SG = g.SG; A.ntx = g.ntx;
     A.width = (int)g.width; A.nrows = (int)(g.row1 - g.row0);
@@ -409,18 +458,19 @@ static GridArgs make_args(skagrid_plan *plan, const double *table, double *grid)
     return A;
 }
 
-template <int R, int MT, int DEPTH>
+template <int R, int MT, int DEPTH, int TY>
 static int launch_tiled(skagrid_ctx *ctx, const GridArgs &A, cudaStream_t st) {
+    constexpr int NT = 16 * TY;
     const size_t smem = (size_t)A.SG * A.SG * sizeof(double2);
     static bool configured = false;
     if (!configured) {
-        SK_CUDA(ctx, cudaFuncSetAttribute(grid_tiled_kernel<R, MT, DEPTH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        SK_CUDA(ctx, cudaFuncSetAttribute(grid_tiled_kernel<R, MT, DEPTH, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     int per_sm = 0;
-    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_tiled_kernel<R, MT, DEPTH>, GRID_THREADS, smem));
+    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_tiled_kernel<R, MT, DEPTH, TY>, NT, smem));
     if (per_sm < 1) return sk_fail(ctx, SKAGRID_ECUDA, "tiled gridder does not fit on an SM (smem %zu)", smem);
-    grid_tiled_kernel<R, MT, DEPTH><<<ctx->sm_count * per_sm, GRID_THREADS, smem, st>>>(A);
+    grid_tiled_kernel<R, MT, DEPTH, TY><<<ctx->sm_count * per_sm, NT, smem, st>>>(A);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
@@ -431,7 +481,9 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
     cudaStream_t st = sk_stream(ctx, stream);
     if (plan->count == 0) return SKAGRID_OK;
     if (!plan->has_vis) return sk_fail(ctx, SKAGRID_EINVAL, "grid: the plan was built without visibilities (degrid-only)");
-    GridArgs A = make_args(plan, table, grid);
+    const double *ptab;
+    SK_TRY(prepare_table(ctx, plan, table, st, &ptab));
+    GridArgs A = make_args(plan, ptab, grid);
     const int R = plan->g.R;
     if (variant == 1 || R == 0) {
         grid_atomic_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(A);
@@ -442,11 +494,15 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
     const int MT = plan->g.MT;
     if (R == 16) {
         // three tap slots in flight (B200, S=15, 1e8 visibilities: 27.1 ms; two slots (variant 2): 27.6 ms)
-        if (variant == 2) return MT == 2 ? launch_tiled<16, 2, 2>(ctx, A, st) : launch_tiled<16, 4, 2>(ctx, A, st);
-        return MT == 2 ? launch_tiled<16, 2, 3>(ctx, A, st) : launch_tiled<16, 4, 3>(ctx, A, st);
+        if (variant == 2) return MT == 2 ? launch_tiled<16, 2, 2, 16>(ctx, A, st) : launch_tiled<16, 4, 2, 16>(ctx, A, st);
+        if (variant == 3) return MT == 2 ? launch_tiled<16, 2, 3, 16>(ctx, A, st) : launch_tiled<16, 4, 3, 16>(ctx, A, st);
+        if (variant == 4) return MT == 2 ? launch_tiled<16, 2, 2, 8>(ctx, A, st) : launch_tiled<16, 4, 2, 8>(ctx, A, st);
+        if (variant == 5) return MT == 2 ? launch_tiled<16, 2, 2, 4>(ctx, A, st) : launch_tiled<16, 4, 2, 4>(ctx, A, st);
+        if (variant == 6) return MT == 2 ? launch_tiled<16, 2, 3, 4>(ctx, A, st) : launch_tiled<16, 4, 3, 4>(ctx, A, st);
+        return MT == 2 ? launch_tiled<16, 2, 3, 8>(ctx, A, st) : launch_tiled<16, 4, 3, 8>(ctx, A, st);
     }
-    if (R == 32) return MT == 2 ? launch_tiled<32, 2, 2>(ctx, A, st) : launch_tiled<32, 4, 2>(ctx, A, st);
-    return MT == 2 ? launch_tiled<64, 2, 2>(ctx, A, st) : launch_tiled<64, 4, 2>(ctx, A, st);
+    if (R == 32) return MT == 2 ? launch_tiled<32, 2, 2, 16>(ctx, A, st) : launch_tiled<32, 4, 2, 16>(ctx, A, st);
+    return MT == 2 ? launch_tiled<64, 2, 2, 16>(ctx, A, st) : launch_tiled<64, 4, 2, 16>(ctx, A, st);
 }
 
 extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, const double *grid, double *vis_out,
@@ -457,7 +513,9 @@ extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const do
     if (plan->count == 0) return SKAGRID_OK;
     // visibilities without a tap on the owned rows are not in the record list: their output is 0
     SK_CUDA(ctx, cudaMemsetAsync(vis_out, 0, (size_t)plan->count * sizeof(double2), st));
-    GridArgs A = make_args(plan, table, const_cast<double *>(grid));
+    const double *ptab;
+    SK_TRY(prepare_table(ctx, plan, table, st, &ptab));
+    GridArgs A = make_args(plan, ptab, const_cast<double *>(grid));
     A.vis_out = reinterpret_cast<double2 *>(vis_out);
     // SKAGRID_DEGRID_VARIANT=1 selects the untiled kernel (A/B measurements; B200, S=15: tiled 28.6 ms, untiled 35.1 ms per 1e8)
     static const int variant = getenv("SKAGRID_DEGRID_VARIANT") ? atoi(getenv("SKAGRID_DEGRID_VARIANT")) : 0;

@@ -14,7 +14,7 @@
 
 struct BinParams {
     double halfwf, wf, halfhf, hf, qpxf, qpxfrac;
-    i64 qpx, width, height, row0, row1, gh, gw, halfgh, halfgw, nw;
+    i64 qpx, width, height, row0, row1, gh, gw, halfgh, halfgw, nw, kpitch;
     int ntx, nty, normalise, slice_override;
     int mt_shift, mtr;  // micro-tile edge = 1 << mt_shift; micro-tiles per tile row
 };
@@ -30,7 +30,7 @@ static BinParams make_bin_params(const Geom &g, int slice_override) {
     p.qpx = g.qpx; p.width = g.width; p.height = g.height; p.row0 = g.row0; p.row1 = g.row1;
     p.gh = g.gh; p.gw = g.gw; p.halfgh = g.gh / 2; p.halfgw = g.gw / 2; p.nw = g.nw;
     p.ntx = g.ntx; p.nty = g.nty; p.normalise = g.normalise; p.slice_override = slice_override;
-    p.mt_shift = g.MT == 4 ? 2 : 1; p.mtr = g.MTR;
+    p.mt_shift = g.MT == 4 ? 2 : 1; p.mtr = g.MTR; p.kpitch = g.kpitch;
     return p;
 }
 
@@ -55,9 +55,10 @@ int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, Geom *g) {
     while (g->MT < 4 && g->MT * 2 - 1 + smax <= rr) g->MT *= 2;
     g->MTR = TILE / g->MT;
     g->SG = TILE - g->MT + rr;
+    g->kpitch = g->R ? (int)((in->gw + 15) / 16 * 16) : (int)in->gw;
     const i64 nkeys = ntx * nty * g->MTR * g->MTR;
     if (nkeys >= (i64)0xFFFFFFF0ll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: grid too large for 32-bit bucket keys");
-    if (in->nw * in->qpx * in->qpx * in->gh * in->gw >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel table has more than 2^32 taps");
+    if (in->nw * in->qpx * in->qpx * in->gh * g->kpitch >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel table has more than 2^32 taps");
     g->ntx = (int)ntx; g->nty = (int)nty; g->nkeys = nkeys; g->normalise = 1;
     return SKAGRID_OK;
 }
@@ -85,7 +86,7 @@ __device__ __forceinline__ bool bin_vis(const BinParams &P, double pu, double pv
     const uint32_t mtm = (1u << P.mt_shift) - 1u, dx = (uint32_t)lx & mtm, dy = (uint32_t)ly & mtm;
     loc = (0x10000u << ((dy << P.mt_shift) | dx)) | ((uint32_t)ly << 8) | (uint32_t)lx;
     // element offset of tap (-dy, -dx) of the slice, modulo 2^32: the gridder adds its per-thread tap offset
-    slice = slice * (uint32_t)(P.gh * P.gw) - (dy * (uint32_t)P.gw + dx);
+    slice = slice * (uint32_t)(P.gh * P.kpitch) - (dy * (uint32_t)P.kpitch + dx);
     key = (uint32_t)(ty * P.ntx + tx) * (uint32_t)(P.mtr * P.mtr) + mt;
     return true;
 }
@@ -228,13 +229,14 @@ void sk_plan_free(skagrid_plan *p) {
     if (p->d_items) cudaFree(p->d_items);
     if (p->d_counters) cudaFree(p->d_counters);
     if (p->d_blocksums) cudaFree(p->d_blocksums);
+    if (p->d_table) cudaFree(p->d_table);
     delete p;
 }
 
 int sk_plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double *u, const double *v,
                      const i64 *wbin, const double *vis, cudaStream_t st) {
     if (count < 0 || count > p->capacity) return sk_fail(ctx, SKAGRID_EINVAL, "plan: count %lld exceeds capacity %lld", count, p->capacity);
-    if (p->slice_override && count * p->g.gh * p->g.gw >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "plan: per-visibility kernel table has more than 2^32 taps");
+    if (p->slice_override && count * p->g.gh * p->g.kpitch >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "plan: per-visibility kernel table has more than 2^32 taps");
     if (count > 0 && (!u || !v)) return sk_fail(ctx, SKAGRID_EINVAL, "plan: u/v is NULL");
     p->count = count;
     p->has_vis = vis != nullptr;
