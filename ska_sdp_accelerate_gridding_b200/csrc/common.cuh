@@ -36,7 +36,7 @@ struct WorkItem {
     uint32_t pad;
 };
 
-constexpr int TILE = 32;                       // uv tile edge in footprint-origin cells
+constexpr int TILE = 16;                       // uv tile edge in footprint-origin cells
 constexpr int CHUNK = 4096;                    // max records per work item (load balance)
 constexpr int GRID_THREADS = 256;              // threads per gridder / degridder block
 

@@ -110,7 +110,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // (TY = 8 for R = 16) halve the per-visibility bookkeeping (record decode, broadcast shared-memory reads, loop
 // control), which matters because the kernel is bound by the L1/shared-memory data pipe and the issue slots.
 template <int R, int MT, int DEPTH, int TY>
-__global__ void __launch_bounds__(16 * TY, (R == 16 ? 6 : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
+__global__ void __launch_bounds__(16 * TY, (R == 16 ? (TY == 8 ? 8 : 6) : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
     constexpr int CY = R / TY, CX = R / 16;  // residues per thread
     constexpr int NT = 16 * TY;              // threads per block
     extern __shared__ double2 sg[];
