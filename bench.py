@@ -318,7 +318,7 @@ def main():
             traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "grid_tiled_kernel<16,2,3>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "bound": "hbm", "kernel": "grid_tiled_kernel<R=16,MT=2,DEPTH=3,TY=8>" if SUPPORT <= 15 else "grid_tiled_kernel<R=32,MT=2,DEPTH=2,TY=16>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "kernel_ms": kern_ms,
         "note": "compulsory-byte accounting (64 B/vis + 16 N^2 + table); the tiled gridder is bound by L2->SM kernel-tap traffic (3.7 KB/vis), see DESIGN.md 4.2 and the l2_taps entry",
         "fp64": {"achieved_tflops": FLOP_PER_VIS * V / (kern_ms * 1e-3) / 1e12, "peak_tflops_measured": fp64_peak,
@@ -336,11 +336,12 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": "config 4: synthetic SKA1-Low-shaped visibilities, 8192^2 c128 grid, support 15, oversampling 8, 32 w-planes, "
+            "workload": ("config 4: " if (N_GRID, SUPPORT, NW) == (8192, 15, 32) else "") +
+                        f"synthetic SKA1-Low-shaped visibilities, {N_GRID}^2 c128 grid, support {SUPPORT}, oversampling {QPX}, {NW} w-planes, "
                         "visibility-sharded (one batch per GPU) with NCCL all-reduce of the grid",
             "vis_per_gpu_per_step": V, "uv": "uniform" if args.uniform else "core-dominated mixture (SURVEY 8d)", "seed": SEED,
             "step": "bin+bucket -> tiled gridder -> all-reduce (N>1) -> hermitian+IFFT+real/max -> degridder",
-            "l2": "inputs (4.0 GB at 1e8 vis) and grid (1.07 GB) exceed the 126 MB L2; no explicit flush",
+            "l2": f"inputs ({V * 40 / 1e9:.1f} GB) and grid ({N_GRID * N_GRID * 16 / 1e9:.2f} GB) exceed the 126 MB L2; no explicit flush",
             "gridder_variant": args.variant, "plan": stats,
         },
         "stages_ms": sm,

@@ -23,7 +23,7 @@ struct __align__(16) VisRec {
     double re, im;       // visibility (0 for degrid-only plans)
     uint32_t kbase;      // (slice * gh*kpitch - (dy*kpitch + dx)) mod 2^32, slice = (wbin*qpx + yf)*qpx + xf or the visibility index (AW):
                          // padded-table element of tap (i,j) of this visibility = kbase + (dy+i)*kpitch + (dx+j)
-    uint32_t loc;        // one-hot(dy*MT + dx) << 16 | ly << 8 | lx: footprint origin inside the tile (0..TILE-1) and inside its micro-tile
+    uint32_t loc;        // one-hot(dy*MT + dx) << 16 | ly << 8 | lx: footprint origin inside the tile (0..tile-1) and inside its micro-tile
     uint32_t index;      // position of the visibility in the caller's arrays (degrid output slot)
     uint32_t tile;       // uv tile ty * ntx + tx (lets a record be placed on the grid without its work item)
 };
@@ -36,7 +36,9 @@ struct WorkItem {
     uint32_t pad;
 };
 
-constexpr int TILE = 16;                       // uv tile edge in footprint-origin cells
+// The uv tile edge (in footprint-origin cells) is a per-plan choice, 16 or 32 (Geom::tile): small tiles keep the
+// shared-memory subgrid small (more resident blocks per SM: best for dense uv coverage), large tiles amortise the
+// per-tile zero/flush over more visibilities (best for sparse coverage and for wide kernels).
 constexpr int CHUNK = 4096;                    // max records per work item (load balance)
 constexpr int GRID_THREADS = 256;              // threads per gridder / degridder block
 
@@ -49,8 +51,9 @@ struct Geom {
     int ntx, nty;        // tiles per dimension
     int R;               // register region edge: 16, 32 or 64 (0: shape not supported by the tiled kernels)
     int MT;              // micro-tile edge: 2 or 4
-    int MTR;             // micro-tiles per tile row = TILE / MT
-    int SG;              // shared-memory subgrid edge = TILE - MT + R
+    int tile, tshift;    // uv tile edge (16 or 32) and its log2
+    int MTR;             // micro-tiles per tile row = tile / MT
+    int SG;              // shared-memory subgrid edge = tile - MT + R
     int kpitch;          // row pitch (taps) of the padded copy of the kernel table the kernels read: gw rounded up to 16
                          // (rows start on 256-byte boundaries: a 15-tap row is 2 L1 lines instead of up to 3); gw if R == 0
     i64 nkeys;           // ntx * nty * MTR * MTR
@@ -134,7 +137,7 @@ static inline cudaStream_t sk_stream(skagrid_ctx *ctx, void *s) { (void)ctx; ret
 // ---------------------------------------------------------------------------------------------
 // internal device-pointer entry points implemented across the TUs (all asynchronous on `st`)
 // ---------------------------------------------------------------------------------------------
-int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, Geom *g);
+int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, i64 capacity, Geom *g);
 int sk_plan_alloc(skagrid_ctx *ctx, const skagrid_geom *geom, i64 capacity, int slice_override, skagrid_plan **out);
 int sk_plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double *u, const double *v, const i64 *wbin, const double *vis,
                  cudaStream_t st);

@@ -38,6 +38,7 @@ struct GridArgs {
     int gh, gw, s2;
     int kpitch;       // row pitch (taps) of the padded kernel table; a slice is gh * kpitch taps
     int mt_mask;      // ~(MT - 1)
+    int tile, tshift; // uv tile edge (footprint origins) and its log2
     int SG;           // subgrid edge (= pitch)
     int ntx;
     int width, nrows; // grid width, owned rows
@@ -96,7 +97,9 @@ __device__ __forceinline__ void mt_setup(MtState<CY, CX> &S, uint32_t key, int t
         }
 }
 
-constexpr int REC_BATCH = 48;   // records staged in shared memory per batch (threads 0..127 load one each)
+// records staged in shared memory per batch: 48 for the 16-wide region (keeps 8 blocks of 17.6 KB resident per SM),
+// 128 for the wider ones (their subgrid, not the staging buffers, limits residency)
+template <int R> struct RecBatch { static constexpr int value = R == 16 ? 48 : 128; };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -110,9 +113,11 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // (TY = 8 for R = 16) halve the per-visibility bookkeeping (record decode, broadcast shared-memory reads, loop
 // control), which matters because the kernel is bound by the L1/shared-memory data pipe and the issue slots.
 template <int R, int MT, int DEPTH, int TY>
-__global__ void __launch_bounds__(16 * TY, (R == 16 ? (TY == 8 ? 8 : 6) : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
+__global__ void __launch_bounds__(16 * TY, (R == 16 ? (TY == 8 ? 8 : 6) : (R == 32 ? (TY == 8 ? 3 : 2) : 1))) grid_tiled_kernel(const GridArgs A) {
     constexpr int CY = R / TY, CX = R / 16;  // residues per thread
     constexpr int NT = 16 * TY;              // threads per block
+    constexpr int REC_BATCH = RecBatch<R>::value;
+    static_assert(REC_BATCH <= NT, "one staging thread per record");
     extern __shared__ double2 sg[];
     __shared__ __align__(16) uint4 s_rec[2][REC_BATCH * 2];  // double-buffered record batches (32 B each)
     __shared__ uint32_t s_item;
@@ -250,7 +255,7 @@ __global__ void __launch_bounds__(16 * TY, (R == 16 ? (TY == 8 ? 8 : 6) : (R == 
 
         // subgrid -> grid.  Cells outside the owned rows / the grid are dropped (fixoutofbounds).
         const int tyi = (int)(it.tile / (uint32_t)A.ntx), txi = (int)(it.tile % (uint32_t)A.ntx);
-        const int gx0 = txi * TILE - (A.gw - 1), gy0 = tyi * TILE - (A.gh - 1);
+        const int gx0 = (txi << A.tshift) - (A.gw - 1), gy0 = (tyi << A.tshift) - (A.gh - 1);
         for (int c = tid; c < ncell; c += NT) {
             const double2 v = sg[c];
             if (v.x == 0.0 && v.y == 0.0) continue;
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(256) grid_atomic_kernel(const GridArgs A) {
         const int lx = (int)(meta.y & 255u), ly = (int)((meta.y >> 8) & 255u);
         const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
         const int tyi = (int)(meta.w / (uint32_t)A.ntx), txi = (int)(meta.w % (uint32_t)A.ntx);
-        const int gx = txi * TILE + lx - (A.gw - 1) + j, gy = tyi * TILE + ly - (A.gh - 1) + i;
+        const int gx = (txi << A.tshift) + lx - (A.gw - 1) + j, gy = (tyi << A.tshift) + ly - (A.gh - 1) + i;
         if ((unsigned)gx >= (unsigned)A.width || (unsigned)gy >= (unsigned)A.nrows) continue;
         const double2 k = ldg2(A.table + (uint32_t)(meta.x + (dy + (uint32_t)i) * (uint32_t)A.kpitch + dx + (uint32_t)j));
         double *g = reinterpret_cast<double *>(A.grid + (size_t)gy * A.width + gx);
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(256) degrid_warp_kernel(const GridArgs A) {
             const int lx = (int)(meta.y & 255u), ly = (int)((meta.y >> 8) & 255u);
             const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
             const int tyi = (int)(meta.w / (uint32_t)A.ntx), txi = (int)(meta.w % (uint32_t)A.ntx);
-            const int gx0 = txi * TILE + lx - (A.gw - 1), gy0 = tyi * TILE + ly - (A.gh - 1);
+            const int gx0 = (txi << A.tshift) + lx - (A.gw - 1), gy0 = (tyi << A.tshift) + ly - (A.gh - 1);
             const uint32_t kslice = meta.x + dy * (uint32_t)A.kpitch + dx;
             const int i0 = max(0, -gy0), i1 = min(A.gh, A.nrows - gy0);
             for (int j = hl; j < A.gw; j += 16) {
@@ -350,7 +355,7 @@ __global__ void __launch_bounds__(GRID_THREADS, 4) degrid_tile_kernel(const Grid
     extern __shared__ double2 sg[];
     __shared__ uint32_t s_item;
     const int tid = threadIdx.x, hl = tid & 15, hw = tid >> 4;
-    const int SGW = TILE - 1 + A.gw, SGH = TILE - 1 + A.gh;  // staged region (pitch SGW)
+    const int SGW = A.tile - 1 + A.gw, SGH = A.tile - 1 + A.gh;  // staged region (pitch SGW)
     const uint32_t n_items = A.counters[0];
     for (;;) {
         __syncthreads();  // all half-warps are done with the previous subgrid
@@ -360,7 +365,7 @@ __global__ void __launch_bounds__(GRID_THREADS, 4) degrid_tile_kernel(const Grid
         if (item >= n_items) break;
         const WorkItem it = A.items[item];
         const int tyi = (int)(it.tile / (uint32_t)A.ntx), txi = (int)(it.tile % (uint32_t)A.ntx);
-        const int gx0 = txi * TILE - (A.gw - 1), gy0 = tyi * TILE - (A.gh - 1);
+        const int gx0 = (txi << A.tshift) - (A.gw - 1), gy0 = (tyi << A.tshift) - (A.gh - 1);
         for (int c = tid; c < SGW * SGH; c += GRID_THREADS) {
             const int cy = c / SGW, cx = c - cy * SGW;
             const int gx = gx0 + cx, gy = gy0 + cy;
@@ -451,6 +456,7 @@ static GridArgs make_args(skagrid_plan *plan, const double *table, double *grid)
     A.vis_out = nullptr;
     A.gh = (int)g.gh; A.gw = (int)g.gw; A.s2 = (int)(g.gh * g.gw);
     A.kpitch = g.kpitch;
+    A.tile = g.tile; A.tshift = g.tshift;
     A.mt_mask = ~(g.MT - 1);
     A.SG = g.SG; A.ntx = g.ntx;
     A.width = (int)g.width; A.nrows = (int)(g.row1 - g.row0);
@@ -501,7 +507,11 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
         if (variant == 6) return MT == 2 ? launch_tiled<16, 2, 3, 4>(ctx, A, st) : launch_tiled<16, 4, 3, 4>(ctx, A, st);
         return MT == 2 ? launch_tiled<16, 2, 3, 8>(ctx, A, st) : launch_tiled<16, 4, 3, 8>(ctx, A, st);
     }
-    if (R == 32) return MT == 2 ? launch_tiled<32, 2, 2, 16>(ctx, A, st) : launch_tiled<32, 4, 2, 16>(ctx, A, st);
+    if (R == 32) {
+        if (variant == 4) return MT == 2 ? launch_tiled<32, 2, 2, 8>(ctx, A, st) : launch_tiled<32, 4, 2, 8>(ctx, A, st);
+        if (variant == 3) return MT == 2 ? launch_tiled<32, 2, 3, 16>(ctx, A, st) : launch_tiled<32, 4, 3, 16>(ctx, A, st);
+        return MT == 2 ? launch_tiled<32, 2, 2, 16>(ctx, A, st) : launch_tiled<32, 4, 2, 16>(ctx, A, st);
+    }
     return MT == 2 ? launch_tiled<64, 2, 2, 16>(ctx, A, st) : launch_tiled<64, 4, 2, 16>(ctx, A, st);
 }
 
@@ -519,7 +529,7 @@ extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const do
     A.vis_out = reinterpret_cast<double2 *>(vis_out);
     // SKAGRID_DEGRID_VARIANT=1 selects the untiled kernel (A/B measurements; B200, S=15: tiled 28.6 ms, untiled 35.1 ms per 1e8)
     static const int variant = getenv("SKAGRID_DEGRID_VARIANT") ? atoi(getenv("SKAGRID_DEGRID_VARIANT")) : 0;
-    const size_t tile_smem = (size_t)(TILE - 1 + A.gw) * (TILE - 1 + A.gh) * sizeof(double2);
+    const size_t tile_smem = (size_t)(A.tile - 1 + A.gw) * (A.tile - 1 + A.gh) * sizeof(double2);
     if (variant != 1 && tile_smem <= 200 * 1024) {
         A.queue = 5;
         SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 5, 0, sizeof(uint32_t), st));

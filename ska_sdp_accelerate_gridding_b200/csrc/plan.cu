@@ -8,6 +8,7 @@
 // gets an integer key (uv tile of its footprint origin, 2x2 micro-tile inside the tile) and a counting
 // sort (histogram -> exclusive scan -> scatter) groups the 32-byte records per key.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -17,6 +18,7 @@ struct BinParams {
     i64 qpx, width, height, row0, row1, gh, gw, halfgh, halfgw, nw, kpitch;
     int ntx, nty, normalise, slice_override;
     int mt_shift, mtr;  // micro-tile edge = 1 << mt_shift; micro-tiles per tile row
+    int tshift;         // log2 of the uv tile edge
 };
 
 static BinParams make_bin_params(const Geom &g, int slice_override) {
@@ -30,11 +32,11 @@ static BinParams make_bin_params(const Geom &g, int slice_override) {
     p.qpx = g.qpx; p.width = g.width; p.height = g.height; p.row0 = g.row0; p.row1 = g.row1;
     p.gh = g.gh; p.gw = g.gw; p.halfgh = g.gh / 2; p.halfgw = g.gw / 2; p.nw = g.nw;
     p.ntx = g.ntx; p.nty = g.nty; p.normalise = g.normalise; p.slice_override = slice_override;
-    p.mt_shift = g.MT == 4 ? 2 : 1; p.mtr = g.MTR; p.kpitch = g.kpitch;
+    p.mt_shift = g.MT == 4 ? 2 : 1; p.mtr = g.MTR; p.kpitch = g.kpitch; p.tshift = g.tshift;
     return p;
 }
 
-int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, Geom *g) {
+int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, i64 capacity, Geom *g) {
     if (!in) return sk_fail(ctx, SKAGRID_EINVAL, "geom is NULL");
     if (in->height <= 0 || in->width <= 0 || in->qpx <= 0 || in->gh <= 0 || in->gw <= 0 || in->nw <= 0)
         return sk_fail(ctx, SKAGRID_EINVAL, "geom: non-positive dimension");
@@ -43,8 +45,6 @@ int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, Geom *g) {
     if (in->gh > 127 || in->gw > 127) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel support %lldx%lld above the supported 127", (i64)in->gh, (i64)in->gw);
     g->height = in->height; g->width = in->width; g->row0 = in->row0; g->row1 = in->row1;
     g->nw = in->nw; g->qpx = in->qpx; g->gh = in->gh; g->gw = in->gw;
-    const i64 ntx = (in->width + in->gw - 1 + TILE - 1) / TILE;
-    const i64 nty = ((in->row1 - in->row0) + in->gh - 1 + TILE - 1) / TILE;
     // register region / micro-tile of the tiled kernels: smallest R in {16,32,64} with R >= S+1, then the
     // largest power-of-two micro-tile (<= 4, so that (dy,dx) fits a 16-bit one-hot) whose footprints still fit:
     // MT - 1 + S <= R
@@ -53,8 +53,17 @@ int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, Geom *g) {
     const int rr = g->R ? g->R : 64;
     g->MT = 2;
     while (g->MT < 4 && g->MT * 2 - 1 + smax <= rr) g->MT *= 2;
-    g->MTR = TILE / g->MT;
-    g->SG = TILE - g->MT + rr;
+    // uv tile edge: 16 when the batch is dense enough (>= 128 visibilities per 16x16 tile on average over the owned area)
+    // and the kernel fits the 16-wide region, else 32 (measured on B200: config 4, S=15, 1e8 visibilities on 8192^2:
+    // tile 16 -> 22.5 ms, tile 32 -> 25.7 ms; config-5 shape, S=31, 5e7 on 32768^2: tile 16 -> 81.7 ms, tile 32 -> 64.9 ms)
+    const double tiles16 = ((double)in->width / 16.0) * ((double)(in->row1 - in->row0) / 16.0);
+    g->tile = (g->R == 16 && (double)capacity >= 128.0 * tiles16) ? 16 : 32;
+    if (const char *e = getenv("SKAGRID_TILE")) { const int t = atoi(e); if (t == 16 || t == 32) g->tile = t; }  // tuning experiments
+    g->tshift = g->tile == 16 ? 4 : 5;
+    const i64 ntx = (in->width + in->gw - 1 + g->tile - 1) / g->tile;
+    const i64 nty = ((in->row1 - in->row0) + in->gh - 1 + g->tile - 1) / g->tile;
+    g->MTR = g->tile / g->MT;
+    g->SG = g->tile - g->MT + rr;
     g->kpitch = g->R ? (int)((in->gw + 15) / 16 * 16) : (int)in->gw;
     const i64 nkeys = ntx * nty * g->MTR * g->MTR;
     if (nkeys >= (i64)0xFFFFFFF0ll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: grid too large for 32-bit bucket keys");
@@ -80,8 +89,8 @@ __device__ __forceinline__ bool bin_vis(const BinParams &P, double pu, double pv
         slice = (uint32_t)((wb * P.qpx + yf) * P.qpx + xf);
     }
     const i64 oxs = ox + P.gw - 1, oys = oy + P.gh - 1 - P.row0;
-    const int tx = (int)(oxs / TILE), ty = (int)(oys / TILE);
-    const int lx = (int)(oxs % TILE), ly = (int)(oys % TILE);
+    const int tx = (int)(oxs >> P.tshift), ty = (int)(oys >> P.tshift);
+    const int lx = (int)(oxs & ((1 << P.tshift) - 1)), ly = (int)(oys & ((1 << P.tshift) - 1));
     const uint32_t mt = (uint32_t)((ly >> P.mt_shift) * P.mtr + (lx >> P.mt_shift));
     const uint32_t mtm = (1u << P.mt_shift) - 1u, dx = (uint32_t)lx & mtm, dy = (uint32_t)ly & mtm;
     loc = (0x10000u << ((dy << P.mt_shift) | dx)) | ((uint32_t)ly << 8) | (uint32_t)lx;
@@ -272,7 +281,7 @@ int sk_plan_alloc(skagrid_ctx *ctx, const skagrid_geom *geom, i64 capacity, int 
     if (capacity < 0 || capacity >= (i64)0xFFFFFFF0ll) return sk_fail(ctx, SKAGRID_EINVAL, "plan: count %lld out of range", capacity);
     skagrid_plan *p = new skagrid_plan();
     memset(p, 0, sizeof *p);
-    int rc = sk_geom_init(ctx, geom, &p->g);
+    int rc = sk_geom_init(ctx, geom, capacity, &p->g);
     if (rc) { delete p; return rc; }
     p->capacity = capacity > 0 ? capacity : 1;
     p->slice_override = slice_override;
