@@ -350,8 +350,9 @@ __global__ void __launch_bounds__(256) degrid_warp_kernel(const GridArgs A) {
 // bounds checks), then its 16 half-warps take the item's records round-robin.  Grid cells are then conflict-free
 // 128-bit shared-memory loads (two wavefronts per 15-lane row instead of three unaligned L1 lines); only the kernel
 // taps still come from L2.
-template <int UNROLL>
-__global__ void __launch_bounds__(GRID_THREADS, 4) degrid_tile_kernel(const GridArgs A) {
+template <int UNROLL, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT) degrid_tile_kernel(const GridArgs A) {
+    constexpr int NHW = NT / 16;  // half-warps per block
     extern __shared__ double2 sg[];
     __shared__ uint32_t s_item;
     const int tid = threadIdx.x, hl = tid & 15, hw = tid >> 4;
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(GRID_THREADS, 4) degrid_tile_kernel(const Grid
         const WorkItem it = A.items[item];
         const int tyi = (int)(it.tile / (uint32_t)A.ntx), txi = (int)(it.tile % (uint32_t)A.ntx);
         const int gx0 = (txi << A.tshift) - (A.gw - 1), gy0 = (tyi << A.tshift) - (A.gh - 1);
-        for (int c = tid; c < SGW * SGH; c += GRID_THREADS) {
+        for (int c = tid; c < SGW * SGH; c += NT) {
             const int cy = c / SGW, cx = c - cy * SGW;
             const int gx = gx0 + cx, gy = gy0 + cy;
             double2 v = make_double2(0.0, 0.0);
@@ -375,9 +376,9 @@ __global__ void __launch_bounds__(GRID_THREADS, 4) degrid_tile_kernel(const Grid
         }
         __syncthreads();
         const uint32_t nrec = it.end - it.begin;
-        const uint32_t rounds = (nrec + 15u) / 16u;
+        const uint32_t rounds = (nrec + (uint32_t)NHW - 1u) / (uint32_t)NHW;
         for (uint32_t q = 0; q < rounds; ++q) {
-            const uint32_t r = q * 16u + (uint32_t)hw;  // both halves of a warp stay in the loop (shuffles below)
+            const uint32_t r = q * (uint32_t)NHW + (uint32_t)hw;  // both halves of a warp stay in the loop (shuffles below)
             const bool live = r < nrec;
             double ar = 0.0, ai = 0.0;
             uint32_t out_index = 0;
@@ -534,11 +535,21 @@ extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const do
         A.queue = 5;
         SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 5, 0, sizeof(uint32_t), st));
         static bool configured = false;
-        if (!configured) { SK_CUDA(ctx, cudaFuncSetAttribute(degrid_tile_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); configured = true; }
+        if (!configured) {
+            SK_CUDA(ctx, cudaFuncSetAttribute(degrid_tile_kernel<15, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            SK_CUDA(ctx, cudaFuncSetAttribute(degrid_tile_kernel<15, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = true;
+        }
         int per_sm = 0;
-        SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_tile_kernel<15>, GRID_THREADS, tile_smem));
-        if (per_sm < 1) per_sm = 1;
-        degrid_tile_kernel<15><<<ctx->sm_count * per_sm, GRID_THREADS, tile_smem, st>>>(A);
+        if (variant == 2) {
+            SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_tile_kernel<15, 256>, 256, tile_smem));
+            if (per_sm < 1) per_sm = 1;
+            degrid_tile_kernel<15, 256><<<ctx->sm_count * per_sm, 256, tile_smem, st>>>(A);
+        } else {
+            SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_tile_kernel<15, 128>, 128, tile_smem));
+            if (per_sm < 1) per_sm = 1;
+            degrid_tile_kernel<15, 128><<<ctx->sm_count * per_sm, 128, tile_smem, st>>>(A);
+        }
     } else {
         degrid_warp_kernel<15><<<ctx->sm_count * 8, 256, 0, st>>>(A);  // unroll 15 -> 2.9e9 vis/s, unroll 5 -> 2.1e9 (B200, S=15)
     }
