@@ -29,6 +29,12 @@
  * Haskell should bind with `foreign import ccall safe` (calls block for ms..s).
  *
  * Host-pointer functions ("skagrid_<name>") copy inputs H2D, compute, copy results D2H.
+ * Context-resident grid: skagrid_convgrid, skagrid_convgrid2, skagrid_convdegrid, skagrid_convdegrid2,
+ * skagrid_conv_imaging2 (grid_out) and skagrid_grid_to_image accept a NULL grid pointer, meaning "the grid the
+ * previous of these calls on this context left on the device" (no upload, no download; SKAGRID_EINVAL if there
+ * is none of that shape).  A chain conv_imaging2 -> grid_to_image -> convdegrid2 then moves only visibilities
+ * over PCIe, as the reference's single fused Accelerate program does.  skagrid_grid_to_image transforms in
+ * place, so afterwards the resident buffer holds the (complex) image plane.
  * Device-pointer functions ("skagrid_dev_<name>") work on device-resident buffers on a caller
  * stream and never synchronise the host unless documented (used by bench.py, the multi-GPU host
  * layer, and callers that keep kernels/grids resident across calls).

@@ -72,6 +72,30 @@ static int plan_acquire(skagrid_ctx *ctx, const skagrid_geom *geom, i64 capacity
 }
 static void plan_release(skagrid_ctx *, skagrid_plan *) {}  // stays cached; freed by skagrid_destroy
 
+// Context-resident grid: the host-pointer gridders / degridders / grid_to_image accept grid == NULL, meaning "the grid
+// the previous call on this context left on the device".  A chain conv_imaging2 -> grid_to_image -> convdegrid2 then
+// moves only visibilities over PCIe, like the single fused Accelerate program of the reference does.
+static int grid_in(skagrid_ctx *ctx, const double *host, i64 h, i64 w, void **dgrid, const char *what) {
+    const size_t bytes = (size_t)(h * w) * 16;
+    if (host) {
+        SK_TRY(up(ctx, "grid", host, bytes, dgrid));
+    } else {
+        if (ctx->resident_h != h || ctx->resident_w != w)
+            return sk_fail(ctx, SKAGRID_EINVAL, "%s: grid is NULL but the context holds no resident %lld x %lld grid", what, h, w);
+        SK_TRY(sk_scratch(ctx, "grid", bytes, dgrid));
+    }
+    ctx->resident_h = h; ctx->resident_w = w;
+    return SKAGRID_OK;
+}
+static int grid_fresh(skagrid_ctx *ctx, i64 h, i64 w, void **dgrid) {
+    const size_t bytes = (size_t)(h * w) * 16;
+    ctx->resident_h = ctx->resident_w = 0;
+    SK_TRY(sk_scratch(ctx, "grid", bytes, dgrid));
+    SK_CUDA(ctx, cudaMemsetAsync(*dgrid, 0, bytes, ctx->stream));
+    ctx->resident_h = h; ctx->resident_w = w;
+    return SKAGRID_OK;
+}
+
 #define NEED(ctx, cond, what) \
     do { if (!(cond)) return sk_fail((ctx), SKAGRID_EINVAL, "%s", (what)); } while (0)
 
@@ -199,6 +223,8 @@ static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double
     // the copy stream must not overwrite scratch that earlier work on the compute stream still uses
     e = cudaEventRecord(ctx->ev_done[0], ctx->stream);
     if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_done[1], ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_d2h[0], ctx->d2h_stream);
+    if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_d2h[1], ctx->d2h_stream);
     i64 ci = 0;
     for (i64 off = 0; off < count && e == cudaSuccess && !rc; off += chunk, ++ci) {
         const int b = (int)(ci & 1);
@@ -220,8 +246,13 @@ static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double
         rc = sk_plan_fill(ctx, plan, n, du[b], dv[b], wbin ? dwb[b] : nullptr, degrid ? nullptr : dvis[b], ctx->stream);
         if (!rc) {
             if (degrid) {
-                rc = skagrid_dev_degrid(ctx, plan, d_table, d_grid, dvis[b], ctx->stream);
-                if (!rc) e = cudaMemcpyAsync(vis_out + 2 * off, dvis[b], (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->stream);
+                // dvis[b] still holds the results of chunk c-2 until their D2H copy (on the third stream) is done
+                e = cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0);
+                if (e == cudaSuccess) rc = skagrid_dev_degrid(ctx, plan, d_table, d_grid, dvis[b], ctx->stream);
+                if (!rc && e == cudaSuccess) e = cudaEventRecord(ctx->ev_k[b], ctx->stream);
+                if (!rc && e == cudaSuccess) e = cudaStreamWaitEvent(ctx->d2h_stream, ctx->ev_k[b], 0);
+                if (!rc && e == cudaSuccess) e = cudaMemcpyAsync(vis_out + 2 * off, dvis[b], (size_t)n * 16, cudaMemcpyDeviceToHost, ctx->d2h_stream);
+                if (!rc && e == cudaSuccess) e = cudaEventRecord(ctx->ev_d2h[b], ctx->d2h_stream);
             } else {
                 rc = skagrid_dev_grid(ctx, plan, d_table, d_grid, 0, ctx->stream);
             }
@@ -231,6 +262,10 @@ static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     else cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->copy_stream);
+    {
+        const cudaError_t e2 = cudaStreamSynchronize(ctx->d2h_stream);
+        if (e == cudaSuccess) e = e2;
+    }
     plan_release(ctx, plan);
     if (rc) return rc;
     if (e != cudaSuccess) return sk_fail(ctx, SKAGRID_ECUDA, "table gridder: %s", cudaGetErrorString(e));
@@ -248,16 +283,16 @@ static int table_host(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 gh, i64 gw, const d
                       const double *u, const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, const char *what) {
     SK_TRY(enter(ctx));
     SK_TRY(check_table_args(ctx, nw, qpx, gh, gw, height, width, count));
-    NEED(ctx, gcf && grid, "NULL kernel table or grid");
+    NEED(ctx, gcf, "NULL kernel table");
     if (count > 0) NEED(ctx, u && v && (degrid ? vis_out != nullptr : vis != nullptr), "NULL visibility array");
     Timer t(ctx);
     void *dtab, *dgrid;
     const size_t tab_bytes = (size_t)(nw * qpx * qpx * gh * gw) * 16, grid_bytes = (size_t)(height * width) * 16;
     SK_TRY(up(ctx, "tab", gcf, tab_bytes, &dtab));
-    SK_TRY(up(ctx, "grid", grid, grid_bytes, &dgrid));
+    SK_TRY(grid_in(ctx, grid, height, width, &dgrid, what));
     skagrid_geom geom = {height, width, 0, height, nw, qpx, gh, gw};
     SK_TRY(stream_table(ctx, &geom, (double *)dtab, (double *)dgrid, count, u, v, wbin, vis, vis_out, degrid));
-    if (!degrid) SK_TRY(down(ctx, grid, dgrid, grid_bytes));
+    if (!degrid && grid) SK_TRY(down(ctx, grid, dgrid, grid_bytes));
     SK_TRY(t.finish());
     return check_flags(ctx, what);
 }
@@ -297,7 +332,7 @@ extern "C" int skagrid_grid(skagrid_ctx *ctx, int64_t height, int64_t width, dou
     void *dvis, *dgrid;
     SK_TRY(up_uvw(ctx, count, u, v, nullptr, &du, &dv, &dw));
     SK_TRY(up(ctx, "pre_vis", vis, (size_t)count * 16, &dvis));
-    SK_TRY(up(ctx, "grid", grid, (size_t)(height * width) * 16, &dgrid));
+    SK_TRY((ctx->resident_h = ctx->resident_w = 0, up(ctx, "grid", grid, (size_t)(height * width) * 16, &dgrid)));  // overwrites the resident grid
     SK_TRY(sk_grid_simple_dev(ctx, height, width, (double *)dgrid, count, du, dv, (double *)dvis, ctx->stream));
     SK_TRY(down(ctx, grid, dgrid, (size_t)(height * width) * 16));
     return t.finish();
@@ -350,7 +385,7 @@ static int aw_host(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 s, const double *wkern
     void *dwk, *dak, *dgrid, *du, *dv, *dwb, *da1, *da2, *dvis;
     SK_TRY(up(ctx, "aw_wk", wkerns, (size_t)(nw * qpx * qpx * s * s) * 16, &dwk));
     SK_TRY(up(ctx, "aw_ak", akerns, (size_t)(nant * s * s) * 16, &dak));
-    SK_TRY(up(ctx, "grid", grid, (size_t)(height * width) * 16, &dgrid));
+    SK_TRY((ctx->resident_h = ctx->resident_w = 0, up(ctx, "grid", grid, (size_t)(height * width) * 16, &dgrid)));  // overwrites the resident grid
     SK_TRY(up(ctx, "pre_u", u, (size_t)count * 8, &du));
     SK_TRY(up(ctx, "pre_v", v, (size_t)count * 8, &dv));
     SK_TRY(up(ctx, "aw_wb", wbin, (size_t)count * 8, &dwb));
@@ -423,7 +458,7 @@ extern "C" int skagrid_make_grid_hermitian(skagrid_ctx *ctx, int64_t n, const do
     NEED(ctx, n > 0 && grid && out, "make_grid_hermitian: bad size or NULL pointer");
     Timer t(ctx);
     void *dg;
-    SK_TRY(up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg));
+    SK_TRY((ctx->resident_h = ctx->resident_w = 0, up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg)));  // overwrites the resident grid
     SK_TRY(sk_hermitian_dev(ctx, n, (double *)dg, (double *)dg, ctx->stream));
     SK_TRY(down(ctx, out, dg, (size_t)(n * n) * 16));
     return t.finish();
@@ -434,7 +469,7 @@ extern "C" int skagrid_ifft(skagrid_ctx *ctx, int64_t n, const double *grid, dou
     NEED(ctx, n > 0 && grid && out, "ifft: bad size or NULL pointer");
     Timer t(ctx);
     void *dg;
-    SK_TRY(up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg));
+    SK_TRY((ctx->resident_h = ctx->resident_w = 0, up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg)));  // overwrites the resident grid
     SK_TRY(sk_fft2c_dev(ctx, n, (double *)dg, (double *)dg, 1, ctx->stream));
     SK_TRY(down(ctx, out, dg, (size_t)(n * n) * 16));
     return t.finish();
@@ -448,7 +483,7 @@ extern "C" int skagrid_fft(skagrid_ctx *ctx, int64_t n, const double *grid, doub
     i64 big = 1;
     while (big < n) big <<= 1;
     void *dg;
-    SK_TRY(up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg));
+    SK_TRY((ctx->resident_h = ctx->resident_w = 0, up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg)));  // overwrites the resident grid
     if (big == n) {
         SK_TRY(sk_fft2c_dev(ctx, n, (double *)dg, (double *)dg, 0, ctx->stream));
         SK_TRY(down(ctx, out, dg, (size_t)(n * n) * 16));
@@ -465,10 +500,10 @@ extern "C" int skagrid_fft(skagrid_ctx *ctx, int64_t n, const double *grid, doub
 
 extern "C" int skagrid_grid_to_image(skagrid_ctx *ctx, int64_t n, const double *grid, double *image, double *max_out) {
     SK_TRY(enter(ctx));
-    NEED(ctx, n > 0 && grid, "grid_to_image: bad size or NULL grid");
+    NEED(ctx, n > 0, "grid_to_image: bad size");
     Timer t(ctx);
     void *dg, *dimg = nullptr, *dmax;
-    SK_TRY(up(ctx, "grid", grid, (size_t)(n * n) * 16, &dg));
+    SK_TRY(grid_in(ctx, grid, n, n, &dg, "grid_to_image"));
     if (image) SK_TRY(sk_scratch(ctx, "image", (size_t)(n * n) * 8, &dimg));
     SK_TRY(sk_scratch(ctx, "image_max", 16, &dmax));
     SK_TRY(sk_grid_to_image_dev(ctx, n, (double *)dg, (double *)dimg, (double *)dmax, ctx->stream));
@@ -492,7 +527,7 @@ extern "C" int skagrid_simple_imaging(skagrid_ctx *ctx, double theta, int64_t la
     (void)w;
     Timer t(ctx);
     void *dgrid;
-    SK_TRY(sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid));
+    SK_TRY((ctx->resident_h = ctx->resident_w = 0, sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid)));  // overwrites the resident grid
     SK_CUDA(ctx, cudaMemsetAsync(dgrid, 0, (size_t)(n * n) * 16, ctx->stream));
     if (count > 0) {
         NEED(ctx, u && v && vis, "simple_imaging: NULL visibility array");
@@ -520,7 +555,7 @@ extern "C" int skagrid_conv_imaging(skagrid_ctx *ctx, int64_t qpx, int64_t gh, i
     Timer t(ctx);
     void *dgrid, *dtab;
     SK_TRY(up(ctx, "tab", gcf, (size_t)(qpx * qpx * gh * gw) * 16, &dtab));
-    SK_TRY(sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid));
+    SK_TRY((ctx->resident_h = ctx->resident_w = 0, sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid)));  // overwrites the resident grid
     SK_CUDA(ctx, cudaMemsetAsync(dgrid, 0, (size_t)(n * n) * 16, ctx->stream));
     if (count > 0) {
         NEED(ctx, u && v && vis, "conv_imaging: NULL visibility array");
@@ -554,17 +589,16 @@ extern "C" int skagrid_conv_imaging2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, 
     SK_TRY(enter(ctx));
     const i64 n = grid_side(theta, lam);
     SK_TRY(check_table_args(ctx, nw, qpx, gh, gw, n, n, count));
-    NEED(ctx, gcf && grid_out, "conv_imaging2: NULL kernel or grid");
+    NEED(ctx, gcf, "conv_imaging2: NULL kernel table");
     if (count > 0) NEED(ctx, u && v && wbin && vis, "conv_imaging2: NULL visibility array");
     (void)w;
     Timer t(ctx);
     void *dgrid, *dtab;
     SK_TRY(up(ctx, "tab", gcf, (size_t)(nw * qpx * qpx * gh * gw) * 16, &dtab));
-    SK_TRY(sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid));
-    SK_CUDA(ctx, cudaMemsetAsync(dgrid, 0, (size_t)(n * n) * 16, ctx->stream));
+    SK_TRY(grid_fresh(ctx, n, n, &dgrid));
     skagrid_geom geom = {n, n, 0, n, nw, qpx, gh, gw};
     SK_TRY(stream_table(ctx, &geom, (double *)dtab, (double *)dgrid, count, u, v, wbin, vis, nullptr, 0, (double)lam));
-    SK_TRY(down(ctx, grid_out, dgrid, (size_t)(n * n) * 16));
+    if (grid_out) SK_TRY(down(ctx, grid_out, dgrid, (size_t)(n * n) * 16));
     SK_TRY(t.finish());
     return check_flags(ctx, "conv_imaging2");
 }
@@ -606,7 +640,7 @@ extern "C" int skagrid_aw_gridding(skagrid_ctx *ctx, double theta, int64_t lam, 
     SK_TRY(up(ctx, "aw_wk", wkerns, (size_t)(nw * qpx * qpx * s * s) * 16, &dwk));
     SK_TRY(up(ctx, "aw_ak", akerns, (size_t)(nant * s * s) * 16, &dak));
     SK_TRY(up(ctx, "aw_wbins", wbins, (size_t)nw * 8, &dwbins));
-    SK_TRY(sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid));
+    SK_TRY((ctx->resident_h = ctx->resident_w = 0, sk_scratch(ctx, "grid", (size_t)(n * n) * 16, &dgrid)));  // overwrites the resident grid
     SK_CUDA(ctx, cudaMemsetAsync(dgrid, 0, (size_t)(n * n) * 16, ctx->stream));
     SK_TRY(up(ctx, "pre_u", u_m, (size_t)count * 8, &du));
     SK_TRY(up(ctx, "pre_v", v_m, (size_t)count * 8, &dv));

@@ -89,6 +89,8 @@ struct skagrid_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;      // compute stream
     cudaStream_t copy_stream = nullptr; // H2D prefetch stream of the chunked host API
+    cudaStream_t d2h_stream = nullptr;  // D2H stream of the chunked degridder (results leave while the next chunk computes)
+    cudaEvent_t ev_k[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::string err;
     uint32_t *d_flags = nullptr;        // device error word: bit0 index out of range, bit1 cell outside the weight grid
@@ -97,6 +99,7 @@ struct skagrid_ctx {
     std::map<std::string, DevBuf> pool;   // named scratch buffers, grown on demand, freed at destroy
     std::map<i64, cufftHandle> fft_plans; // n -> Z2Z n x n plan
     std::map<i64, DevBuf> fft_work;
+    i64 resident_h = 0, resident_w = 0;   // shape of the grid the last host-pointer call left in the "grid" scratch (0: none)
     skagrid_plan *cached_plan = nullptr;  // plan kept between host-pointer calls (api.cu plan_acquire)
 };
 

@@ -62,10 +62,13 @@ extern "C" int skagrid_create(int device, skagrid_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&ctx->d2h_stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i)
         ok = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_flags, 16 * sizeof(uint32_t)) == cudaSuccess && cudaMemset(ctx->d_flags, 0, 16 * sizeof(uint32_t)) == cudaSuccess;
     if (!ok) { skagrid_destroy(ctx); return sk_fail(nullptr, SKAGRID_ECUDA, "stream/event creation failed"); }
     *out = ctx;
@@ -83,11 +86,14 @@ extern "C" void skagrid_destroy(skagrid_ctx *ctx) {
     for (int i = 0; i < 2; ++i) {
         if (ctx->ev_copy[i]) cudaEventDestroy(ctx->ev_copy[i]);
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
+        if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
+        if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
     }
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->d2h_stream) cudaStreamDestroy(ctx->d2h_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }

@@ -385,3 +385,35 @@ def test_two_gpu_torchrun_if_available():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29511", os.path.join(root, "tests", "mgpu_check.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_context_resident_grid_chain(G, orc):
+    """grid == NULL chains conv_imaging2 -> grid_to_image / convdegrid2 on the grid left on the device."""
+    import ctypes as C
+    from ska_sdp_accelerate_gridding_b200 import _lib
+    from ska_sdp_accelerate_gridding_b200.context import get_context
+    ctx = get_context()
+    rng = np.random.default_rng(61)
+    theta, lam, nw, q, s, cnt = 0.02, 6400, 3, 4, 15, 5000   # N = 128
+    n = 128
+    gcf = _rand_c(rng, (nw, q, q, s, s))
+    u, v = rng.uniform(-0.45, 0.45, cnt) * lam, rng.uniform(-0.45, 0.45, cnt) * lam
+    wb = rng.integers(0, nw, cnt)
+    vis = _rand_c(rng, cnt)
+    p = lambda a: a.ctypes.data
+    ctx.check(ctx.lib.skagrid_conv_imaging2(ctx.h, nw, q, s, s, p(gcf), theta, lam, cnt, p(u), p(v), p(u), p(wb), p(vis), None))
+    og = orc.convgrid(gcf, np.zeros((n, n), complex), u / lam, v / lam, vis, wbin=wb)
+    pu, pv = u / lam, v / lam
+    out = np.empty(cnt, complex)
+    ctx.check(ctx.lib.skagrid_convdegrid2(ctx.h, nw, q, s, s, p(gcf), n, n, None, cnt, p(pu), p(pv), p(wb), p(out)))
+    assert rel_err(out, orc.convdegrid(gcf, og, pu, pv, wbin=wb)) < TOL
+    mx = np.zeros(1)
+    img = np.empty((n, n))
+    ctx.check(ctx.lib.skagrid_grid_to_image(ctx.h, n, None, p(img), p(mx)))
+    oimg = np.real(orc.ifft(orc.make_grid_hermitian(og)))
+    assert rel_err(img, oimg) < TOL
+    # a call that overwrites the scratch invalidates the resident grid; a wrong shape is refused
+    G.make_grid_hermitian(np.zeros((8, 8), complex))
+    assert ctx.lib.skagrid_grid_to_image(ctx.h, n, None, None, p(mx)) == -1
+    with pytest.raises(_lib.SkagridError):
+        ctx.check(ctx.lib.skagrid_convdegrid2(ctx.h, nw, q, s, s, p(gcf), 64, 64, None, cnt, p(pu), p(pv), p(wb), p(out)))
