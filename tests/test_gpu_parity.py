@@ -417,3 +417,17 @@ def test_context_resident_grid_chain(G, orc):
     assert ctx.lib.skagrid_grid_to_image(ctx.h, n, None, None, p(mx)) == -1
     with pytest.raises(_lib.SkagridError):
         ctx.check(ctx.lib.skagrid_convdegrid2(ctx.h, nw, q, s, s, p(gcf), 64, 64, None, cnt, p(pu), p(pv), p(wb), p(out)))
+
+
+def test_c_abi_from_plain_c(tmp_path):
+    """The boundary is a C ABI: compile tests/c_abi_smoke.c with gcc against include/skagrid.h and run it."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "ska_sdp_accelerate_gridding_b200")
+    exe = str(tmp_path / "c_abi_smoke")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "c_abi_smoke.c"),
+                        "-L" + pkg, "-lskagrid", "-lm", "-Wl,-rpath," + pkg, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "c_abi_smoke ok" in r.stdout
