@@ -56,7 +56,10 @@ struct Geom {
     int SG;              // shared-memory subgrid edge = tile - MT + R
     int kpitch;          // row pitch (taps) of the padded copy of the kernel table the kernels read: gw rounded up to 16
                          // (rows start on 256-byte boundaries: a 15-tap row is 2 L1 lines instead of up to 3); gw if R == 0
-    i64 nkeys;           // ntx * nty * MTR * MTR
+    int kpt;             // bucket keys per uv tile: MTR*MTR (micro-tile buckets) or tile*tile (cell buckets, `cellsort`)
+    int cellsort;        // records are additionally grouped by exact footprint origin inside each micro-tile (lets the
+                         // degridder keep its grid column in registers across a run of same-cell visibilities)
+    i64 nkeys;           // ntx * nty * kpt
     int normalise;
 };
 

@@ -411,6 +411,85 @@ __global__ void __launch_bounds__(NT, 1024 / NT) degrid_tile_kernel(const GridAr
     }
 }
 
+// Degridder, register-resident grid column (gh, gw <= 16; plans with cell-granular buckets): as degrid_tile_kernel,
+// but every half-warp takes a CONTIGUOUS run of the item's records, which the plan has grouped by exact footprint
+// origin, and keeps its column of the footprint's grid cells (gh complex values per lane) in registers while the origin
+// does not change.  In dense uv regions hundreds of consecutive visibilities share the origin, so the per-visibility
+// work is just the tap stream: gh 128-bit loads and 4*gh FMAs per lane -- half of the L1/shared-memory wavefronts of
+// the tiled kernel, which is bound by exactly that pipe.
+template <int GH, int NT, int MINB, bool EXACT>
+__global__ void __launch_bounds__(NT, MINB) degrid_reg_kernel(const GridArgs A) {
+    // EXACT: gh == GH, so the row loops carry no predicate; the padded table (pitch 16 >= gw, zero pad columns) lets every
+    // lane load its tap unconditionally, lanes >= gw just read the pad
+    constexpr int NHW = NT / 16;
+    extern __shared__ double2 sg[];
+    __shared__ uint32_t s_item;
+    const int tid = threadIdx.x, hl = tid & 15, hw = tid >> 4;
+    const int SGW = A.tile - 1 + A.gw, SGH = A.tile - 1 + A.gh;
+    const uint32_t n_items = A.counters[0];
+    const bool col = hl < A.gw;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = atomicAdd(&A.counters[A.queue], 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_items) break;
+        const WorkItem it = A.items[item];
+        const int tyi = (int)(it.tile / (uint32_t)A.ntx), txi = (int)(it.tile % (uint32_t)A.ntx);
+        const int gx0 = (txi << A.tshift) - (A.gw - 1), gy0 = (tyi << A.tshift) - (A.gh - 1);
+        for (int c = tid; c < SGW * SGH; c += NT) {
+            const int cy = c / SGW, cx = c - cy * SGW;
+            const int gx = gx0 + cx, gy = gy0 + cy;
+            double2 v = make_double2(0.0, 0.0);
+            if ((unsigned)gx < (unsigned)A.width && (unsigned)gy < (unsigned)A.nrows) v = ldg2(A.grid + (size_t)gy * A.width + gx);
+            sg[c] = v;
+        }
+        __syncthreads();
+        const uint32_t nrec = it.end - it.begin;
+        const uint32_t chunk = (nrec + (uint32_t)NHW - 1u) / (uint32_t)NHW;  // contiguous records per half-warp
+        const uint32_t r0 = (uint32_t)hw * chunk;
+        double2 g[GH];
+#pragma unroll
+        for (int i = 0; i < GH; ++i) g[i] = make_double2(0.0, 0.0);
+        uint32_t cur = 0xFFFFFFFFu;
+        for (uint32_t q = 0; q < chunk; ++q) {  // both halves of a warp run the same trip count (shuffles below)
+            const uint32_t r = r0 + q;
+            const bool live = r < nrec;
+            double ar = 0.0, ai = 0.0;
+            uint32_t out_index = 0;
+            if (live) {
+                const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(A.rec + it.begin + r) + 1);
+                out_index = meta.z;
+                const uint32_t origin = meta.y & 0xFFFFu;
+                if (origin != cur) {  // half-warp-uniform: (re)load this lane's column of the footprint
+                    cur = origin;
+                    const int lx = (int)(origin & 255u), ly = (int)(origin >> 8);
+                    const double2 *gp = sg + ly * SGW + lx + hl;
+#pragma unroll
+                    for (int i = 0; i < GH; ++i) g[i] = (col && (EXACT || i < A.gh)) ? gp[i * SGW] : make_double2(0.0, 0.0);
+                }
+                const int lx = (int)(origin & 255u), ly = (int)(origin >> 8);
+                const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
+                const double2 *kp = A.table + (uint32_t)(meta.x + dy * (uint32_t)A.kpitch + dx + (uint32_t)hl);
+                double2 k[GH];
+#pragma unroll
+                for (int i = 0; i < GH; ++i) k[i] = (EXACT || i < A.gh) ? ldg2(kp + i * A.kpitch) : make_double2(0.0, 0.0);
+#pragma unroll
+                for (int i = 0; i < GH; ++i) {  // conj(k) * g
+                    ar = fma(k[i].x, g[i].x, ar); ar = fma(k[i].y, g[i].y, ar);
+                    ai = fma(k[i].x, g[i].y, ai); ai = fma(-k[i].y, g[i].x, ai);
+                }
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                ar += __shfl_xor_sync(0xffffffffu, ar, o);
+                ai += __shfl_xor_sync(0xffffffffu, ai, o);
+            }
+            if (live && hl == 0) A.vis_out[out_index] = make_double2(ar, ai);
+        }
+    }
+}
+
 // Padded copy of the caller's kernel table: [slice][gh][kpitch], zero in the pad columns.  A few MB for a w-kernel
 // table (microseconds), one S x S kernel per visibility on the AW path.
 __global__ void __launch_bounds__(256) pad_table_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, i64 nslices, int gh, int gw,
@@ -528,10 +607,26 @@ extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const do
     SK_TRY(prepare_table(ctx, plan, table, st, &ptab));
     GridArgs A = make_args(plan, ptab, const_cast<double *>(grid));
     A.vis_out = reinterpret_cast<double2 *>(vis_out);
-    // SKAGRID_DEGRID_VARIANT=1 selects the untiled kernel (A/B measurements; B200, S=15: tiled 28.6 ms, untiled 35.1 ms per 1e8)
+    // SKAGRID_DEGRID_VARIANT (A/B measurements): 0 register-column kernel when applicable (4 blocks/SM, 128 registers),
+    // 4 the same squeezed to 5 blocks/SM, 3 tiled (128 threads), 2 tiled (256 threads), 1 untiled.
+    // B200, S=15, 1e8 visibilities: untiled 35.1 ms, tiled 28.6 ms, register-column 23.9 ms (5 blocks: 25.1 ms)
     static const int variant = getenv("SKAGRID_DEGRID_VARIANT") ? atoi(getenv("SKAGRID_DEGRID_VARIANT")) : 0;
     const size_t tile_smem = (size_t)(A.tile - 1 + A.gw) * (A.tile - 1 + A.gh) * sizeof(double2);
-    if (variant != 1 && tile_smem <= 200 * 1024) {
+    if (variant != 1 && variant != 2 && variant != 3 && plan->g.cellsort && A.gh <= 16 && A.gw <= 16 && A.kpitch == 16 && tile_smem <= 48 * 1024) {
+        A.queue = 5;
+        SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 5, 0, sizeof(uint32_t), st));
+        int per_sm = 0;
+        if (A.gh == 15 && variant == 4) {
+            SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_reg_kernel<15, 128, 5, true>, 128, tile_smem));
+            degrid_reg_kernel<15, 128, 5, true><<<ctx->sm_count * (per_sm < 1 ? 1 : per_sm), 128, tile_smem, st>>>(A);
+        } else if (A.gh == 15) {
+            SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_reg_kernel<15, 128, 4, true>, 128, tile_smem));
+            degrid_reg_kernel<15, 128, 4, true><<<ctx->sm_count * (per_sm < 1 ? 1 : per_sm), 128, tile_smem, st>>>(A);
+        } else {
+            SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_reg_kernel<16, 128, 4, false>, 128, tile_smem));
+            degrid_reg_kernel<16, 128, 4, false><<<ctx->sm_count * (per_sm < 1 ? 1 : per_sm), 128, tile_smem, st>>>(A);
+        }
+    } else if (variant != 1 && tile_smem <= 200 * 1024) {
         A.queue = 5;
         SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 5, 0, sizeof(uint32_t), st));
         static bool configured = false;

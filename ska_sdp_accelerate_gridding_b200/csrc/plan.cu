@@ -19,6 +19,7 @@ struct BinParams {
     int ntx, nty, normalise, slice_override;
     int mt_shift, mtr;  // micro-tile edge = 1 << mt_shift; micro-tiles per tile row
     int tshift;         // log2 of the uv tile edge
+    int kpt, cellsort;  // bucket keys per tile; cell-granular buckets
 };
 
 static BinParams make_bin_params(const Geom &g, int slice_override) {
@@ -32,7 +33,7 @@ static BinParams make_bin_params(const Geom &g, int slice_override) {
     p.qpx = g.qpx; p.width = g.width; p.height = g.height; p.row0 = g.row0; p.row1 = g.row1;
     p.gh = g.gh; p.gw = g.gw; p.halfgh = g.gh / 2; p.halfgw = g.gw / 2; p.nw = g.nw;
     p.ntx = g.ntx; p.nty = g.nty; p.normalise = g.normalise; p.slice_override = slice_override;
-    p.mt_shift = g.MT == 4 ? 2 : 1; p.mtr = g.MTR; p.kpitch = g.kpitch; p.tshift = g.tshift;
+    p.mt_shift = g.MT == 4 ? 2 : 1; p.mtr = g.MTR; p.kpitch = g.kpitch; p.tshift = g.tshift; p.kpt = g.kpt; p.cellsort = g.cellsort;
     return p;
 }
 
@@ -65,7 +66,11 @@ int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, i64 capacity, Geom *g
     g->MTR = g->tile / g->MT;
     g->SG = g->tile - g->MT + rr;
     g->kpitch = g->R ? (int)((in->gw + 15) / 16 * 16) : (int)in->gw;
-    const i64 nkeys = ntx * nty * g->MTR * g->MTR;
+    // cell-granular buckets when the offset table stays small (<= 2^27 keys, 0.5 GB); else micro-tile buckets
+    g->cellsort = (ntx * nty * (i64)g->tile * g->tile <= ((i64)1 << 27)) ? 1 : 0;
+    if (const char *e = getenv("SKAGRID_CELLSORT")) g->cellsort = atoi(e) ? 1 : 0;  // tuning experiments
+    g->kpt = g->cellsort ? g->tile * g->tile : g->MTR * g->MTR;
+    const i64 nkeys = ntx * nty * g->kpt;
     if (nkeys >= (i64)0xFFFFFFF0ll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: grid too large for 32-bit bucket keys");
     if (in->nw * in->qpx * in->qpx * in->gh * g->kpitch >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel table has more than 2^32 taps");
     g->ntx = (int)ntx; g->nty = (int)nty; g->nkeys = nkeys; g->normalise = 1;
@@ -96,7 +101,8 @@ __device__ __forceinline__ bool bin_vis(const BinParams &P, double pu, double pv
     loc = (0x10000u << ((dy << P.mt_shift) | dx)) | ((uint32_t)ly << 8) | (uint32_t)lx;
     // element offset of tap (-dy, -dx) of the slice, modulo 2^32: the gridder adds its per-thread tap offset
     slice = slice * (uint32_t)(P.gh * P.kpitch) - (dy * (uint32_t)P.kpitch + dx);
-    key = (uint32_t)(ty * P.ntx + tx) * (uint32_t)(P.mtr * P.mtr) + mt;
+    // micro-tile major; inside the micro-tile optionally by exact origin (dy, dx)
+    key = (uint32_t)(ty * P.ntx + tx) * (uint32_t)P.kpt + (P.cellsort ? ((mt << (2 * P.mt_shift)) | (dy << P.mt_shift) | dx) : mt);
     return true;
 }
 
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(BinParams P, i64 count
         // halves the store instructions the LSU has to queue compared with two 128-bit stores
         const unsigned long long q0 = (unsigned long long)__double_as_longlong(vv.x), q1 = (unsigned long long)__double_as_longlong(vv.y);
         const unsigned long long q2 = (unsigned long long)slice | ((unsigned long long)loc << 32);
-        const unsigned long long q3 = (unsigned long long)(uint32_t)k | ((unsigned long long)(key / (uint32_t)(P.mtr * P.mtr)) << 32);
+        const unsigned long long q3 = (unsigned long long)(uint32_t)k | ((unsigned long long)(key / (uint32_t)P.kpt) << 32);
         asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(rec + pos), "l"(q0), "l"(q1), "l"(q2), "l"(q3) : "memory");
     }
 }
@@ -272,7 +278,7 @@ int sk_plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double *u, 
         SK_LAUNCH_CHECK(ctx);
     }
     const int ntiles = g.ntx * g.nty;
-    make_items_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(p->d_offs, ntiles, g.MTR * g.MTR, p->d_items, p->d_counters, (uint32_t)p->max_items);
+    make_items_kernel<<<(ntiles + 255) / 256, 256, 0, st>>>(p->d_offs, ntiles, g.kpt, p->d_items, p->d_counters, (uint32_t)p->max_items);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
