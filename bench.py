@@ -310,11 +310,11 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     alg_bytes = BYTES_PER_VIS * V + 16 * N_GRID * N_GRID + table.numel() * 16
     traffic = None   # dram__bytes_read+write of the gridder per launch, from the committed ncu capture of this workload
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_v5_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_v21_traffic.json")
     if os.path.exists(tpath) and N_GRID == 8192 and SUPPORT == 15 and not args.uniform and args.variant == 0:
         tj = json.load(open(tpath))
         if int(tj.get("vis_per_launch", 0)) == V:
-            k = tj["grid_tiled_kernel<16,2>"]
+            k = tj["grid_tiled_kernel"]
             traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {
