@@ -54,7 +54,7 @@ int sk_convolve2d_dev(skagrid_ctx *ctx, i64 n, i64 count, const double *a, const
     if (count <= 0) return SKAGRID_OK;
     if (n <= 0 || n > 64) return sk_fail(ctx, SKAGRID_EINVAL, "convolve2d: size %lld outside [1,64]", n);
     const size_t smem = (size_t)(2 * n * n) * sizeof(double2);
-    if (smem > 48 * 1024) SK_CUDA(ctx, cudaFuncSetAttribute(convolve2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > 48 * 1024) SK_CUDA(ctx, cudaFuncSetAttribute(convolve2d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per call: cheap, and correct on any device
     convolve2d_kernel<<<(unsigned)count, 256, smem, st>>>((int)n, (const double2 *)a, ai, (const double2 *)b, bi, (double2 *)out, conj_out);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;

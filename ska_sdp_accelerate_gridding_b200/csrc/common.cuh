@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -103,6 +104,7 @@ struct skagrid_ctx {
     std::map<i64, cufftHandle> fft_plans; // n -> Z2Z n x n plan
     std::map<i64, DevBuf> fft_work;
     i64 resident_h = 0, resident_w = 0;   // shape of the grid the last host-pointer call left in the "grid" scratch (0: none)
+    std::set<const void *> smem_configured;  // kernels whose dynamic shared-memory limit was raised on this device
     skagrid_plan *cached_plan = nullptr;  // plan kept between host-pointer calls (api.cu plan_acquire)
 };
 

@@ -8,16 +8,18 @@
 // B200 design (not a translation):
 //  * the plan (plan.cu) has already grouped the visibilities per uv tile and per MT x MT micro-tile;
 //  * a persistent thread block pulls work items (runs of <= CHUNK records of one tile) from a queue and
-//    owns a (TILE-MT+R)^2 complex-double subgrid in shared memory for the duration of the item;
+//    owns a (tile-MT+R)^2 complex-double subgrid in shared memory for the duration of the item (tile = 16 or
+//    32 footprint origins per dimension, chosen per plan);
 //  * inside the block every subgrid cell is owned by exactly one thread for the whole item, by residue:
 //    cell (cy, cx) belongs to the thread with (cy mod R, cx mod R) in its residue set.  A footprint of
 //    S <= R-MT+1 taps per dimension covers each residue at most once, so a thread has at most one tap per
 //    residue per visibility, accumulates it in REGISTERS while the micro-tile stays the same, and folds
 //    the registers into its own shared-memory cells when it changes -- no atomics, no barriers, no bank
 //    conflicts in the hot loop;
-//  * the kernel taps are 128-bit loads; the 16 threads of a row read 16 consecutive taps of the slice; the
-//    loop is software-pipelined (records two ahead, taps one ahead) so the L2 latency of the tap loads is
-//    covered by the FMAs of the previous visibility;
+//  * the kernel taps are 128-bit loads from a padded copy of the table (rows on 256-byte boundaries); the 16
+//    threads of a row read 16 consecutive taps of the slice; records are staged through shared memory with
+//    cp.async and DEPTH tap slots rotate per residue, so DEPTH x residues loads per thread are in flight before
+//    the first FMA needs one;
 //  * at the end of the item the subgrid is added to the grid in HBM/L2 with fp64 RED (no return value).
 //    Dense tiles are split over many blocks for load balance, which is why the flush is a reduction and
 //    not a plain store; its share of the runtime is small (one flush per <= 4096 visibilities).
@@ -548,11 +550,8 @@ template <int R, int MT, int DEPTH, int TY>
 static int launch_tiled(skagrid_ctx *ctx, const GridArgs &A, cudaStream_t st) {
     constexpr int NT = 16 * TY;
     const size_t smem = (size_t)A.SG * A.SG * sizeof(double2);
-    static bool configured = false;
-    if (!configured) {
+    if (ctx->smem_configured.insert((const void *)grid_tiled_kernel<R, MT, DEPTH, TY>).second)  // per device, hence per context
         SK_CUDA(ctx, cudaFuncSetAttribute(grid_tiled_kernel<R, MT, DEPTH, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
     int per_sm = 0;
     SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_tiled_kernel<R, MT, DEPTH, TY>, NT, smem));
     if (per_sm < 1) return sk_fail(ctx, SKAGRID_ECUDA, "tiled gridder does not fit on an SM (smem %zu)", smem);
@@ -629,11 +628,9 @@ extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const do
     } else if (variant != 1 && tile_smem <= 200 * 1024) {
         A.queue = 5;
         SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 5, 0, sizeof(uint32_t), st));
-        static bool configured = false;
-        if (!configured) {
+        if (ctx->smem_configured.insert((const void *)degrid_tile_kernel<15, 256>).second) {
             SK_CUDA(ctx, cudaFuncSetAttribute(degrid_tile_kernel<15, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             SK_CUDA(ctx, cudaFuncSetAttribute(degrid_tile_kernel<15, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            configured = true;
         }
         int per_sm = 0;
         if (variant == 2) {
