@@ -109,6 +109,7 @@ def cpu_reference_rate(sample, u, v, wb, vis, table):
     """The reference semantics on the host cores (oracle/oracle.c, OpenMP): grid + degrid of `sample`
     visibilities on the same 8192^2 grid and kernel table.  Returns (vis/s, threads, seconds)."""
     from oracle import oracle as orc
+    orc.use_all_cores()
     grid0 = np.zeros((N_GRID, N_GRID), np.complex128)
     t0 = time.perf_counter()
     g = orc.convgrid(table, grid0, u, v, vis, wbin=wb, parallel=True)

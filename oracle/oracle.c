@@ -346,6 +346,15 @@ void orc_make_grid_hermitian(i64 n, const double *g, double *out) {
  * visibility order) and the bands are claimed dynamically by the threads.  Per-cell summation
  * order is visibility order, as in orc_convgrid2, so the result is bit-identical to it.
  * ========================================================================= */
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline wants every host core it may use */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

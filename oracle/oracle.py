@@ -76,6 +76,13 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def use_all_cores() -> int:
+    """Let OpenMP use every core this process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().orc_set_num_threads(C.c_int(n))
+    return num_threads()
+
+
 # ----------------------------------------------------------------------------- binning
 def frac_coord(n, qpx, p, normalise=True):
     """src/Gridding.hs:126-140.  Returns (fl, frac) int64 arrays."""
