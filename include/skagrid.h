@@ -234,6 +234,20 @@ int skagrid_dev_synth_vis(skagrid_ctx *ctx, uint64_t seed, int64_t first, int64_
                           int64_t support, int64_t nw, int uniform, double *u, double *v,
                           int64_t *wbin, double *vis, void *stream);
 
+/* Pre-steps on device arrays (same kernels as the host-pointer functions): (u,v,w) *= a or /= a (uvw_lambda with
+ * a = f/299792458.0, src/ImageDataset.hs:181-187; div3 with a = lam, src/Gridding.hs:838-839), mirror_uvw (:551-562;
+ * d_vis may be NULL), findClosest (:895-907), doweight (:564-583).  Range problems (a visibility outside the weight
+ * grid, an index out of range in a plan) are recorded in the context's device error word: skagrid_dev_take_error
+ * reads and clears it (bit 0: index out of range, bit 1: outside the weight grid) and synchronises `stream`. */
+int skagrid_dev_uvw_scale(skagrid_ctx *ctx, int64_t count, double *d_u, double *d_v, double *d_w, double a,
+                          int divide, void *stream);
+int skagrid_dev_mirror_uvw(skagrid_ctx *ctx, int64_t count, double *d_u, double *d_v, double *d_w, double *d_vis,
+                           void *stream);
+int skagrid_dev_find_closest(skagrid_ctx *ctx, int64_t nw, const double *d_wbins, int64_t count, const double *d_w,
+                             int64_t *d_out, void *stream);
+int skagrid_dev_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u,
+                         const double *d_v, double *d_vis, void *stream);
+int skagrid_dev_take_error(skagrid_ctx *ctx, void *stream, int *flags_out);
 /* frac_coord (src/Gridding.hs:126-140) on device arrays. */
 int skagrid_dev_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, int64_t count, const double *d_p,
                            int64_t *d_fl, int64_t *d_frac, int flags, void *stream);

@@ -65,6 +65,11 @@ _SIGS = {
     "skagrid_dev_synth_vis": [vp, C.c_uint64, i64, i64, i64, i64, i64, ip, vp, vp, vp, vp, vp],
     "skagrid_dev_w_kernels": [vp, dbl, i64, vp, i64, i64, i64, ip, vp, vp],
     "skagrid_dev_frac_coord": [vp, i64, i64, i64, vp, vp, vp, ip, vp],
+    "skagrid_dev_uvw_scale": [vp, i64, vp, vp, vp, dbl, ip, vp],
+    "skagrid_dev_mirror_uvw": [vp, i64, vp, vp, vp, vp, vp],
+    "skagrid_dev_find_closest": [vp, i64, vp, i64, vp, vp, vp],
+    "skagrid_dev_doweight": [vp, dbl, i64, i64, vp, vp, vp, vp],
+    "skagrid_dev_take_error": [vp, vp, C.POINTER(C.c_int)],
 }
 _RESTYPES = {
     "skagrid_destroy": None,

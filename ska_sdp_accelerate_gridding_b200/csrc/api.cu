@@ -708,3 +708,49 @@ extern "C" int skagrid_dev_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, 
     NEED(ctx, d_p && d_fl && d_frac, "dev_frac_coord: NULL pointer");
     return sk_frac_coord_dev(ctx, n, qpx, count, d_p, (i64 *)d_fl, (i64 *)d_frac, flags & SKAGRID_FRAC_NORMALISE, sk_stream(ctx, stream));
 }
+
+// ------------------------------------------------------------------------------------------ device-resident pre-steps
+// The element-wise pre-steps of ImageDataset.aw_gridding on device arrays, for callers that keep the visibilities
+// resident (same kernels as the host-pointer functions above).
+extern "C" int skagrid_dev_uvw_scale(skagrid_ctx *ctx, int64_t count, double *d_u, double *d_v, double *d_w, double a, int divide,
+                                     void *stream) {
+    SK_TRY(enter(ctx));
+    if (count <= 0) return SKAGRID_OK;
+    NEED(ctx, d_u && d_v && d_w, "dev_uvw_scale: NULL pointer");
+    return sk_scale3_dev(ctx, count, d_u, d_v, d_w, a, divide, sk_stream(ctx, stream));
+}
+
+extern "C" int skagrid_dev_mirror_uvw(skagrid_ctx *ctx, int64_t count, double *d_u, double *d_v, double *d_w, double *d_vis, void *stream) {
+    SK_TRY(enter(ctx));
+    if (count <= 0) return SKAGRID_OK;
+    NEED(ctx, d_u && d_v && d_w, "dev_mirror_uvw: NULL pointer");
+    return sk_mirror_dev(ctx, count, d_u, d_v, d_w, d_vis, sk_stream(ctx, stream));
+}
+
+extern "C" int skagrid_dev_find_closest(skagrid_ctx *ctx, int64_t nw, const double *d_wbins, int64_t count, const double *d_w,
+                                        int64_t *d_out, void *stream) {
+    SK_TRY(enter(ctx));
+    NEED(ctx, nw > 0, "dev_find_closest: empty wbins");
+    if (count <= 0) return SKAGRID_OK;
+    NEED(ctx, d_wbins && d_w && d_out, "dev_find_closest: NULL pointer");
+    return sk_find_closest_dev(ctx, nw, d_wbins, count, d_w, (i64 *)d_out, sk_stream(ctx, stream));
+}
+
+// Out-of-grid visibilities set bit 1 of the context's error word; skagrid_dev_take_error reads and clears it.
+extern "C" int skagrid_dev_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u, const double *d_v,
+                                    double *d_vis, void *stream) {
+    SK_TRY(enter(ctx));
+    if (count <= 0) return SKAGRID_OK;
+    NEED(ctx, d_u && d_v && d_vis, "dev_doweight: NULL pointer");
+    const i64 n = grid_side(theta, lam);
+    NEED(ctx, n > 0, "dev_doweight: round(theta*lam) must be positive");
+    return sk_doweight_dev(ctx, n, (double)lam, count, d_u, d_v, d_vis, ctx->d_flags, sk_stream(ctx, stream));
+}
+
+extern "C" int skagrid_dev_take_error(skagrid_ctx *ctx, void *stream, int *flags_out) {
+    SK_TRY(enter(ctx));
+    uint32_t f = 0;
+    SK_TRY(sk_take_flags(ctx, sk_stream(ctx, stream), &f));
+    if (flags_out) *flags_out = (int)f;
+    return SKAGRID_OK;
+}

@@ -53,6 +53,51 @@ def frac_coord(n, qpx, p, normalise=True, ctx=None):
     return fl, fr
 
 
+def uvw_lambda_(freq, u, v, w, ctx=None):
+    """In place (u,v,w) *= freq/299792458.0 (src/ImageDataset.hs:181-187)."""
+    ctx = ctx or context_for_current_device()
+    for t in (u, v, w):
+        _chk(t, torch.float64, "uvw")
+    ctx.check(ctx.lib.skagrid_dev_uvw_scale(ctx.h, u.numel(), _p(u), _p(v), _p(w), float(freq) / 299792458.0, 0, _stream()))
+
+
+def div3_(lam, u, v, w, ctx=None):
+    """In place (u,v,w) /= lam (src/Gridding.hs:838-839)."""
+    ctx = ctx or context_for_current_device()
+    for t in (u, v, w):
+        _chk(t, torch.float64, "uvw")
+    ctx.check(ctx.lib.skagrid_dev_uvw_scale(ctx.h, u.numel(), _p(u), _p(v), _p(w), float(lam), 1, _stream()))
+
+
+def mirror_uvw_(u, v, w, vis=None, ctx=None):
+    """In place mirror_uvw (src/Gridding.hs:551-562)."""
+    ctx = ctx or context_for_current_device()
+    for t in (u, v, w):
+        _chk(t, torch.float64, "uvw")
+    _chk(vis, torch.complex128, "vis")
+    ctx.check(ctx.lib.skagrid_dev_mirror_uvw(ctx.h, u.numel(), _p(u), _p(v), _p(w), _p(vis), _stream()))
+
+
+def find_closest(wbins, w, ctx=None):
+    """findClosest (src/Gridding.hs:895-907) of a CUDA vector of w against the sorted CUDA vector wbins."""
+    ctx = ctx or context_for_current_device()
+    _chk(wbins, torch.float64, "wbins"); _chk(w, torch.float64, "w")
+    out = torch.empty(w.shape, dtype=torch.int64, device=w.device)
+    ctx.check(ctx.lib.skagrid_dev_find_closest(ctx.h, wbins.numel(), _p(wbins), w.numel(), _p(w), _p(out), _stream()))
+    return out
+
+
+def doweight_(theta, lam, u, v, vis, ctx=None):
+    """In place doweight (src/Gridding.hs:564-583): vis /= number of visibilities sharing its cell."""
+    ctx = ctx or context_for_current_device()
+    _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(vis, torch.complex128, "vis")
+    ctx.check(ctx.lib.skagrid_dev_doweight(ctx.h, float(theta), int(lam), u.numel(), _p(u), _p(v), _p(vis), _stream()))
+    flags = C.c_int()
+    ctx.check(ctx.lib.skagrid_dev_take_error(ctx.h, _stream(), C.byref(flags)))
+    if flags.value & 2:
+        raise _lib.SkagridError(-5, "doweight: a visibility falls outside the weight grid")
+
+
 def w_kernel_table(theta, ws, npixff, npixkern, qpx, conjugate=True, ctx=None):
     """w_kernel (src/Gridding.hs:610-728) for every w in `ws`, built in device memory -> [nw,qpx,qpx,s,s]."""
     ctx = ctx or context_for_current_device()

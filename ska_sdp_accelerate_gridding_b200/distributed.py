@@ -70,10 +70,11 @@ def owners_of_rows(y0: torch.Tensor, gh: int, bounds: Sequence[int]):
     return lo, hi, on_grid
 
 
-def route_by_rows(y0: torch.Tensor, gh: int, bounds: Sequence[int], payload: Sequence[torch.Tensor], group=None):
+def route_by_rows(y0: torch.Tensor, gh: int, bounds: Sequence[int], payload: Sequence[torch.Tensor], group=None, return_route=False):
     """All-to-all of per-visibility payload tensors (each [count, ...]) to the ranks owning their footprint rows.
     Returns the received payload tensors (concatenated over source ranks, in source-rank order) and the
-    per-source receive counts."""
+    per-source receive counts; with return_route=True the second value is the full route
+    {"order", "in_splits", "out_splits"} needed to send per-record results back (`return_to_source`)."""
     world = dist.get_world_size(group)
     lo, hi, on_grid = owners_of_rows(y0, gh, bounds)
     send_idx = []
@@ -93,7 +94,21 @@ def route_by_rows(y0: torch.Tensor, gh: int, bounds: Sequence[int], payload: Seq
         out = torch.empty((sum(out_splits),) + tuple(as_real.shape[1:]), dtype=as_real.dtype, device=as_real.device)
         dist.all_to_all_single(out, as_real, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
         received.append(torch.view_as_complex(out) if src.is_complex() else out)
+    if return_route:
+        return received, {"order": order, "in_splits": in_splits, "out_splits": out_splits}
     return received, out_splits
+
+
+def return_to_source(values: torch.Tensor, route, count: int, group=None):
+    """Inverse of route_by_rows for per-record results: `values[i]` belongs to the i-th received record.  Sends them
+    back to the ranks the records came from and sums the contributions of every source visibility (a visibility
+    whose footprint straddles slabs was sent to several owners; each returns the partial sum over its own rows)."""
+    as_real = torch.view_as_real(values) if values.is_complex() else values
+    back = torch.empty((sum(route["in_splits"]),) + tuple(as_real.shape[1:]), dtype=as_real.dtype, device=as_real.device)
+    dist.all_to_all_single(back, as_real.contiguous(), output_split_sizes=route["in_splits"], input_split_sizes=route["out_splits"], group=group)
+    out = torch.zeros((count,) + tuple(as_real.shape[1:]), dtype=as_real.dtype, device=as_real.device)
+    out.index_add_(0, route["order"], back)
+    return torch.view_as_complex(out) if values.is_complex() else out
 
 
 def allreduce_grid(grid: torch.Tensor, group=None, dst: int | None = None):
@@ -158,14 +173,15 @@ class TileShardedGridder:
         self.set_bounds(balanced_slab_bounds(hist, self.world))
         return self.bounds
 
-    def route(self, u, v, wbin, vis):
+    def route(self, u, v, wbin, vis=None, return_route=False):
         from . import device as dv
         gh = self.table.shape[-2]
         qpx = self.table.shape[-3]
-        y, _ = dv.frac_coord(self.h, qpx, v)
+        payload = (u, v, wbin) if vis is None else (u, v, wbin, vis)
         if self.world == 1:
-            return (u, v, wbin, vis), [u.numel()]
-        return route_by_rows(y - gh // 2, gh, self.bounds, (u, v, wbin, vis), self.group)
+            return payload, (None if return_route else [u.numel()])
+        y, _ = dv.frac_coord(self.h, qpx, v)
+        return route_by_rows(y - gh // 2, gh, self.bounds, payload, self.group, return_route=return_route)
 
     def grid(self, u, v, wbin, vis, out=None):
         """Routes, then grids into this rank's slab [rows, width] (no reduction)."""
@@ -184,3 +200,17 @@ class TileShardedGridder:
                 plan.update(ru, rv, rwb, rvis)
             plan.grid(self.table, out)
         return out
+
+    def degrid(self, slab, u, v, wbin):
+        """Adjoint of `grid`: `slab` holds this rank's rows of the (model) grid.  Coordinates are routed to the owners,
+        every owner degrids the taps that fall on its rows, the partial sums travel back and are added per visibility."""
+        from . import device as dv
+        (ru, rv, rwb), route = self.route(u, v, wbin, return_route=True)
+        partial = torch.zeros(ru.numel(), dtype=torch.complex128, device=u.device)
+        if ru.numel() > 0:
+            plan = dv.Plan(self.h, self.w, self.table.shape, ru, rv, rwb, None, rows=self.rows)
+            plan.degrid(self.table, slab, partial)
+            plan.close()
+        if route is None:
+            return partial
+        return return_to_source(partial, route, u.numel(), self.group)

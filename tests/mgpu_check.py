@@ -43,10 +43,16 @@ def main():
     slab = ts.grid(lu, lv, lwb, lvis).cpu().numpy()
     r0, r1 = ts.rows
     err_t = np.abs(slab - full[r0:r1]).max() / peak
+    ts.balance(lv)   # data-balanced slabs, then the adjoint with partial sums returned to the source ranks
+    r0, r1 = ts.rows
+    dt = ts.degrid(t(full[r0:r1]), lu, lv, lwb).cpu().numpy()
+    err_td = np.abs(dt - od).max() / np.abs(od).max()
+    slab2 = ts.grid(lu, lv, lwb, lvis).cpu().numpy()
+    err_t = max(err_t, np.abs(slab2 - full[r0:r1]).max() / peak, err_td)
     res = torch.tensor([err_v, err_d, err_t], dtype=torch.float64, device="cuda")
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"world={world} vis-sharded grid err {res[0]:.2e}, degrid err {res[1]:.2e}, tile-sharded err {res[2]:.2e}")
+        print(f"world={world} vis-sharded grid err {res[0]:.2e}, degrid err {res[1]:.2e}, tile-sharded (grid, balanced grid, degrid) err {res[2]:.2e}")
     dist.destroy_process_group()
     sys.exit(0 if float(res.max()) < 1e-10 else 1)
 

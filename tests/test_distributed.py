@@ -53,7 +53,7 @@ def _worker(rank, world, port, mode, ret):
             y0 = torch.from_numpy(y - s // 2)
             payload = (torch.from_numpy(u[sl].copy()), torch.from_numpy(v[sl].copy()), torch.from_numpy(wb[sl].copy()),
                        torch.from_numpy(vis[sl].copy()))
-            (ru, rv, rwb, rvis), splits = D.route_by_rows(y0, s, bounds, payload)
+            (ru, rv, rwb, rvis), route = D.route_by_rows(y0, s, bounds, payload, return_route=True)
             r0, r1 = bounds[rank], bounds[rank + 1]
             # every received footprint intersects the owned slab, and nothing that does was left behind
             ry, _ = orc.frac_coord(n, q, rv.numpy())
@@ -64,6 +64,15 @@ def _worker(rank, world, port, mode, ret):
             # grid the routed visibilities, clip to the slab, compare with the same rows of the full grid
             g = orc.convgrid(gcf, np.zeros((n, n), complex), ru.numpy(), rv.numpy(), rvis.numpy(), wbin=rwb.numpy())
             err = np.abs(g[r0:r1] - full[r0:r1]).max() / np.abs(full).max()
+            # adjoint: every owner degrids only its rows of a model grid; the partial sums go back and add up
+            rng = np.random.default_rng(5)
+            model = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+            clipped = np.zeros_like(model)
+            clipped[r0:r1] = model[r0:r1]
+            part = orc.convdegrid(gcf, clipped, ru.numpy(), rv.numpy(), wbin=rwb.numpy())
+            back = D.return_to_source(torch.from_numpy(part), route, cnt).numpy()
+            ref = orc.convdegrid(gcf, model, u[sl], v[sl], wbin=wb[sl])
+            err = max(err, np.abs(back - ref).max() / np.abs(ref).max())
             ret[rank] = ("ok", float(err), int(ru.numel()))
     except Exception as e:  # pragma: no cover
         ret[rank] = ("fail", repr(e), 0)

@@ -432,3 +432,31 @@ def test_c_abi_from_plain_c(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "c_abi_smoke ok" in r.stdout
+
+
+def test_device_resident_presteps(orc):
+    """uvw_lambda / doweight / mirror / findClosest / div3 on device arrays are bit-identical to the oracle."""
+    from ska_sdp_accelerate_gridding_b200 import _lib
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    rng = np.random.default_rng(71)
+    cnt, theta, lam, freq = 40000, 0.01, 30000, 1.1e8
+    sc = 299792458.0 / freq
+    u, v, w = (rng.uniform(-14000, 14000, cnt) * sc for _ in range(3))
+    vis = _rand_c(rng, cnt)
+    wbins = np.sort(rng.uniform(-15000, 15000, 33))
+    du, dv_, dw, dvis = _t(u), _t(v), _t(w), _t(vis)
+    dv.uvw_lambda_(freq, du, dv_, dw)
+    ou, ov, ow = orc.uvw_lambda(freq, u, v, w)
+    assert np.array_equal(du.cpu().numpy(), ou) and np.array_equal(dw.cpu().numpy(), ow)
+    wt = _t(np.ones(cnt, complex))
+    dv.doweight_(theta, lam, du, dv_, wt)
+    assert np.array_equal(wt.cpu().numpy(), orc.doweight(theta, lam, ou, ov, np.ones(cnt, complex)))
+    dv.mirror_uvw_(du, dv_, dw, dvis)
+    mu, mv, mw, mvis = orc.mirror_uvw(ou, ov, ow, vis)
+    assert np.array_equal(dv_.cpu().numpy(), mv) and np.array_equal(dvis.cpu().numpy(), mvis)
+    assert np.array_equal(dv.find_closest(_t(wbins), dw).cpu().numpy(), orc.find_closest(wbins, mw))
+    dv.div3_(lam, du, dv_, dw)
+    pu, pv, pw = orc.div3(float(lam), mu, mv, mw)
+    assert np.array_equal(du.cpu().numpy(), pu) and np.array_equal(dv_.cpu().numpy(), pv)
+    with pytest.raises(_lib.SkagridError):
+        dv.doweight_(theta, lam, _t(u * 1000), _t(v), _t(vis))
