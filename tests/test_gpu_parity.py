@@ -460,3 +460,28 @@ def test_device_resident_presteps(orc):
     assert np.array_equal(du.cpu().numpy(), pu) and np.array_equal(dv_.cpu().numpy(), pv)
     with pytest.raises(_lib.SkagridError):
         dv.doweight_(theta, lam, _t(u * 1000), _t(v), _t(vis))
+
+
+@pytest.mark.parametrize("tile,cellsort", [(16, 0), (16, 1), (32, 0), (32, 1)])
+def test_plan_layout_choices(orc, monkeypatch, tile, cellsort):
+    """The per-plan layout choices (uv tile 16/32, cell- or micro-tile-granular buckets) are performance knobs only:
+    every combination reproduces the oracle (they select different gridder residency and degridder kernels)."""
+    import torch
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    monkeypatch.setenv("SKAGRID_TILE", str(tile))
+    monkeypatch.setenv("SKAGRID_CELLSORT", str(cellsort))
+    rng = np.random.default_rng(100 + tile + cellsort)
+    n, s, q, nw, cnt = 160, 15, 8, 3, 30000
+    gcf = _rand_c(rng, (nw, q, q, s, s))
+    u = np.clip(rng.normal(0, 0.08, cnt), -0.52, 0.52)
+    v = np.abs(np.clip(rng.normal(0, 0.08, cnt), -0.52, 0.52))
+    wb = rng.integers(0, nw, cnt)
+    vis = _rand_c(rng, cnt)
+    og = orc.convgrid(gcf, np.zeros((n, n), complex), u, v, vis, wbin=wb, parallel=True)
+    plan = dv.Plan(n, n, gcf.shape, _t(u), _t(v), _t(wb), _t(vis))
+    grid = torch.zeros((n, n), dtype=torch.complex128, device="cuda")
+    plan.grid(_t(gcf), grid)
+    assert rel_err(grid.cpu().numpy(), og) < TOL
+    d = plan.degrid(_t(gcf), _t(og)).cpu().numpy()
+    assert rel_err(d, orc.convdegrid(gcf, og, u, v, wbin=wb, parallel=True)) < TOL
+    plan.close()
