@@ -319,7 +319,7 @@ def main():
             traffic = k["dram_bytes_read"] + k["dram_bytes_write"]
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": "grid_tiled_kernel<R=16,MT=2,DEPTH=3,TY=8>" if SUPPORT <= 15 else "grid_tiled_kernel<R=32,MT=2,DEPTH=2,TY=16>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+        "bound": "hbm", "kernel": "grid_tiled_kernel<R=16,MT=2,DEPTH=3,TY=8>" if SUPPORT <= 15 else "grid_tiled_kernel<R=32,MT=2,DEPTH=3,TY=32>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
         "traffic": traffic, "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "kernel_ms": kern_ms,
         "note": "compulsory-byte accounting (64 B/vis + 16 N^2 + table); the tiled gridder is bound by L2->SM kernel-tap traffic (3.7 KB/vis), see DESIGN.md 4.2 and the l2_taps entry",
         "fp64": {"achieved_tflops": FLOP_PER_VIS * V / (kern_ms * 1e-3) / 1e12, "peak_tflops_measured": fp64_peak,

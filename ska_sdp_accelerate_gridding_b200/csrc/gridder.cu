@@ -589,7 +589,11 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
     if (R == 32) {
         if (variant == 4) return MT == 2 ? launch_tiled<32, 2, 2, 8>(ctx, A, st) : launch_tiled<32, 4, 2, 8>(ctx, A, st);
         if (variant == 3) return MT == 2 ? launch_tiled<32, 2, 3, 16>(ctx, A, st) : launch_tiled<32, 4, 3, 16>(ctx, A, st);
-        return MT == 2 ? launch_tiled<32, 2, 2, 16>(ctx, A, st) : launch_tiled<32, 4, 2, 16>(ctx, A, st);
+        if (variant == 5) return MT == 2 ? launch_tiled<32, 2, 2, 32>(ctx, A, st) : launch_tiled<32, 4, 2, 32>(ctx, A, st);
+        if (variant == 2) return MT == 2 ? launch_tiled<32, 2, 2, 16>(ctx, A, st) : launch_tiled<32, 4, 2, 16>(ctx, A, st);
+        // 32 x 16 threads, two residues each, three tap slots, 64 registers -> 2 x 16 warps per SM
+        // (B200, S=31, 5e7 visibilities on 32768^2: 62 ms; 16 x 16 threads with four residues each (variant 2): 71 ms)
+        return MT == 2 ? launch_tiled<32, 2, 3, 32>(ctx, A, st) : launch_tiled<32, 4, 3, 32>(ctx, A, st);
     }
     return MT == 2 ? launch_tiled<64, 2, 2, 16>(ctx, A, st) : launch_tiled<64, 4, 2, 16>(ctx, A, st);
 }
@@ -633,7 +637,7 @@ extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const do
             SK_CUDA(ctx, cudaFuncSetAttribute(degrid_tile_kernel<15, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         }
         int per_sm = 0;
-        if (variant == 2) {
+        if (variant == 2 || (variant == 0 && A.tile == 32)) {  // large tiles: more threads to stage the subgrid (28.3 vs 31.8 ms at S=15)
             SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_tile_kernel<15, 256>, 256, tile_smem));
             if (per_sm < 1) per_sm = 1;
             degrid_tile_kernel<15, 256><<<ctx->sm_count * per_sm, 256, tile_smem, st>>>(A);
