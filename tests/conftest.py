@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The built libraries are git-ignored: on a fresh checkout build them once (nvcc cross-compiles without a GPU).
+    # This only builds; if nvcc is missing the ABI / GPU tests fail loudly, there is no fallback.
+    try:
+        from ska_sdp_accelerate_gridding_b200 import _lib, build as _build
+        if not os.path.exists(_lib.LIB_PATH):
+            _build.build()
+    except Exception as e:  # pragma: no cover
+        print(f"[conftest] libskagrid.so could not be built: {e}", file=sys.stderr)
 
 
 def pytest_collection_modifyitems(config, items):
