@@ -217,8 +217,8 @@ int skagrid_dev_plan_stats(skagrid_ctx *ctx, skagrid_plan *plan, void *stream, i
 
 /* grid[row0:row1, :] += sum over the plan's visibilities of vis_k * table[slice_k].
  * variant: 0 = tiled shared-memory gridder (default), 1 = one-thread-per-tap global-atomic gridder
- * (the literal `permute (+)`; baseline and cross-check), 2 = tiled gridder with two instead of three
- * kernel-tap loads in flight per thread (A/B measurements). */
+ * (the literal `permute (+)`; baseline and cross-check), 2..4 = earlier thread layouts / pipeline depths of
+ * the tiled gridder kept for A/B measurements (see gridder.cu). */
 int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, double *grid,
                      int variant, void *stream);
 /* vis_out[k] = sum conj(table[slice_k][i,j]) * grid[...] for the plan's visibilities (others = 0). */

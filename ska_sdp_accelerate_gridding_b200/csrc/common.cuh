@@ -41,7 +41,6 @@ struct WorkItem {
 // shared-memory subgrid small (more resident blocks per SM: best for dense uv coverage), large tiles amortise the
 // per-tile zero/flush over more visibilities (best for sparse coverage and for wide kernels).
 constexpr int CHUNK = 4096;                    // max records per work item (load balance)
-constexpr int GRID_THREADS = 256;              // threads per gridder / degridder block
 
 // Geometry of one plan.  A uv tile is TILE x TILE footprint origins; inside a tile the origins are
 // bucketed by MT x MT micro-tiles.  All footprints of one micro-tile lie inside an R x R cell region

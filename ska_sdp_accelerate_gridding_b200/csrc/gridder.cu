@@ -115,7 +115,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // (TY = 8 for R = 16) halve the per-visibility bookkeeping (record decode, broadcast shared-memory reads, loop
 // control), which matters because the kernel is bound by the L1/shared-memory data pipe and the issue slots.
 template <int R, int MT, int DEPTH, int TY>
-__global__ void __launch_bounds__(16 * TY, (R == 16 ? (TY == 8 ? 8 : 6) : (R == 32 ? (TY == 8 ? 3 : 2) : 1))) grid_tiled_kernel(const GridArgs A) {
+__global__ void __launch_bounds__(16 * TY, (R == 16 ? (TY == 8 ? 8 : 6) : (R == 32 ? 2 : 1))) grid_tiled_kernel(const GridArgs A) {
     constexpr int CY = R / TY, CX = R / 16;  // residues per thread
     constexpr int NT = 16 * TY;              // threads per block
     constexpr int REC_BATCH = RecBatch<R>::value;
@@ -577,22 +577,20 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
     }
     SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 1, 0, sizeof(uint32_t), st));
     const int MT = plan->g.MT;
+    // variants (A/B measurements on B200; 1e8 visibilities, config 4, per launch):
+    //   0  default.  R=16: 8x16 threads, two residues each, three tap slots (22.5 ms)
+    //                R=32: 32x16 threads, two residues each, three tap slots (S=31, 5e7 on 32768^2: 62 ms)
+    //   2  16x16 threads, R/16 x R/16 residues each, two tap slots (R=16: 27.6 ms with 32-cell tiles; R=32: 71 ms)
+    //   3  R=16: 16x16 threads, three tap slots (27.1 ms with 32-cell tiles)
+    //   4  R=16: 8x16 threads, two tap slots (23.5 ms)
     if (R == 16) {
-        // three tap slots in flight (B200, S=15, 1e8 visibilities: 27.1 ms; two slots (variant 2): 27.6 ms)
         if (variant == 2) return MT == 2 ? launch_tiled<16, 2, 2, 16>(ctx, A, st) : launch_tiled<16, 4, 2, 16>(ctx, A, st);
         if (variant == 3) return MT == 2 ? launch_tiled<16, 2, 3, 16>(ctx, A, st) : launch_tiled<16, 4, 3, 16>(ctx, A, st);
         if (variant == 4) return MT == 2 ? launch_tiled<16, 2, 2, 8>(ctx, A, st) : launch_tiled<16, 4, 2, 8>(ctx, A, st);
-        if (variant == 5) return MT == 2 ? launch_tiled<16, 2, 2, 4>(ctx, A, st) : launch_tiled<16, 4, 2, 4>(ctx, A, st);
-        if (variant == 6) return MT == 2 ? launch_tiled<16, 2, 3, 4>(ctx, A, st) : launch_tiled<16, 4, 3, 4>(ctx, A, st);
         return MT == 2 ? launch_tiled<16, 2, 3, 8>(ctx, A, st) : launch_tiled<16, 4, 3, 8>(ctx, A, st);
     }
     if (R == 32) {
-        if (variant == 4) return MT == 2 ? launch_tiled<32, 2, 2, 8>(ctx, A, st) : launch_tiled<32, 4, 2, 8>(ctx, A, st);
-        if (variant == 3) return MT == 2 ? launch_tiled<32, 2, 3, 16>(ctx, A, st) : launch_tiled<32, 4, 3, 16>(ctx, A, st);
-        if (variant == 5) return MT == 2 ? launch_tiled<32, 2, 2, 32>(ctx, A, st) : launch_tiled<32, 4, 2, 32>(ctx, A, st);
         if (variant == 2) return MT == 2 ? launch_tiled<32, 2, 2, 16>(ctx, A, st) : launch_tiled<32, 4, 2, 16>(ctx, A, st);
-        // 32 x 16 threads, two residues each, three tap slots, 64 registers -> 2 x 16 warps per SM
-        // (B200, S=31, 5e7 visibilities on 32768^2: 62 ms; 16 x 16 threads with four residues each (variant 2): 71 ms)
         return MT == 2 ? launch_tiled<32, 2, 3, 32>(ctx, A, st) : launch_tiled<32, 4, 3, 32>(ctx, A, st);
     }
     return MT == 2 ? launch_tiled<64, 2, 2, 16>(ctx, A, st) : launch_tiled<64, 4, 2, 16>(ctx, A, st);
