@@ -593,7 +593,7 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
         if (variant == 2) return MT == 2 ? launch_tiled<32, 2, 2, 16>(ctx, A, st) : launch_tiled<32, 4, 2, 16>(ctx, A, st);
         return MT == 2 ? launch_tiled<32, 2, 3, 32>(ctx, A, st) : launch_tiled<32, 4, 3, 32>(ctx, A, st);
     }
-    return MT == 2 ? launch_tiled<64, 2, 2, 16>(ctx, A, st) : launch_tiled<64, 4, 2, 16>(ctx, A, st);
+    return MT == 2 ? launch_tiled<64, 2, 2, 32>(ctx, A, st) : launch_tiled<64, 4, 2, 32>(ctx, A, st);  // 32x16 threads, 2x4 residues each
 }
 
 extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, const double *grid, double *vis_out,
