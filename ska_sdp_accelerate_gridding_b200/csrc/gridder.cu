@@ -161,24 +161,29 @@ __global__ void __launch_bounds__(16 * TY, (R == 16 ? (TY == 8 ? 8 : 6) : (R == 
             const uint2 m = *reinterpret_cast<const uint2 *>(&buf[2 * j + 1]);  // kbase, loc (broadcast read)
             const uint32_t key = m.y & mtkey_mask;
             s.sw = key != S.key;
-            if (s.sw) mt_setup<R, CY, CX, MT>(S, key, ty, tx, A);  // warp-uniform
+            if (s.sw) {  // warp-uniform: all threads walk the same records
+                mt_setup<R, CY, CX, MT>(S, key, ty, tx, A);
+#pragma unroll
+                for (int a = 0; a < CY; ++a)
+#pragma unroll
+                    for (int b = 0; b < CX; ++b) s.cell[a][b] = S.cell[a][b];  // only read when s.sw
+            }
 #pragma unroll
             for (int a = 0; a < CY; ++a)
 #pragma unroll
                 for (int b = 0; b < CX; ++b) {
-                    s.cell[a][b] = S.cell[a][b];
-                    s.k[a][b] = make_double2(0.0, 0.0);
+                    s.k[a][b] = make_double2(0.0, 0.0);  // a residue without a tap adds +0 (cheaper than predicating the FMAs)
                     if (S.vmask[a][b] & m.y) s.k[a][b] = ldg2(A.table + (uint32_t)(m.x + (uint32_t)S.toff[a][b]));
                 }
         };
         // acc += vis_j * k
         auto consume = [&](const uint4 *buf, uint32_t j, const Slot &s) {
             const double2 vis = *reinterpret_cast<const double2 *>(&buf[2 * j]);
+            if (s.sw) {  // fold the register accumulators into the thread's own subgrid cells and retarget them
 #pragma unroll
-            for (int a = 0; a < CY; ++a)
+                for (int a = 0; a < CY; ++a)
 #pragma unroll
-                for (int b = 0; b < CX; ++b) {
-                    if (s.sw) {  // fold the register accumulator into the thread's own subgrid cell and retarget it
+                    for (int b = 0; b < CX; ++b) {
                         if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
                             double2 t = sg[cell_cur[a][b]];
                             t.x += acc[a][b].x; t.y += acc[a][b].y;
@@ -187,7 +192,11 @@ __global__ void __launch_bounds__(16 * TY, (R == 16 ? (TY == 8 ? 8 : 6) : (R == 
                         }
                         cell_cur[a][b] = s.cell[a][b];
                     }
-                    // (vr + i vi)(kr + i ki); an invalid cell has a zero tap and adds +0
+            }
+#pragma unroll
+            for (int a = 0; a < CY; ++a)
+#pragma unroll
+                for (int b = 0; b < CX; ++b) {  // (vr + i vi)(kr + i ki)
                     acc[a][b].x = fma(vis.x, s.k[a][b].x, acc[a][b].x);
                     acc[a][b].x = fma(-vis.y, s.k[a][b].y, acc[a][b].x);
                     acc[a][b].y = fma(vis.x, s.k[a][b].y, acc[a][b].y);
