@@ -484,19 +484,24 @@ __global__ void __launch_bounds__(NT, MINB) degrid_reg_kernel(const GridArgs A) 
                 const double2 *kp = A.table + (uint32_t)(meta.x + dy * (uint32_t)A.kpitch + dx + (uint32_t)hl);
                 double2 k[GH];
 #pragma unroll
-                for (int i = 0; i < GH; ++i) k[i] = (EXACT || i < A.gh) ? ldg2(kp + i * A.kpitch) : make_double2(0.0, 0.0);
+                for (int i = 0; i < GH; ++i) k[i] = (EXACT || i < A.gh) ? ldg2(kp + i * 16) : make_double2(0.0, 0.0);  // kpitch == 16 here: immediate offsets
 #pragma unroll
                 for (int i = 0; i < GH; ++i) {  // conj(k) * g
                     ar = fma(k[i].x, g[i].x, ar); ar = fma(k[i].y, g[i].y, ar);
                     ai = fma(k[i].x, g[i].y, ai); ai = fma(-k[i].y, g[i].x, ai);
                 }
             }
+            // 16-lane reduction of (ar, ai) with half the shuffles: after the first exchange the lanes with bit 3 clear
+            // carry only the real sum and the others only the imaginary one, so the remaining three steps move one double
+            {
+                const bool hi = (hl & 8) != 0;
+                const double send = hi ? ar : ai, keep = hi ? ai : ar;
+                double sum = keep + __shfl_xor_sync(0xffffffffu, send, 8);
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                ar += __shfl_xor_sync(0xffffffffu, ar, o);
-                ai += __shfl_xor_sync(0xffffffffu, ai, o);
+                for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                // lane 0 of the half-warp holds the real part, lane 8 the imaginary part
+                if (live && (hl & 7) == 0) reinterpret_cast<double *>(A.vis_out + out_index)[hi ? 1 : 0] = sum;
             }
-            if (live && hl == 0) A.vis_out[out_index] = make_double2(ar, ai);
         }
     }
 }
