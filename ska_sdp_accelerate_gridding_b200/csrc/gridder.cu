@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256) degrid_warp_kernel(const GridArgs A) {
 }
 
 // Degridder, tiled: a persistent block pulls the same work items as the gridder, stages the item's subgrid
-// (TILE-1+S)^2 from the grid into shared memory once (zero outside the owned rows / the grid, so the hot loop has no
+// (tile-1+S)^2 from the grid into shared memory once (zero outside the owned rows / the grid, so the hot loop has no
 // bounds checks), then its 16 half-warps take the item's records round-robin.  Grid cells are then conflict-free
 // 128-bit shared-memory loads (two wavefronts per 15-lane row instead of three unaligned L1 lines); only the kernel
 // taps still come from L2.

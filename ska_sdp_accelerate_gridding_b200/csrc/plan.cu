@@ -5,8 +5,10 @@
 //   frac_coord   src/Gridding.hs:126-140      frac_coords  src/Gridding.hs:142-151
 //   findClosest  src/Gridding.hs:895-907      fixoutofbounds (clip, never wrap) src/Gridding.hs:883-891
 // The reference has no sort: its `permute (+)` scatters V*S^2 taps unordered.  Here every visibility
-// gets an integer key (uv tile of its footprint origin, 2x2 micro-tile inside the tile) and a counting
-// sort (histogram -> exclusive scan -> scatter) groups the 32-byte records per key.
+// gets an integer key -- uv tile of its footprint origin (16 or 32 cells, chosen per plan), MT x MT micro-tile
+// inside the tile, and (when the offset table stays small) the exact origin inside the micro-tile -- and a
+// counting sort (histogram -> exclusive scan -> scatter, one 256-bit store per record) groups the 32-byte
+// records per key.  One thread per tile then cuts the tile's records into work items of <= CHUNK records.
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
