@@ -485,3 +485,18 @@ def test_plan_layout_choices(orc, monkeypatch, tile, cellsort):
     d = plan.degrid(_t(gcf), _t(og)).cpu().numpy()
     assert rel_err(d, orc.convdegrid(gcf, og, u, v, wbin=wb, parallel=True)) < TOL
     plan.close()
+
+
+def test_non_square_grid(G, orc):
+    """height != width: x from u with the width, y from v with the height (src/Gridding.hs:142-151)."""
+    rng = np.random.default_rng(5150)
+    h, w, s, q, nw, cnt = 96, 130, 15, 4, 2, 8000
+    gcf = _rand_c(rng, (nw, q, q, s, s))
+    u, v = rng.uniform(-0.55, 0.55, cnt), rng.uniform(-0.55, 0.55, cnt)
+    wb = rng.integers(0, nw, cnt)
+    vis = _rand_c(rng, cnt)
+    start = _rand_c(rng, (h, w))
+    g = G.convgrid2(gcf, start, (u, v), wb, vis)
+    og = orc.convgrid(gcf, start, u, v, vis, wbin=wb)
+    assert g.shape == (h, w) and rel_err(g, og) < TOL
+    assert rel_err(G.convdegrid2(gcf, og, (u, v), wb), orc.convdegrid(gcf, og, u, v, wbin=wb)) < TOL
