@@ -35,6 +35,12 @@ BYTES_PER_VIS = 64                                   # SURVEY.md 8d compulsory r
 UPD_BYTES_PER_VIS = 64 + 16 * SUPPORT * SUPPORT      # grid-update-equivalent accounting
 
 
+def workload_name():
+    return (("config 4: " if (N_GRID, SUPPORT, NW) == (8192, 15, 32) else "") +
+            f"synthetic SKA1-Low-shaped visibilities, {N_GRID}^2 c128 grid, support {SUPPORT}, oversampling {QPX}, {NW} w-planes, "
+            "visibility-sharded (one batch per GPU) with NCCL all-reduce of the grid")
+
+
 def parse():
     global N_GRID, SUPPORT, NW, FLOP_PER_VIS, UPD_BYTES_PER_VIS
     ap = argparse.ArgumentParser()
@@ -142,12 +148,12 @@ def run_reference(args, rank):
             rates.append(r); t_g.append(tg); t_d.append(td)
     ms = 1e3 * sample / float(np.mean(rates))
     val = sample / (ms * 1e-3)
-    desc = f"{sample} of the config-4 visibilities per step (grid + degrid, 8192^2 grid, S=15, Q=8, 32 w-planes)"
+    desc = f"{sample} of the workload's visibilities per step (grid + degrid on the same {N_GRID}^2 grid and kernel table), CPU restatement of the reference semantics"
     print(json.dumps({
         "impl": "reference", "metric": "visibilities/sec gridded+degridded", "value": val, "unit": "vis/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config 4: synthetic SKA1-Low-shaped visibilities, 8192^2 c128 grid, support 15, oversampling 8, 32 w-planes", "sample": desc},
+        "config": {"workload": workload_name(), "sample": desc},
         "cpu_baseline": {"value": val, "unit": "vis/s", "cores": threads, "kind": "port", "sample": desc,
                          "grid_s": float(np.mean(t_g)), "degrid_s": float(np.mean(t_d))},
         "e2e": {"value": val, "unit": "vis/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -337,9 +343,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {
-            "workload": ("config 4: " if (N_GRID, SUPPORT, NW) == (8192, 15, 32) else "") +
-                        f"synthetic SKA1-Low-shaped visibilities, {N_GRID}^2 c128 grid, support {SUPPORT}, oversampling {QPX}, {NW} w-planes, "
-                        "visibility-sharded (one batch per GPU) with NCCL all-reduce of the grid",
+            "workload": workload_name(),
             "vis_per_gpu_per_step": V, "uv": "uniform" if args.uniform else "core-dominated mixture (SURVEY 8d)", "seed": SEED,
             "step": "bin+bucket -> tiled gridder -> all-reduce (N>1) -> hermitian+IFFT+real/max -> degridder",
             "l2": f"inputs ({V * 40 / 1e9:.1f} GB) and grid ({N_GRID * N_GRID * 16 / 1e9:.2f} GB) exceed the 126 MB L2; no explicit flush",
