@@ -500,3 +500,24 @@ def test_non_square_grid(G, orc):
     og = orc.convgrid(gcf, start, u, v, vis, wbin=wb)
     assert g.shape == (h, w) and rel_err(g, og) < TOL
     assert rel_err(G.convdegrid2(gcf, og, (u, v), wb), orc.convdegrid(gcf, og, u, v, wbin=wb)) < TOL
+
+
+def test_nan_inf_and_far_off_grid_visibilities_are_dropped(G, orc):
+    """Non-finite or absurd coordinates never touch the grid (the reference would index out of bounds); finite
+    visibilities in the same batch are unaffected, and their degridded values are exact while the dropped ones read 0."""
+    rng = np.random.default_rng(404)
+    n, s, q, nw, cnt = 96, 9, 4, 2, 2000
+    gcf = _rand_c(rng, (nw, q, q, s, s))
+    u, v = rng.uniform(-0.5, 0.5, cnt), rng.uniform(-0.5, 0.5, cnt)
+    wb = rng.integers(0, nw, cnt)
+    vis = _rand_c(rng, cnt)
+    bad = np.array([3, 77, 500, 1999])
+    u2, v2 = u.copy(), v.copy()
+    u2[bad[0]] = np.nan; v2[bad[1]] = np.inf; u2[bad[2]] = -np.inf; v2[bad[3]] = 1e30
+    keep = np.ones(cnt, bool); keep[bad] = False
+    g = G.convgrid2(gcf, np.zeros((n, n), complex), (u2, v2), wb, vis)
+    og = orc.convgrid(gcf, np.zeros((n, n), complex), u[keep], v[keep], vis[keep], wbin=wb[keep])
+    assert rel_err(g, og) < TOL
+    d = G.convdegrid2(gcf, og, (u2, v2), wb)
+    od = orc.convdegrid(gcf, og, u[keep], v[keep], wbin=wb[keep])
+    assert rel_err(d[keep], od) < TOL and not d[bad].any()
