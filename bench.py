@@ -250,7 +250,10 @@ def main():
     plan = dv.Plan(N_GRID, N_GRID, table.shape, u, v, wb, vis)
     stats = plan.stats()
     fp64_peak = ctx.fp64_tflops()
-    l2_peak = ctx.l2_read_tbs(int(table.numel()) * 16)   # measured L2->SM read bandwidth over a table-sized buffer
+    # measured L2->SM read bandwidth over a table-sized buffer: a coalesced stream, and (S=15) the kernels' own access
+    # pattern -- 15 taps of 15 consecutive 256-byte rows of a random slice per half-warp, useful bytes only
+    l2_stream = ctx.l2_read_tbs(int(table.numel()) * 16, 0)
+    l2_peak = ctx.l2_read_tbs(int(table.numel()) * 16, 1) if SUPPORT == 15 else l2_stream
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
     stage_ms = {k: [] for k in ("plan", "grid", "reduce", "image", "degrid")}
@@ -332,8 +335,10 @@ def main():
                  "frac": FLOP_PER_VIS * V / (kern_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None},
         "l2_taps": {"achieved_tbs": 16.0 * SUPPORT * SUPPORT * V / (kern_ms * 1e-3) / 1e12, "peak_tbs_measured": l2_peak,
                     "frac": 16.0 * SUPPORT * SUPPORT * V / (kern_ms * 1e-3) / 1e12 / l2_peak if l2_peak else None,
-                    "note": "kernel taps streamed L2->SM (16 B x S^2 per visibility) vs the L2 read bandwidth measured in this run "
-                            "(skagrid_measure_l2_read_tbs: 128-bit ld.global.cg over a table-sized buffer)"},
+                    "peak_tbs_coalesced_stream": l2_stream,
+                    "note": "kernel taps streamed L2->SM (16 B x S^2 per visibility) vs the L2 read bandwidth measured in this run with the same "
+                            "access pattern and nothing else (skagrid_measure_l2_pattern_tbs: random 15x15-tap slices of a table-sized buffer, "
+                            "useful bytes); this is the ceiling of any gridder that fetches one kernel slice per visibility from L2"},
         "hbm_update_equiv": {"achieved": UPD_BYTES_PER_VIS * V / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak,
                              "frac": UPD_BYTES_PER_VIS * V / (kern_ms * 1e-3) / 1e9 / hbm_peak},
     }

@@ -80,6 +80,9 @@ int skagrid_measure_fp64_tflops(skagrid_ctx *ctx, double *tflops);
 /* Measures the L2 -> SM read bandwidth (TB/s) with 128-bit L2-only loads over a `bytes`-sized, L2-resident buffer:
  * the ceiling of the tiled gridder / degridder, whose kernel taps stream from an L2-resident table. */
 int skagrid_measure_l2_read_tbs(skagrid_ctx *ctx, int64_t bytes, double *tbs);
+/* The same with an access pattern: 0 = fully coalesced stream, 1 = what the S=15 gridder / degridder do (every
+ * half-warp reads the 15 taps of 15 consecutive 256-byte rows of a pseudo-random slice); useful bytes only. */
+int skagrid_measure_l2_pattern_tbs(skagrid_ctx *ctx, int64_t bytes, int pattern, double *tbs);
 
 /* ------------------------------------------------------------------ binning (bit-exact)
  * frac_coord  src/Gridding.hs:126-140, frac_coords :142-151 (x,xf from u with width; y,yf from v with height) */

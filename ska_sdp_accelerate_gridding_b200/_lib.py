@@ -30,6 +30,7 @@ _SIGS = {
     "skagrid_launch_count": [vp],
     "skagrid_measure_fp64_tflops": [vp, C.POINTER(dbl)],
     "skagrid_measure_l2_read_tbs": [vp, i64, C.POINTER(dbl)],
+    "skagrid_measure_l2_pattern_tbs": [vp, i64, ip, C.POINTER(dbl)],
     "skagrid_frac_coord": [vp, i64, i64, i64, vp, vp, vp, ip],
     "skagrid_frac_coords": [vp, i64, i64, i64, i64, vp, vp, vp, vp, vp, vp, ip],
     "skagrid_find_closest": [vp, i64, vp, i64, vp, vp],

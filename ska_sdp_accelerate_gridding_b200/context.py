@@ -52,9 +52,10 @@ class Context:
 
 
 
-    def l2_read_tbs(self, nbytes: int = 8 << 20) -> float:
+    def l2_read_tbs(self, nbytes: int = 8 << 20, pattern: int = 0) -> float:
+        """Measured L2 -> SM read bandwidth in TB/s: pattern 0 coalesced stream, 1 random 15x15-tap slices (useful bytes)."""
         out = C.c_double()
-        self.check(self.lib.skagrid_measure_l2_read_tbs(self.h, int(nbytes), C.byref(out)))
+        self.check(self.lib.skagrid_measure_l2_pattern_tbs(self.h, int(nbytes), int(pattern), C.byref(out)))
         return out.value
 
 

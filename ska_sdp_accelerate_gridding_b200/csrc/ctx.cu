@@ -171,6 +171,54 @@ __global__ void __launch_bounds__(256) l2_read_kernel(const double2 *__restrict_
     if (sx == 1.2345e300 && sy == 1.0) out[0] = sx;  // never true; keeps the loads alive
 }
 
+// The same measurement with the gridder's / degridder's access pattern: every half-warp reads the 15 (of 16) taps of
+// 15 consecutive 256-byte rows of a pseudo-randomly chosen 3840-byte slice, slice after slice -- no arithmetic, no
+// other traffic.  This is the ceiling of "kernel taps streamed from an L2-resident table" for S = 15.
+__global__ void __launch_bounds__(256) l2_slice_read_kernel(const double2 *__restrict__ buf, unsigned nslices, int iters, double *out) {
+    const unsigned hw = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, lane = threadIdx.x & 15;
+    unsigned state = hw * 2654435761u + 12345u;
+    double sx = 0.0, sy = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+        state = state * 1664525u + 1013904223u;
+        const double2 *p = buf + (size_t)((state >> 8) % nslices) * 240 + lane;
+        double2 v[15];
+#pragma unroll
+        for (int r = 0; r < 15; ++r) v[r] = lane < 15 ? __ldcg(p + r * 16) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int r = 0; r < 15; ++r) { sx += v[r].x; sy += v[r].y; }
+    }
+    if (sx == 1.2345e300 && sy == 1.0) out[0] = sx;
+}
+
+// pattern: 0 = fully coalesced stream (skagrid_measure_l2_read_tbs), 1 = random 15x15-tap slices
+extern "C" int skagrid_measure_l2_pattern_tbs(skagrid_ctx *ctx, int64_t bytes, int pattern, double *tbs) {
+    if (pattern == 0) return skagrid_measure_l2_read_tbs(ctx, bytes, tbs);
+    if (!ctx || !tbs || bytes < (1 << 20) || bytes > ((int64_t)1 << 30)) return SKAGRID_EINVAL;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    void *buf, *out;
+    SK_TRY(sk_scratch(ctx, "l2_buf", (size_t)bytes, &buf));
+    SK_TRY(sk_scratch(ctx, "dfma_out", 64, &out));
+    SK_CUDA(ctx, cudaMemsetAsync(buf, 0, (size_t)bytes, ctx->stream));
+    const unsigned nslices = (unsigned)((size_t)bytes / 3840);
+    const int blocks = ctx->sm_count * 8, iters = 512;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        SK_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        l2_slice_read_kernel<<<blocks, 256, 0, ctx->stream>>>((const double2 *)buf, nslices, iters, (double *)out);
+        SK_LAUNCH_CHECK(ctx);
+        SK_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        SK_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        SK_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        const double moved = 3600.0 * iters * 16.0 * blocks;  // useful bytes: 225 taps x 16 B per half-warp and iteration
+        const double t = moved / (ms * 1e-3) / 1e12;
+        if (rep > 0 && t > best) best = t;
+    }
+    *tbs = best;
+    return SKAGRID_OK;
+}
+
 extern "C" int skagrid_measure_l2_read_tbs(skagrid_ctx *ctx, int64_t bytes, double *tbs) {
     if (!ctx || !tbs || bytes < (1 << 20) || bytes > ((int64_t)1 << 30)) return SKAGRID_EINVAL;
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
