@@ -33,6 +33,12 @@ def test_header_compiles_as_c():
     assert r.returncode == 0, r.stderr
 
 
+def test_cpp_mirror_header_compiles():
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-fsyntax-only", "-I" + os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "cpp_smalltest.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():

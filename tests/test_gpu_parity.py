@@ -521,3 +521,17 @@ def test_nan_inf_and_far_off_grid_visibilities_are_dropped(G, orc):
     d = G.convdegrid2(gcf, og, (u2, v2), wb)
     od = orc.convdegrid(gcf, og, u[keep], v[keep], wbin=wb[keep])
     assert rel_err(d[keep], od) < TOL and not d[bad].any()
+
+
+def test_cpp_host_mirror_replays_the_reference_tests(tmp_path):
+    """include/skagrid.hpp (C++ mirror of Gridding.hs / ImageDataset.hs): test/SmallTest.hs and old/BrokenNumbers.hs."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "ska_sdp_accelerate_gridding_b200")
+    exe = str(tmp_path / "cpp_smalltest")
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-I" + os.path.join(root, "include"), os.path.join(root, "tests", "cpp_smalltest.cpp"),
+                        "-L" + pkg, "-lskagrid", "-Wl,-rpath," + pkg, "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "cpp_smalltest ok" in r.stdout
