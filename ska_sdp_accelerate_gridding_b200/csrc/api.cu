@@ -653,10 +653,7 @@ extern "C" int skagrid_aw_gridding(skagrid_ctx *ctx, double theta, int64_t lam, 
         SK_TRY(sk_scale3_dev(ctx, count, (double *)du, (double *)dv, (double *)dw, freq / 299792458.0, 0, ctx->stream));
         void *dwt;
         SK_TRY(sk_scratch(ctx, "aw_wt", (size_t)count * 16, &dwt));
-        std::vector<double> ones((size_t)count * 2);
-        for (i64 k = 0; k < count; ++k) { ones[2 * k] = 1.0; ones[2 * k + 1] = 0.0; }
-        SK_CUDA(ctx, cudaMemcpyAsync(dwt, ones.data(), (size_t)count * 16, cudaMemcpyHostToDevice, ctx->stream));
-        SK_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `ones` is pageable and about to go out of scope
+        SK_TRY(sk_fill_complex_dev(ctx, count, (double *)dwt, 1.0, 0.0, ctx->stream));  // `ones` of src/ImageDataset.hs:58
         SK_TRY(sk_doweight_dev(ctx, n, (double)lam, count, (double *)du, (double *)dv, (double *)dwt, ctx->d_flags + 0, ctx->stream));
         SK_TRY(sk_mirror_dev(ctx, count, (double *)du, (double *)dv, (double *)dw, (double *)dvis, ctx->stream));
         SK_TRY(sk_cmul_dev(ctx, count, (double *)dvis, (double *)dwt, ctx->stream));

@@ -163,6 +163,7 @@ int sk_doweight_dev(skagrid_ctx *ctx, i64 n, double lam, i64 count, const double
 int sk_grid_simple_dev(skagrid_ctx *ctx, i64 h, i64 w, double *grid, i64 count, const double *u,
                        const double *v, const double *vis, cudaStream_t st);
 int sk_cmul_dev(skagrid_ctx *ctx, i64 count, double *a, const double *b, cudaStream_t st);
+int sk_fill_complex_dev(skagrid_ctx *ctx, i64 count, double *a, double re, double im, cudaStream_t st);
 
 int sk_convolve2d_dev(skagrid_ctx *ctx, i64 n, i64 count, const double *a, const i64 *ai, const double *b,
                       const i64 *bi, double *out, int conj_out, cudaStream_t st);

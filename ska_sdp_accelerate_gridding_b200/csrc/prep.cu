@@ -147,3 +147,16 @@ int sk_cmul_dev(skagrid_ctx *ctx, i64 count, double *a, const double *b, cudaStr
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
+
+// a[k] = re + i im (the `ones` vector of src/ImageDataset.hs:58 is built on the device)
+__global__ void __launch_bounds__(256) fill_complex_kernel(i64 count, double2 *__restrict__ a, double re, double im) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) a[k] = make_double2(re, im);
+}
+
+int sk_fill_complex_dev(skagrid_ctx *ctx, i64 count, double *a, double re, double im, cudaStream_t st) {
+    if (count <= 0) return SKAGRID_OK;
+    fill_complex_kernel<<<blocks_for(ctx, count), 256, 0, st>>>(count, (double2 *)a, re, im);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
