@@ -641,7 +641,7 @@ extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const do
             SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_reg_kernel<16, 128, 4, false>, 128, tile_smem));
             degrid_reg_kernel<16, 128, 4, false><<<ctx->sm_count * (per_sm < 1 ? 1 : per_sm), 128, tile_smem, st>>>(A);
         }
-    } else if (variant != 1 && tile_smem <= 200 * 1024) {
+    } else if (variant != 1 && tile_smem <= 110 * 1024) {  // at least two blocks per SM; beyond that the untiled kernel wins (S=63: 110 vs 281 ms per 2e7)
         A.queue = 5;
         SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 5, 0, sizeof(uint32_t), st));
         if (ctx->smem_configured.insert((const void *)degrid_tile_kernel<15, 256>).second) {
