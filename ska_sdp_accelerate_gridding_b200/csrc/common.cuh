@@ -49,7 +49,7 @@ struct Geom {
     i64 height, width, row0, row1;
     i64 nw, qpx, gh, gw;
     int ntx, nty;        // tiles per dimension
-    int R;               // register region edge: 16, 32 or 64 (0: shape not supported by the tiled kernels)
+    int R;               // register region edge: 16, 32, 48 or 64 (0: shape not supported by the tiled kernels)
     int MT;              // micro-tile edge: 2 or 4
     int tile, tshift;    // uv tile edge (16 or 32) and its log2
     int MTR;             // micro-tiles per tile row = tile / MT

@@ -62,6 +62,13 @@ struct MtState {
     int cell[CY][CX];              // shared-memory cell of residue (a,b)
 };
 
+// (x mod R) for x in (-R, 2R); R = 48 is the one region edge that is not a power of two
+template <int R>
+__device__ __forceinline__ int mod_region(int x) {
+    if constexpr ((R & (R - 1)) == 0) return x & (R - 1);
+    else { x += x < 0 ? R : 0; return x >= R ? x - R : x; }
+}
+
 template <int R, int CY, int CX, int MT>
 __device__ __forceinline__ void mt_setup(MtState<CY, CX> &S, uint32_t key, int ty, int tx, const GridArgs &A) {
     constexpr int TY = R / CY;  // thread rows of the block
@@ -71,7 +78,7 @@ __device__ __forceinline__ void mt_setup(MtState<CY, CX> &S, uint32_t key, int t
     uint32_t ym[CY], xm[CX];
 #pragma unroll
     for (int a = 0; a < CY; ++a) {
-        roty[a] = (ty + TY * a - my) & (R - 1);
+        roty[a] = mod_region<R>(ty + TY * a - my);
         ym[a] = 0;
 #pragma unroll
         for (int d = 0; d < MT; ++d)
@@ -79,7 +86,7 @@ __device__ __forceinline__ void mt_setup(MtState<CY, CX> &S, uint32_t key, int t
     }
 #pragma unroll
     for (int b = 0; b < CX; ++b) {
-        rotx[b] = (tx + 16 * b - mx) & (R - 1);
+        rotx[b] = mod_region<R>(tx + 16 * b - mx);
         xm[b] = 0;
 #pragma unroll
         for (int d = 0; d < MT; ++d)
@@ -607,6 +614,7 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
         if (variant == 2) return MT == 2 ? launch_tiled<32, 2, 2, 16>(ctx, A, st) : launch_tiled<32, 4, 2, 16>(ctx, A, st);
         return MT == 2 ? launch_tiled<32, 2, 3, 32>(ctx, A, st) : launch_tiled<32, 4, 3, 32>(ctx, A, st);
     }
+    if (R == 48) return MT == 2 ? launch_tiled<48, 2, 2, 24>(ctx, A, st) : launch_tiled<48, 4, 2, 24>(ctx, A, st);  // 24x16 threads, 2x3 residues each
     return MT == 2 ? launch_tiled<64, 2, 2, 32>(ctx, A, st) : launch_tiled<64, 4, 2, 32>(ctx, A, st);  // 32x16 threads, 2x4 residues each
 }
 

@@ -48,11 +48,11 @@ int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, i64 capacity, Geom *g
     if (in->gh > 127 || in->gw > 127) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel support %lldx%lld above the supported 127", (i64)in->gh, (i64)in->gw);
     g->height = in->height; g->width = in->width; g->row0 = in->row0; g->row1 = in->row1;
     g->nw = in->nw; g->qpx = in->qpx; g->gh = in->gh; g->gw = in->gw;
-    // register region / micro-tile of the tiled kernels: smallest R in {16,32,64} with R >= S+1, then the
+    // register region / micro-tile of the tiled kernels: smallest R in {16,32,48,64} with R >= S+1, then the
     // largest power-of-two micro-tile (<= 4, so that (dy,dx) fits a 16-bit one-hot) whose footprints still fit:
     // MT - 1 + S <= R
     const i64 smax = in->gh > in->gw ? in->gh : in->gw;
-    g->R = smax <= 15 ? 16 : (smax <= 31 ? 32 : (smax <= 63 ? 64 : 0));
+    g->R = smax <= 15 ? 16 : (smax <= 31 ? 32 : (smax <= 47 ? 48 : (smax <= 63 ? 64 : 0)));
     const int rr = g->R ? g->R : 64;
     g->MT = 2;
     while (g->MT < 4 && g->MT * 2 - 1 + smax <= rr) g->MT *= 2;

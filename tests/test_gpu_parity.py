@@ -124,6 +124,9 @@ CASES = [
     (128, (13, 13), 4, 2, 4000, 0.5),
     (160, (5, 11), 3, 2, 3000, 0.5),
     (160, (33, 33), 2, 1, 600, 0.5),
+    (192, (47, 47), 2, 2, 500, 0.5),
+    (200, (49, 49), 1, 1, 300, 0.5),
+    (224, (63, 63), 1, 1, 200, 0.5),
     (64, (1, 1), 1, 1, 1000, 0.5),
     (260, (65, 65), 1, 1, 100, 0.45),
 ]
