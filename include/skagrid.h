@@ -191,6 +191,39 @@ int skagrid_aw_gridding(skagrid_ctx *ctx, double theta, int64_t lam, int64_t nw,
 int skagrid_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *w, int64_t npixff,
                       int64_t npixkern, int64_t qpx, int conjugate, double *out);
 
+/* ================================================================== multi-GPU, single process
+ * ONE host thread drives `nctx` (1..16) contexts, one per device (ctxs[i] from skagrid_create(device_i); contexts on the
+ * same device are allowed).  Everything is enqueued on the contexts' streams, so the devices work concurrently; the
+ * call returns when all of them are done.  Arguments as skagrid_convgrid2 / skagrid_convdegrid2 (nw = 1 and
+ * wbin = NULL give convgrid / convdegrid).  Errors of any context are reported through ctxs[0];
+ * skagrid_last_device_ms(ctxs[0]) covers the whole call.
+ *
+ * _vis  visibility-sharded (BASELINE config 4): context d takes the d-th contiguous share of the visibilities.
+ *       Gridding: full local grids, then a reduce-scatter over NVLink peer memory (context d sums row slab d of every
+ *       peer), the slabs return to `grid` (in/out, accumulated into) over nctx PCIe links in parallel, and an
+ *       all-gather leaves the sum RESIDENT on every context.  grid == NULL: start from zero, no download.
+ *       Degridding: every context uploads one row slab of `grid`, the rest arrives by all-gather; grid == NULL uses
+ *       the resident grids.  The result differs from the single-device one only by summation order.
+ * _tile uv-tile-sharded (BASELINE config 5): context d owns grid rows [bounds[d], bounds[d+1]), chosen at the d/nctx
+ *       quantiles of this batch's footprint rows; visibilities are routed device-to-device to every owner their
+ *       footprint intersects, owners clip taps to their rows (fixoutofbounds, src/Gridding.hs:883-891); no grid
+ *       reduction; degridding returns the owners' partial sums to the source device and adds them.  No context ever
+ *       holds more than its slab of the grid.  bounds_out (nctx+1 values, may be NULL) receives the bounds used. */
+int skagrid_convgrid2_mgpu_vis(skagrid_ctx *const *ctxs, int nctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw,
+                               const double *gcf, int64_t height, int64_t width, double *grid, int64_t count,
+                               const double *u, const double *v, const int64_t *wbin, const double *vis);
+int skagrid_convdegrid2_mgpu_vis(skagrid_ctx *const *ctxs, int nctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw,
+                                 const double *gcf, int64_t height, int64_t width, const double *grid, int64_t count,
+                                 const double *u, const double *v, const int64_t *wbin, double *vis_out);
+int skagrid_convgrid2_mgpu_tile(skagrid_ctx *const *ctxs, int nctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw,
+                                const double *gcf, int64_t height, int64_t width, double *grid, int64_t count,
+                                const double *u, const double *v, const int64_t *wbin, const double *vis,
+                                int64_t *bounds_out);
+int skagrid_convdegrid2_mgpu_tile(skagrid_ctx *const *ctxs, int nctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw,
+                                  const double *gcf, int64_t height, int64_t width, const double *grid, int64_t count,
+                                  const double *u, const double *v, const int64_t *wbin, double *vis_out,
+                                  int64_t *bounds_out);
+
 /* ================================================================== device-resident API
  * All pointers are DEVICE pointers on ctx's device; `stream` is a cudaStream_t passed as void*
  * (NULL = the CUDA legacy default stream).  Work is ordered on that stream only; nothing here

@@ -14,6 +14,12 @@
 static const i64 VIS_CHUNK = (i64)1 << 23;  // visibilities per pipelined chunk of the table gridders
 static const i64 AW_CHUNK = (i64)1 << 15;   // visibilities per chunk of the AW path (one S x S kernel each)
 
+static inline int up(skagrid_ctx *ctx, const char *name, const void *host, size_t bytes, void **dev) { return sk_api_up(ctx, name, host, bytes, dev); }
+static inline int check_flags(skagrid_ctx *ctx, const char *what) { return sk_api_check_flags(ctx, what); }
+static inline int plan_acquire(skagrid_ctx *ctx, const skagrid_geom *geom, i64 capacity, int slice_override, skagrid_plan **out) {
+    return sk_api_plan_acquire(ctx, geom, capacity, slice_override, out);
+}
+
 struct Timer {
     skagrid_ctx *ctx;
     explicit Timer(skagrid_ctx *c) : ctx(c) { cudaEventRecord(ctx->ev0, ctx->stream); }
@@ -27,7 +33,7 @@ struct Timer {
     }
 };
 
-static int enter(skagrid_ctx *ctx) {
+int sk_api_enter(skagrid_ctx *ctx) {
     if (!ctx) return SKAGRID_EINVAL;
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->err.clear();
@@ -35,7 +41,7 @@ static int enter(skagrid_ctx *ctx) {
 }
 
 // scratch + H2D on the compute stream
-static int up(skagrid_ctx *ctx, const char *name, const void *host, size_t bytes, void **dev) {
+int sk_api_up(skagrid_ctx *ctx, const char *name, const void *host, size_t bytes, void **dev) {
     SK_TRY(sk_scratch(ctx, name, bytes ? bytes : 16, dev));
     if (bytes) SK_CUDA(ctx, cudaMemcpyAsync(*dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
     return SKAGRID_OK;
@@ -44,7 +50,7 @@ static int down(skagrid_ctx *ctx, void *host, const void *dev, size_t bytes) {
     if (bytes) SK_CUDA(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return SKAGRID_OK;
 }
-static int check_flags(skagrid_ctx *ctx, const char *what) {
+int sk_api_check_flags(skagrid_ctx *ctx, const char *what) {
     uint32_t f = 0;
     SK_TRY(sk_take_flags(ctx, ctx->stream, &f));
     if (f & 1u) return sk_fail(ctx, SKAGRID_ERANGE, "%s: a w-plane, oversampling or antenna index is out of range", what);
@@ -54,7 +60,7 @@ static int check_flags(skagrid_ctx *ctx, const char *what) {
 
 // The host-pointer functions keep ONE plan alive in the context (cudaMalloc/cudaFree of its ~0.5 GB of buckets and
 // records per call would cost more than the gridding of a small batch); it is reused when the geometry matches.
-static int plan_acquire(skagrid_ctx *ctx, const skagrid_geom *geom, i64 capacity, int slice_override, skagrid_plan **out) {
+int sk_api_plan_acquire(skagrid_ctx *ctx, const skagrid_geom *geom, i64 capacity, int slice_override, skagrid_plan **out) {
     skagrid_plan *p = ctx->cached_plan;
     if (p) {
         const Geom &g = p->g;
@@ -102,7 +108,7 @@ static int grid_fresh(skagrid_ctx *ctx, i64 h, i64 w, void **dgrid) {
 // ------------------------------------------------------------------------------------------ binning
 extern "C" int skagrid_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, int64_t count, const double *p, int64_t *fl, int64_t *frac,
                                   int flags) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, n > 0 && qpx > 0 && count >= 0, "frac_coord: n, qpx must be positive");
     if (count == 0) return SKAGRID_OK;
     NEED(ctx, p && fl && frac, "frac_coord: NULL pointer");
@@ -125,7 +131,7 @@ extern "C" int skagrid_frac_coords(skagrid_ctx *ctx, int64_t height, int64_t wid
 }
 
 extern "C" int skagrid_find_closest(skagrid_ctx *ctx, int64_t nw, const double *wbins, int64_t count, const double *w, int64_t *out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, nw > 0 && count >= 0, "find_closest: empty wbins");
     if (count == 0) return SKAGRID_OK;
     NEED(ctx, wbins && w && out, "find_closest: NULL pointer");
@@ -148,7 +154,7 @@ static int up_uvw(skagrid_ctx *ctx, i64 count, const double *u, const double *v,
 }
 
 extern "C" int skagrid_uvw_lambda(skagrid_ctx *ctx, double freq, int64_t count, double *u, double *v, double *w) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     if (count <= 0) return SKAGRID_OK;
     NEED(ctx, u && v && w, "uvw_lambda: NULL pointer");
     Timer t(ctx);
@@ -163,7 +169,7 @@ extern "C" int skagrid_uvw_lambda(skagrid_ctx *ctx, double freq, int64_t count, 
 }
 
 extern "C" int skagrid_mirror_uvw(skagrid_ctx *ctx, int64_t count, double *u, double *v, double *w, double *vis) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     if (count <= 0) return SKAGRID_OK;
     NEED(ctx, u && v && w && vis, "mirror_uvw: NULL pointer");
     Timer t(ctx);
@@ -182,7 +188,7 @@ extern "C" int skagrid_mirror_uvw(skagrid_ctx *ctx, int64_t count, double *u, do
 static i64 grid_side(double theta, i64 lam) { return (i64)llround(theta * (double)lam); }
 
 extern "C" int skagrid_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *u, const double *v, double *vis) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     if (count <= 0) return SKAGRID_OK;
     NEED(ctx, u && v && vis, "doweight: NULL pointer");
     const i64 n = grid_side(theta, lam);
@@ -202,8 +208,11 @@ extern "C" int skagrid_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int
 // Device-side core: streams `count` host visibilities through a plan in double-buffered chunks.
 //   degrid == 0: d_grid[row0:row1] += sum vis_k * d_table[slice_k]      (vis is the input)
 //   degrid != 0: vis_out[k] = sum conj(d_table[slice_k]) * d_grid[...]  (vis_out is the output, host)
-static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double *d_table, double *d_grid, i64 count, const double *u,
-                        const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam = 0.0) {
+//
+// sk_api_stream_enqueue only enqueues (events order the three streams; no host synchronisation), so one host thread can
+// keep several devices busy (mgpu.cu); sk_api_stream_wait drains the context's streams.
+int sk_api_stream_enqueue(skagrid_ctx *ctx, const skagrid_geom *geom, const double *d_table, double *d_grid, i64 count, const double *u,
+                          const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam) {
     if (count <= 0) return SKAGRID_OK;
     const i64 chunk = std::min<i64>(count, VIS_CHUNK);
     skagrid_plan *plan = nullptr;
@@ -259,17 +268,32 @@ static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double
         }
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_done[b], ctx->stream);
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    else cudaStreamSynchronize(ctx->stream);
-    cudaStreamSynchronize(ctx->copy_stream);
-    {
-        const cudaError_t e2 = cudaStreamSynchronize(ctx->d2h_stream);
-        if (e == cudaSuccess) e = e2;
+    // later work on the compute stream (a reduction, a D2H of the grid) must also see the degridder's result copies
+    if (e == cudaSuccess && degrid) {
+        e = cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[0], 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[1], 0);
     }
     plan_release(ctx, plan);
     if (rc) return rc;
     if (e != cudaSuccess) return sk_fail(ctx, SKAGRID_ECUDA, "table gridder: %s", cudaGetErrorString(e));
     return SKAGRID_OK;
+}
+
+int sk_api_stream_wait(skagrid_ctx *ctx) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    const cudaError_t e1 = cudaStreamSynchronize(ctx->copy_stream);
+    const cudaError_t e2 = cudaStreamSynchronize(ctx->d2h_stream);
+    if (e == cudaSuccess) e = e1;
+    if (e == cudaSuccess) e = e2;
+    if (e != cudaSuccess) return sk_fail(ctx, SKAGRID_ECUDA, "table gridder: %s", cudaGetErrorString(e));
+    return SKAGRID_OK;
+}
+
+static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double *d_table, double *d_grid, i64 count, const double *u,
+                        const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam = 0.0) {
+    const int rc = sk_api_stream_enqueue(ctx, geom, d_table, d_grid, count, u, v, wbin, vis, vis_out, degrid, lam);
+    const int rw = sk_api_stream_wait(ctx);  // always drain, also after a failed enqueue
+    return rc ? rc : rw;
 }
 
 static int check_table_args(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 gh, i64 gw, i64 height, i64 width, i64 count) {
@@ -281,7 +305,7 @@ static int check_table_args(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 gh, i64 gw, i
 
 static int table_host(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 gh, i64 gw, const double *gcf, i64 height, i64 width, double *grid, i64 count,
                       const double *u, const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, const char *what) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     SK_TRY(check_table_args(ctx, nw, qpx, gh, gw, height, width, count));
     NEED(ctx, gcf, "NULL kernel table");
     if (count > 0) NEED(ctx, u && v && (degrid ? vis_out != nullptr : vis != nullptr), "NULL visibility array");
@@ -323,7 +347,7 @@ extern "C" int skagrid_convdegrid2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, in
 
 extern "C" int skagrid_grid(skagrid_ctx *ctx, int64_t height, int64_t width, double *grid, int64_t count, const double *u, const double *v,
                             const double *vis) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, height > 0 && width > 0 && grid && count >= 0, "grid: bad size or NULL grid");
     if (count == 0) return SKAGRID_OK;
     NEED(ctx, u && v && vis, "grid: NULL visibility array");
@@ -376,7 +400,7 @@ static int aw_core_dev(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 s, const double *d
 static int aw_host(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 s, const double *wkerns, i64 nant, const double *akerns, i64 height, i64 width,
                    double *grid, i64 count, const double *u, const double *v, const int64_t *wbin, const int64_t *a1, const int64_t *a2,
                    const double *vis, double *vis_out, int degrid, const char *what) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     SK_TRY(check_table_args(ctx, nw, qpx, s, s, height, width, count));
     NEED(ctx, nant > 0 && wkerns && akerns && grid, "NULL kernels / grid or nant <= 0");
     NEED(ctx, s <= 63, "AW path: support above 63 is not supported");
@@ -416,7 +440,7 @@ extern "C" int skagrid_convdegrid_aw(skagrid_ctx *ctx, int64_t nw, int64_t qpx, 
 }
 
 extern "C" int skagrid_convolve2d(skagrid_ctx *ctx, int64_t n, const double *a1, const double *a2, double *out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, n > 0 && n <= 64 && a1 && a2 && out, "convolve2d: size outside [1,64] or NULL pointer");
     Timer t(ctx);
     void *d1, *d2, *dout;
@@ -431,7 +455,7 @@ extern "C" int skagrid_convolve2d(skagrid_ctx *ctx, int64_t n, const double *a1,
 extern "C" int skagrid_aw_kernel(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t s, const double *wkerns, int64_t nant,
                                  const double *akerns, int64_t count, const int64_t *wbin, const int64_t *yf, const int64_t *xf,
                                  const int64_t *a1, const int64_t *a2, double *out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, nw > 0 && qpx > 0 && s > 0 && s <= 64 && nant > 0 && count >= 0, "aw_kernel: bad dimension");
     if (count == 0) return SKAGRID_OK;
     NEED(ctx, wkerns && akerns && wbin && yf && xf && a1 && a2 && out, "aw_kernel: NULL pointer");
@@ -454,7 +478,7 @@ extern "C" int skagrid_aw_kernel(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int6
 
 // ------------------------------------------------------------------------------------------ grid -> image
 extern "C" int skagrid_make_grid_hermitian(skagrid_ctx *ctx, int64_t n, const double *grid, double *out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, n > 0 && grid && out, "make_grid_hermitian: bad size or NULL pointer");
     Timer t(ctx);
     void *dg;
@@ -465,7 +489,7 @@ extern "C" int skagrid_make_grid_hermitian(skagrid_ctx *ctx, int64_t n, const do
 }
 
 extern "C" int skagrid_ifft(skagrid_ctx *ctx, int64_t n, const double *grid, double *out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, n > 0 && grid && out, "ifft: bad size or NULL pointer");
     Timer t(ctx);
     void *dg;
@@ -477,7 +501,7 @@ extern "C" int skagrid_ifft(skagrid_ctx *ctx, int64_t n, const double *grid, dou
 
 extern "C" int skagrid_fft(skagrid_ctx *ctx, int64_t n, const double *grid, double *out) {
     // src/Gridding.hs:821-826: pad to the next power of two (transposing padder), centred forward FFT, crop
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, n > 0 && grid && out, "fft: bad size or NULL pointer");
     Timer t(ctx);
     i64 big = 1;
@@ -499,7 +523,7 @@ extern "C" int skagrid_fft(skagrid_ctx *ctx, int64_t n, const double *grid, doub
 }
 
 extern "C" int skagrid_grid_to_image(skagrid_ctx *ctx, int64_t n, const double *grid, double *image, double *max_out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, n > 0, "grid_to_image: bad size");
     Timer t(ctx);
     void *dg, *dimg = nullptr, *dmax;
@@ -513,7 +537,7 @@ extern "C" int skagrid_grid_to_image(skagrid_ctx *ctx, int64_t n, const double *
 }
 
 extern "C" int skagrid_dev_grid_to_image(skagrid_ctx *ctx, int64_t n, double *grid, double *image, double *max_out, void *stream) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, n > 0 && grid, "dev_grid_to_image: bad size or NULL grid");
     return sk_grid_to_image_dev(ctx, n, grid, image, max_out, sk_stream(ctx, stream));
 }
@@ -521,7 +545,7 @@ extern "C" int skagrid_dev_grid_to_image(skagrid_ctx *ctx, int64_t n, double *gr
 // ------------------------------------------------------------------------------------------ imaging drivers
 extern "C" int skagrid_simple_imaging(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *u, const double *v,
                                       const double *w, const double *vis, double *grid_out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     const i64 n = grid_side(theta, lam);
     NEED(ctx, n > 0 && grid_out && count >= 0, "simple_imaging: bad size or NULL grid");
     (void)w;
@@ -547,7 +571,7 @@ extern "C" int skagrid_simple_imaging(skagrid_ctx *ctx, double theta, int64_t la
 
 extern "C" int skagrid_conv_imaging(skagrid_ctx *ctx, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, double theta, int64_t lam,
                                     int64_t count, const double *u, const double *v, const double *w, const double *vis, double *grid_out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     const i64 n = grid_side(theta, lam);
     SK_TRY(check_table_args(ctx, 1, qpx, gh, gw, n, n, count));
     NEED(ctx, gcf && grid_out, "conv_imaging: NULL kernel or grid");
@@ -586,7 +610,7 @@ extern "C" int skagrid_conv_imaging(skagrid_ctx *ctx, int64_t qpx, int64_t gh, i
 extern "C" int skagrid_conv_imaging2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, double theta,
                                      int64_t lam, int64_t count, const double *u, const double *v, const double *w, const int64_t *wbin,
                                      const double *vis, double *grid_out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     const i64 n = grid_side(theta, lam);
     SK_TRY(check_table_args(ctx, nw, qpx, gh, gw, n, n, count));
     NEED(ctx, gcf, "conv_imaging2: NULL kernel table");
@@ -628,7 +652,7 @@ extern "C" int skagrid_aw_gridding(skagrid_ctx *ctx, double theta, int64_t lam, 
                                    const double *wbins, int64_t nant, const double *akerns, int64_t count, const double *u_m,
                                    const double *v_m, const double *w_m, const int64_t *a1, const int64_t *a2, double freq,
                                    const double *vis, double *image, double *max_out, double *grid_out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     const i64 n = grid_side(theta, lam);
     SK_TRY(check_table_args(ctx, nw, qpx, s, s, n, n, count));
     NEED(ctx, nant > 0 && wkerns && wbins && akerns, "aw_gridding: NULL kernels or nant <= 0");
@@ -676,7 +700,7 @@ extern "C" int skagrid_aw_gridding(skagrid_ctx *ctx, double theta, int64_t lam, 
 // ------------------------------------------------------------------------------------------ w-kernels
 extern "C" int skagrid_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *w, int64_t npixff, int64_t npixkern, int64_t qpx,
                                  int conjugate, double *out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, nw > 0 && w && out, "w_kernels: NULL pointer or nw <= 0");
     Timer t(ctx);
     const size_t bytes = (size_t)(nw * qpx * qpx * npixkern * npixkern) * 16;
@@ -690,7 +714,7 @@ extern "C" int skagrid_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, con
 // Device-output variant used by bench.py to build the kernel table without a host round trip.
 extern "C" int skagrid_dev_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *w_host, int64_t npixff, int64_t npixkern,
                                      int64_t qpx, int conjugate, double *d_out, void *stream) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, nw > 0 && w_host && d_out, "dev_w_kernels: NULL pointer or nw <= 0");
     return sk_w_kernels_dev(ctx, theta, nw, w_host, npixff, npixkern, qpx, conjugate, d_out, sk_stream(ctx, stream));
 }
@@ -699,7 +723,7 @@ extern "C" int skagrid_dev_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw,
 // of its bit-exact y cell).
 extern "C" int skagrid_dev_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, int64_t count, const double *d_p, int64_t *d_fl,
                                       int64_t *d_frac, int flags, void *stream) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, n > 0 && qpx > 0 && count >= 0, "dev_frac_coord: n, qpx must be positive");
     if (count == 0) return SKAGRID_OK;
     NEED(ctx, d_p && d_fl && d_frac, "dev_frac_coord: NULL pointer");
@@ -711,14 +735,14 @@ extern "C" int skagrid_dev_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, 
 // resident (same kernels as the host-pointer functions above).
 extern "C" int skagrid_dev_uvw_scale(skagrid_ctx *ctx, int64_t count, double *d_u, double *d_v, double *d_w, double a, int divide,
                                      void *stream) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     if (count <= 0) return SKAGRID_OK;
     NEED(ctx, d_u && d_v && d_w, "dev_uvw_scale: NULL pointer");
     return sk_scale3_dev(ctx, count, d_u, d_v, d_w, a, divide, sk_stream(ctx, stream));
 }
 
 extern "C" int skagrid_dev_mirror_uvw(skagrid_ctx *ctx, int64_t count, double *d_u, double *d_v, double *d_w, double *d_vis, void *stream) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     if (count <= 0) return SKAGRID_OK;
     NEED(ctx, d_u && d_v && d_w, "dev_mirror_uvw: NULL pointer");
     return sk_mirror_dev(ctx, count, d_u, d_v, d_w, d_vis, sk_stream(ctx, stream));
@@ -726,7 +750,7 @@ extern "C" int skagrid_dev_mirror_uvw(skagrid_ctx *ctx, int64_t count, double *d
 
 extern "C" int skagrid_dev_find_closest(skagrid_ctx *ctx, int64_t nw, const double *d_wbins, int64_t count, const double *d_w,
                                         int64_t *d_out, void *stream) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     NEED(ctx, nw > 0, "dev_find_closest: empty wbins");
     if (count <= 0) return SKAGRID_OK;
     NEED(ctx, d_wbins && d_w && d_out, "dev_find_closest: NULL pointer");
@@ -736,7 +760,7 @@ extern "C" int skagrid_dev_find_closest(skagrid_ctx *ctx, int64_t nw, const doub
 // Out-of-grid visibilities set bit 1 of the context's error word; skagrid_dev_take_error reads and clears it.
 extern "C" int skagrid_dev_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u, const double *d_v,
                                     double *d_vis, void *stream) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     if (count <= 0) return SKAGRID_OK;
     NEED(ctx, d_u && d_v && d_vis, "dev_doweight: NULL pointer");
     const i64 n = grid_side(theta, lam);
@@ -745,7 +769,7 @@ extern "C" int skagrid_dev_doweight(skagrid_ctx *ctx, double theta, int64_t lam,
 }
 
 extern "C" int skagrid_dev_take_error(skagrid_ctx *ctx, void *stream, int *flags_out) {
-    SK_TRY(enter(ctx));
+    SK_TRY(sk_api_enter(ctx));
     uint32_t f = 0;
     SK_TRY(sk_take_flags(ctx, sk_stream(ctx, stream), &f));
     if (flags_out) *flags_out = (int)f;

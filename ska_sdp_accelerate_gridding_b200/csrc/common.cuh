@@ -94,6 +94,7 @@ struct skagrid_ctx {
     cudaStream_t copy_stream = nullptr; // H2D prefetch stream of the chunked host API
     cudaStream_t d2h_stream = nullptr;  // D2H stream of the chunked degridder (results leave while the next chunk computes)
     cudaEvent_t ev_k[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    cudaEvent_t ev_mg[2] = {nullptr, nullptr};  // multi-device entry points: [0] local phase done, [1] exchange phase done
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_copy[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
     std::string err;
     uint32_t *d_flags = nullptr;        // device error word: bit0 index out of range, bit1 cell outside the weight grid
@@ -179,6 +180,15 @@ int sk_grid_to_image_dev(skagrid_ctx *ctx, i64 n, double *grid, double *image, d
 int sk_pad_crop_dev(skagrid_ctx *ctx, i64 n_in, const double *in, i64 n_out, double *out, cudaStream_t st);
 int sk_w_kernels_dev(skagrid_ctx *ctx, double theta, i64 nw, const double *w, i64 npixff, i64 npixkern,
                      i64 qpx, int conjugate, double *out, cudaStream_t st);
+
+// host-pointer plumbing of api.cu shared with the multi-device entry points (mgpu.cu)
+int sk_api_enter(skagrid_ctx *ctx);  // cudaSetDevice + clear the error string
+int sk_api_up(skagrid_ctx *ctx, const char *name, const void *host, size_t bytes, void **dev);  // named scratch + H2D on ctx->stream
+int sk_api_check_flags(skagrid_ctx *ctx, const char *what);
+int sk_api_plan_acquire(skagrid_ctx *ctx, const skagrid_geom *geom, i64 capacity, int slice_override, skagrid_plan **out);
+int sk_api_stream_enqueue(skagrid_ctx *ctx, const skagrid_geom *geom, const double *d_table, double *d_grid, i64 count, const double *u,
+                          const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam);
+int sk_api_stream_wait(skagrid_ctx *ctx);
 
 // ---------------------------------------------------------------------------------------------
 // device helpers

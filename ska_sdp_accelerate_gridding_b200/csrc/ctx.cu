@@ -68,7 +68,8 @@ extern "C" int skagrid_create(int device, skagrid_ctx **out) {
         ok = cudaEventCreateWithFlags(&ctx->ev_copy[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&ctx->ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
-             cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess;
+             cudaEventCreateWithFlags(&ctx->ev_d2h[i], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_mg[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_flags, 16 * sizeof(uint32_t)) == cudaSuccess && cudaMemset(ctx->d_flags, 0, 16 * sizeof(uint32_t)) == cudaSuccess;
     if (!ok) { skagrid_destroy(ctx); return sk_fail(nullptr, SKAGRID_ECUDA, "stream/event creation failed"); }
     *out = ctx;
@@ -88,6 +89,7 @@ extern "C" void skagrid_destroy(skagrid_ctx *ctx) {
         if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]);
         if (ctx->ev_k[i]) cudaEventDestroy(ctx->ev_k[i]);
         if (ctx->ev_d2h[i]) cudaEventDestroy(ctx->ev_d2h[i]);
+        if (ctx->ev_mg[i]) cudaEventDestroy(ctx->ev_mg[i]);
     }
     if (ctx->d_flags) cudaFree(ctx->d_flags);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);

@@ -293,13 +293,20 @@ def fft(g, ctx=None):
     return out
 
 
-def grid_to_image(g, want_image=True, ctx=None):
-    """make_grid_hermitian -> ifft -> map real -> maximum, fused (src/ImageDataset.hs:74-77) -> (image, max)."""
+def grid_to_image(g, want_image=True, ctx=None, n=None):
+    """make_grid_hermitian -> ifft -> map real -> maximum, fused (src/ImageDataset.hs:74-77) -> (image, max).
+    g=None with n: the n x n grid the previous call left on the context's device."""
     ctx = ctx or get_context()
-    g = c128(g)
-    img = np.empty(g.shape, np.float64) if want_image else None
+    if g is None:
+        if n is None:
+            raise ValueError("grid_to_image: g=None needs n")
+        shape = (int(n), int(n))
+    else:
+        g = c128(g)
+        shape = g.shape
+    img = np.empty(shape, np.float64) if want_image else None
     mx = np.empty(1, np.float64)
-    ctx.check(ctx.lib.skagrid_grid_to_image(ctx.h, g.shape[0], ptr(g), ptr(img), ptr(mx)))
+    ctx.check(ctx.lib.skagrid_grid_to_image(ctx.h, shape[0], ptr(g), ptr(img), ptr(mx)))
     return img, float(mx[0])
 
 

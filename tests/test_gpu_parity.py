@@ -538,3 +538,94 @@ def test_cpp_host_mirror_replays_the_reference_tests(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "cpp_smalltest ok" in r.stdout
+
+
+# ------------------------------------------------------------------------------------------------ single-process multi-GPU ABI
+def _mg_devices(k):
+    import torch
+    nd = torch.cuda.device_count()
+    return [i % nd for i in range(k)]  # distinct devices when the box has them, else several contexts on one device
+
+
+@pytest.mark.parametrize("nctx", [1, 2, 3])
+@pytest.mark.parametrize("mode", ["vis", "tile"])
+def test_mgpu_abi_parity(orc, nctx, mode):
+    """skagrid_conv(de)grid2_mgpu_{vis,tile}: one host thread, nctx contexts; same grid / visibilities as the oracle."""
+    from ska_sdp_accelerate_gridding_b200.multi_device import MultiDevice
+    rng = np.random.default_rng(77 + nctx)
+    n, s, qpx, nw, count = 320, 15, 4, 3, 30011
+    gcf = _rand_c(rng, (nw, qpx, qpx, s, s))
+    # core-dominated rows (so the balanced slabs differ from equal ones) plus footprints hanging over every grid edge
+    u = rng.uniform(-0.52, 0.52, count)
+    v = np.where(rng.random(count) < 0.7, rng.normal(0.17, 0.05, count), rng.uniform(-0.52, 0.52, count))
+    wb = rng.integers(0, nw, count)
+    vis = _rand_c(rng, count)
+    start = _rand_c(rng, (n, n))
+    md = MultiDevice(_mg_devices(nctx))
+    try:
+        g = md.convgrid2(gcf, start, (u, v), wb, vis, mode=mode)
+        og = orc.convgrid(gcf, start, u, v, vis, wbin=wb)
+        assert rel_err(g, og) < TOL
+        d = md.convdegrid2(gcf, og, (u, v), wb, mode=mode)
+        od = orc.convdegrid(gcf, og, u, v, wbin=wb)
+        assert rel_err(d, od) < TOL
+        if mode == "tile":
+            b = md.bounds
+            assert b[0] == 0 and b[-1] == n and all(b[i] < b[i + 1] for i in range(nctx))
+            if nctx > 1:
+                assert b != [n * i // nctx for i in range(nctx + 1)]  # quantiles of the row histogram, not equal heights
+        # fewer visibilities than contexts, none at all, and the 4-D table form (nw = 1, no wbin)
+        g2 = md.convgrid2(gcf, start, (u[:1], v[:1]), wb[:1], vis[:1], mode=mode)
+        assert rel_err(g2, orc.convgrid(gcf, start, u[:1], v[:1], vis[:1], wbin=wb[:1])) < TOL
+        g0 = md.convgrid2(gcf, start, (u[:0], v[:0]), wb[:0], vis[:0], mode=mode)
+        assert np.array_equal(g0, start)
+        assert md.convdegrid2(gcf, og, (u[:0], v[:0]), wb[:0], mode=mode).size == 0
+        g4 = md.convgrid2(gcf[0], start, (u, v), None, vis, mode=mode)
+        assert rel_err(g4, orc.convgrid(gcf[:1], start, u, v, vis, wbin=np.zeros(count, np.int64))) < TOL
+    finally:
+        md.close()
+
+
+def test_mgpu_abi_resident_chain_and_errors(G, orc):
+    """Visibility-sharded gridding leaves the summed grid on every context: degridding and grid_to_image then take
+    grid == NULL.  Range errors of any context surface through the first one."""
+    import ctypes as C
+    from ska_sdp_accelerate_gridding_b200 import _lib
+    from ska_sdp_accelerate_gridding_b200.multi_device import MultiDevice
+    rng = np.random.default_rng(5)
+    n, s, qpx, nw, count = 256, 9, 2, 2, 9000
+    gcf = _rand_c(rng, (nw, qpx, qpx, s, s))
+    u, v = rng.uniform(-0.45, 0.45, count), rng.uniform(-0.45, 0.45, count)
+    wb = rng.integers(0, nw, count)
+    vis = _rand_c(rng, count)
+    md = MultiDevice(_mg_devices(2))
+    try:
+        with pytest.raises(_lib.SkagridError) as e:  # nothing resident yet
+            md._resident_shape = (n, n)
+            md.convdegrid2(gcf, None, (u, v), wb)
+        assert e.value.code == -1
+        og = orc.convgrid(gcf, np.zeros((n, n), complex), u, v, vis, wbin=wb)
+        oimg = np.real(orc.ifft(orc.make_grid_hermitian(og)))
+        md.conv_grid_resident(gcf, (n, n), (u, v), wb, vis)
+        d = md.convdegrid2(gcf, None, (u, v), wb)
+        assert rel_err(d, orc.convdegrid(gcf, og, u, v, wbin=wb)) < TOL
+        for c in md.ctxs:  # every context holds the full sum
+            img, mx = G.grid_to_image(None, ctx=c, n=n)
+            assert rel_err(img, oimg) < TOL and abs(mx - oimg.max()) <= TOL * abs(oimg.max())
+        assert md.last_device_ms > 0.0
+        bad = wb.copy()
+        bad[-1] = nw  # lands in the last context's share
+        for mode in ("vis", "tile"):
+            with pytest.raises(_lib.SkagridError) as e:
+                md.convgrid2(gcf, np.zeros((n, n), complex), (u, v), bad, vis, mode=mode)
+            assert e.value.code == -5
+        # argument errors: the same context twice, no contexts
+        twice = (C.c_void_p * 2)(md.ctxs[0].h, md.ctxs[0].h)
+        g = np.zeros((n, n), complex)
+        rc = md.lib.skagrid_convgrid2_mgpu_vis(twice, 2, nw, qpx, s, s, gcf.ctypes.data, n, n, g.ctypes.data, 0, None, None, None, None)
+        assert rc == -1 and b"twice" in md.lib.skagrid_last_error(md.ctxs[0].h)
+        assert md.lib.skagrid_convgrid2_mgpu_vis(twice, 0, nw, qpx, s, s, gcf.ctypes.data, n, n, g.ctypes.data, 0, None, None, None, None) == -1
+        # and the contexts stay usable
+        assert rel_err(md.convgrid2(gcf, np.zeros((n, n), complex), (u, v), wb, vis), og) < TOL
+    finally:
+        md.close()
