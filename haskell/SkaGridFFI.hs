@@ -16,6 +16,7 @@ module SkaGridFFI
   ( Ctx, withSkaGrid
   , fracCoords, findClosestV, mirrorUvw, doweight
   , convgrid, convgrid2, convgridAW, convdegrid2, convdegridAW
+  , withSkaGrids, MultiMode(..), convgrid2Multi, convdegrid2Multi
   , makeGridHermitian, ifft, gridToImage, awImaging, awGridding
   ) where
 
@@ -29,6 +30,7 @@ import Foreign.C.String (CString, peekCString)
 import Foreign.C.Types (CDouble(..), CInt(..))
 import Foreign.ForeignPtr (ForeignPtr, castForeignPtr, mallocForeignPtrArray, withForeignPtr)
 import Foreign.Marshal.Alloc (alloca)
+import Foreign.Marshal.Array (withArrayLen)
 import Foreign.Ptr (Ptr, nullPtr)
 import Foreign.Storable (peek)
 
@@ -63,6 +65,19 @@ foreign import ccall safe "skagrid_convdegrid2"  c_convdegrid2
 foreign import ccall safe "skagrid_convdegrid_aw" c_convdegrid_aw
   :: Ctx -> Int64 -> Int64 -> Int64 -> Ptr Double -> Int64 -> Ptr Double -> Int64 -> Int64 -> Ptr Double
   -> Int64 -> Ptr Double -> Ptr Double -> Ptr Int64 -> Ptr Int64 -> Ptr Int64 -> Ptr Double -> IO CInt
+-- single-process multi-GPU: an array of contexts, one per device (include/skagrid.h, "multi-GPU, single process")
+foreign import ccall safe "skagrid_convgrid2_mgpu_vis"    c_convgrid2_mgpu_vis
+  :: Ptr Ctx -> CInt -> Int64 -> Int64 -> Int64 -> Int64 -> Ptr Double -> Int64 -> Int64 -> Ptr Double
+  -> Int64 -> Ptr Double -> Ptr Double -> Ptr Int64 -> Ptr Double -> IO CInt
+foreign import ccall safe "skagrid_convdegrid2_mgpu_vis"  c_convdegrid2_mgpu_vis
+  :: Ptr Ctx -> CInt -> Int64 -> Int64 -> Int64 -> Int64 -> Ptr Double -> Int64 -> Int64 -> Ptr Double
+  -> Int64 -> Ptr Double -> Ptr Double -> Ptr Int64 -> Ptr Double -> IO CInt
+foreign import ccall safe "skagrid_convgrid2_mgpu_tile"   c_convgrid2_mgpu_tile
+  :: Ptr Ctx -> CInt -> Int64 -> Int64 -> Int64 -> Int64 -> Ptr Double -> Int64 -> Int64 -> Ptr Double
+  -> Int64 -> Ptr Double -> Ptr Double -> Ptr Int64 -> Ptr Double -> Ptr Int64 -> IO CInt
+foreign import ccall safe "skagrid_convdegrid2_mgpu_tile" c_convdegrid2_mgpu_tile
+  :: Ptr Ctx -> CInt -> Int64 -> Int64 -> Int64 -> Int64 -> Ptr Double -> Int64 -> Int64 -> Ptr Double
+  -> Int64 -> Ptr Double -> Ptr Double -> Ptr Int64 -> Ptr Double -> Ptr Int64 -> IO CInt
 foreign import ccall safe "skagrid_make_grid_hermitian" c_hermitian :: Ctx -> Int64 -> Ptr Double -> Ptr Double -> IO CInt
 foreign import ccall safe "skagrid_ifft"         c_ifft        :: Ctx -> Int64 -> Ptr Double -> Ptr Double -> IO CInt
 foreign import ccall safe "skagrid_grid_to_image" c_grid_to_image
@@ -174,6 +189,47 @@ convdegrid2 ctx gcf grid u v wbin = do
     withForeignPtr (toForeignPtrs v) $ \pv -> withForeignPtr (toForeignPtrs wbin) $ \pwb -> withForeignPtr out $ \po ->
       c_convdegrid2 ctx (fromIntegral nw) (fromIntegral qpx) (fromIntegral gh) (fromIntegral gw) pk (fromIntegral h) (fromIntegral w) pg
                     (fromIntegral n) pu pv pwb po >>= check ctx "convdegrid2"
+  return (fromForeignPtrs (Z :. n) (castForeignPtr out))
+
+-- | One context per CUDA device, for the multi-GPU calls below (errors are reported through the first context).
+withSkaGrids :: [Int] -> ([Ctx] -> IO a) -> IO a
+withSkaGrids []       k = k []
+withSkaGrids (d : ds) k = withSkaGrid d $ \c -> withSkaGrids ds (k . (c :))
+
+-- | VisSharded: contiguous shares of the visibilities + reduce (BASELINE config 4);
+--   TileSharded: row slabs of the grid + device-to-device routing (config 5).
+data MultiMode = VisSharded | TileSharded
+
+-- | convgrid2 over several devices, driven by this one thread; the grid is accumulated in place.
+convgrid2Multi :: MultiMode -> [Ctx] -> Array DIM5 Visibility -> (Int, Int) -> ForeignPtr Double
+               -> Vector F -> Vector F -> Vector Int64 -> Vector Visibility -> IO ()
+convgrid2Multi mode ctxs gcf (h, w) grid u v wbin vis = do
+  let Z :. nw :. qpx :. _ :. gh :. gw = arrayShape gcf
+      i = fromIntegral
+  withArrayLen ctxs $ \nc pc -> withForeignPtr (cplxPtr gcf) $ \pk -> withForeignPtr grid $ \pg ->
+    withForeignPtr (toForeignPtrs u) $ \pu -> withForeignPtr (toForeignPtrs v) $ \pv ->
+    withForeignPtr (toForeignPtrs wbin) $ \pwb -> withForeignPtr (cplxPtr vis) $ \pvis ->
+      (case mode of
+         VisSharded  -> c_convgrid2_mgpu_vis  pc (i nc) (i nw) (i qpx) (i gh) (i gw) pk (i h) (i w) pg (i (arraySize u)) pu pv pwb pvis
+         TileSharded -> c_convgrid2_mgpu_tile pc (i nc) (i nw) (i qpx) (i gh) (i gw) pk (i h) (i w) pg (i (arraySize u)) pu pv pwb pvis nullPtr)
+        >>= check (head ctxs) "convgrid2Multi"
+
+-- | adjoint of convgrid2Multi
+convdegrid2Multi :: MultiMode -> [Ctx] -> Array DIM5 Visibility -> Array DIM2 Visibility
+                 -> Vector F -> Vector F -> Vector Int64 -> IO (Vector Visibility)
+convdegrid2Multi mode ctxs gcf grid u v wbin = do
+  let Z :. nw :. qpx :. _ :. gh :. gw = arrayShape gcf
+      Z :. h :. w = arrayShape grid
+      n = arraySize u
+      i = fromIntegral
+  out <- newCplx n
+  withArrayLen ctxs $ \nc pc -> withForeignPtr (cplxPtr gcf) $ \pk -> withForeignPtr (cplxPtr grid) $ \pg ->
+    withForeignPtr (toForeignPtrs u) $ \pu -> withForeignPtr (toForeignPtrs v) $ \pv ->
+    withForeignPtr (toForeignPtrs wbin) $ \pwb -> withForeignPtr out $ \po ->
+      (case mode of
+         VisSharded  -> c_convdegrid2_mgpu_vis  pc (i nc) (i nw) (i qpx) (i gh) (i gw) pk (i h) (i w) pg (i n) pu pv pwb po
+         TileSharded -> c_convdegrid2_mgpu_tile pc (i nc) (i nw) (i qpx) (i gh) (i gw) pk (i h) (i w) pg (i n) pu pv pwb po nullPtr)
+        >>= check (head ctxs) "convdegrid2Multi"
   return (fromForeignPtrs (Z :. n) (castForeignPtr out))
 
 -- | adjoint of convgrid3/4

@@ -105,6 +105,8 @@ struct skagrid_ctx {
     std::map<i64, DevBuf> fft_work;
     i64 resident_h = 0, resident_w = 0;   // shape of the grid the last host-pointer call left in the "grid" scratch (0: none)
     std::set<const void *> smem_configured;  // kernels whose dynamic shared-memory limit was raised on this device
+    void *h_pinned = nullptr;             // pinned host staging of the multi-device calls (sk_host_scratch)
+    size_t h_pinned_bytes = 0;
     skagrid_plan *cached_plan = nullptr;  // plan kept between host-pointer calls (api.cu plan_acquire)
 };
 
@@ -138,6 +140,7 @@ int sk_fail(skagrid_ctx *ctx, int code, const char *fmt, ...);
 
 // named, growable device scratch (never shrinks; contents undefined after a grow)
 int sk_scratch(skagrid_ctx *ctx, const char *name, size_t bytes, void **out);
+int sk_host_scratch(skagrid_ctx *ctx, size_t bytes, void **out);  // one pinned host buffer per context, grown on demand
 // device-resident API: the caller's stream as is; NULL is the CUDA (legacy) default stream, which is what
 // torch uses unless told otherwise -- NOT the context's private stream, or launches would race the caller's work
 static inline cudaStream_t sk_stream(skagrid_ctx *ctx, void *s) { (void)ctx; return (cudaStream_t)s; }

@@ -39,6 +39,22 @@ int sk_scratch(skagrid_ctx *ctx, const char *name, size_t bytes, void **out) {
     return SKAGRID_OK;
 }
 
+// pinned host staging (small control data of the multi-device calls: histograms, counters), grown on demand
+int sk_host_scratch(skagrid_ctx *ctx, size_t bytes, void **out) {
+    if (ctx->h_pinned_bytes < bytes) {
+        if (ctx->h_pinned) { cudaFreeHost(ctx->h_pinned); ctx->h_pinned = nullptr; ctx->h_pinned_bytes = 0; }
+        const cudaError_t e = cudaMallocHost(&ctx->h_pinned, bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ctx->h_pinned = nullptr;
+            return sk_fail(ctx, SKAGRID_ENOMEM, "cudaMallocHost(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        ctx->h_pinned_bytes = bytes;
+    }
+    *out = ctx->h_pinned;
+    return SKAGRID_OK;
+}
+
 extern "C" int skagrid_create(int device, skagrid_ctx **out) {
     if (!out) return SKAGRID_EINVAL;
     *out = nullptr;
@@ -92,6 +108,7 @@ extern "C" void skagrid_destroy(skagrid_ctx *ctx) {
         if (ctx->ev_mg[i]) cudaEventDestroy(ctx->ev_mg[i]);
     }
     if (ctx->d_flags) cudaFree(ctx->d_flags);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);

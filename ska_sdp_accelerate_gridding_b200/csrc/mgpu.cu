@@ -16,6 +16,9 @@
 // Contexts on the same device are allowed (the exchange then degenerates to device-local copies), which is how the
 // single-GPU test-suite exercises this file.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -60,14 +63,28 @@ __device__ __forceinline__ int mg_owner(const MgBounds &B, i64 row) {
     return g;
 }
 
-__global__ void __launch_bounds__(256) mg_row_hist_kernel(i64 count, const double *__restrict__ v, i64 height, i64 qpx, i64 gh,
-                                                          uint32_t *__restrict__ hist) {
+// Histogram of footprint-centre rows.  SKA1-Low coverage piles most visibilities onto a few hundred rows, so the counts
+// are privatised per block in shared memory (rows <= MG_HIST_SMEM_ROWS) and merged once; taller grids count in global memory.
+constexpr i64 MG_HIST_SMEM_ROWS = 49152;  // 192 KB of counters
+__global__ void __launch_bounds__(1024) mg_row_hist_kernel(i64 count, const double *__restrict__ v, i64 height, i64 qpx, i64 gh,
+                                                           uint32_t *__restrict__ hist, int privatise) {
+    extern __shared__ uint32_t sh_hist[];
     const double halfhf = (double)(height / 2), hf = (double)height, qpxf = (double)qpx, qpxfrac = 0.5 / (double)qpx;
     const i64 stride = (i64)gridDim.x * blockDim.x;
+    if (privatise) {
+        for (i64 r = threadIdx.x; r < height; r += blockDim.x) sh_hist[r] = 0;
+        __syncthreads();
+    }
     for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
         i64 y, oy;
         if (!mg_rows(v[k], halfhf, hf, qpxf, qpxfrac, qpx, height, gh, y, oy)) continue;
-        atomicAdd(&hist[min(max(y, (i64)0), height - 1)], 1u);
+        const i64 row = min(max(y, (i64)0), height - 1);
+        atomicAdd(privatise ? &sh_hist[row] : &hist[row], 1u);
+    }
+    if (privatise) {
+        __syncthreads();
+        for (i64 r = threadIdx.x; r < height; r += blockDim.x)
+            if (sh_hist[r]) atomicAdd(&hist[r], sh_hist[r]);
     }
 }
 
@@ -160,6 +177,19 @@ struct Mg {
     i64 even_row(int d) const { return height * d / n; }
 };
 
+// SKAGRID_MGPU_TRACE=1: drain every device at each phase boundary and print the phase's wall time to stderr (this
+// serialises the phases, so the sum exceeds the untraced call; for finding out where the time goes)
+void mg_trace(const Mg &m, const char *label) {
+    static const bool on = getenv("SKAGRID_MGPU_TRACE") && atoi(getenv("SKAGRID_MGPU_TRACE")) != 0;
+    static std::chrono::steady_clock::time_point last;
+    if (!on) return;
+    cudaError_t e;
+    m.drain(&e);
+    const auto now = std::chrono::steady_clock::now();
+    if (label) fprintf(stderr, "[skagrid mgpu] %-28s %8.3f ms\n", label, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+}
+
 int mg_init(Mg &m, skagrid_ctx *const *ctxs, int nctx, i64 nw, i64 qpx, i64 gh, i64 gw, const double *gcf, i64 height, i64 width, i64 count,
             const char *what) {
     if (!ctxs || nctx < 1 || !ctxs[0]) return SKAGRID_EINVAL;
@@ -181,17 +211,6 @@ int mg_init(Mg &m, skagrid_ctx *const *ctxs, int nctx, i64 nw, i64 qpx, i64 gh, 
     return SKAGRID_OK;
 }
 
-// enter every context and upload the kernel table to it
-int mg_tables(Mg &m) {
-    const size_t tab_bytes = (size_t)(m.nw * m.qpx * m.qpx * m.gh * m.gw) * 16;
-    for (int d = 0; d < m.n; ++d) {
-        int rc = sk_api_enter(m.ctx(d));
-        if (!rc) rc = sk_api_up(m.ctx(d), "tab", m.gcf, tab_bytes, (void **)&m.dtab[d]);
-        if (rc) return m.fail(d, rc);
-    }
-    return SKAGRID_OK;
-}
-
 // can a kernel on context a's device dereference context b's memory?
 bool mg_peer(skagrid_ctx *a, skagrid_ctx *b) {
     if (a->device == b->device) return true;
@@ -202,6 +221,21 @@ bool mg_peer(skagrid_ctx *a, skagrid_ctx *b) {
     if (e == cudaSuccess) return true;
     cudaGetLastError();
     return e == cudaErrorPeerAccessAlreadyEnabled;
+}
+
+// enter every context and upload the kernel table to it
+int mg_tables(Mg &m) {
+    const size_t tab_bytes = (size_t)(m.nw * m.qpx * m.qpx * m.gh * m.gw) * 16;
+    for (int d = 0; d < m.n; ++d) {
+        int rc = sk_api_enter(m.ctx(d));
+        if (!rc) rc = sk_api_up(m.ctx(d), "tab", m.gcf, tab_bytes, (void **)&m.dtab[d]);
+        if (rc) return m.fail(d, rc);
+    }
+    // map every peer once (best effort): without it cudaMemcpyPeerAsync is staged through host memory instead of NVLink
+    for (int a = 0; a < m.n; ++a)
+        for (int b = 0; b < m.n; ++b)
+            if (a != b) mg_peer(m.ctx(a), m.ctx(b));
+    return SKAGRID_OK;
 }
 
 int mg_finish(Mg &m, int rc, int failed, const char *what, cudaEvent_t t0) {
@@ -416,12 +450,14 @@ struct Route {
     std::vector<double *> du, dv, dvis, su, sv, svis, ru, rv, rvis;
     std::vector<i64 *> dwb, swb, rwb;
     std::vector<uint32_t *> sidx;
+    std::vector<double *> slab;                 // [dst] this owner's rows of the caller's grid (uploaded on the copy stream)
 };
 
 // Uploads the shards, balances the slabs, routes every record to the owners of its footprint rows.  On return the
 // receive buffers ru/rv/rwb(/rvis) of every context are complete once its stream has passed ev_mg[0] of every peer
 // (the function already makes every stream wait for them).
-int mg_route(Mg &m, Route &R, const double *u, const double *v, const int64_t *wbin, const double *vis, bool keep_index, int &failed) {
+int mg_route(Mg &m, Route &R, const double *u, const double *v, const int64_t *wbin, const double *vis, bool keep_index, const double *grid,
+             int &failed) {
     const int P = m.n;
     int rc = SKAGRID_OK;
     failed = 0;
@@ -433,8 +469,10 @@ int mg_route(Mg &m, Route &R, const double *u, const double *v, const int64_t *w
     R.su.assign(P, nullptr); R.sv.assign(P, nullptr); R.svis.assign(P, nullptr); R.swb.assign(P, nullptr);
     R.ru.assign(P, nullptr); R.rv.assign(P, nullptr); R.rvis.assign(P, nullptr); R.rwb.assign(P, nullptr);
     R.sidx.assign(P, nullptr);
-    std::vector<std::vector<uint32_t>> hist(P, std::vector<uint32_t>((size_t)m.height, 0));
+    R.slab.assign(P, nullptr);
+    std::vector<uint32_t *> hist(P, nullptr);  // pinned host staging per context: [height] histogram, then [MG_MAX] counts
     std::vector<uint32_t *> dhist(P, nullptr), dcnt(P, nullptr);
+    mg_trace(m, nullptr);
     // (a) shards to the devices + histogram of footprint-centre rows
     for (int d = 0; d < P; ++d) {
         skagrid_ctx *ctx = m.ctx(d);
@@ -450,14 +488,20 @@ int mg_route(Mg &m, Route &R, const double *u, const double *v, const int64_t *w
         MG_TRY(d, sk_scratch(ctx, "mg_cnt", 2 * MG_MAX * 4, (void **)&dcnt[d]));
         MG_CUDA(d, cudaMemsetAsync(dhist[d], 0, (size_t)m.height * 4, ctx->stream));
         MG_CUDA(d, cudaMemsetAsync(dcnt[d], 0, 2 * MG_MAX * 4, ctx->stream));
+        MG_TRY(d, sk_host_scratch(ctx, (size_t)std::max<i64>(m.height, 2 * MG_MAX) * 4, (void **)&hist[d]));
         if (n > 0) {
-            mg_row_hist_kernel<<<mg_blocks(ctx, n), 256, 0, ctx->stream>>>(n, R.dv[d], m.height, m.qpx, m.gh, dhist[d]);
+            const int privatise = m.height <= MG_HIST_SMEM_ROWS ? 1 : 0;
+            const size_t smem = privatise ? (size_t)m.height * 4 : 0;
+            if (smem > 48 * 1024) MG_CUDA(d, cudaFuncSetAttribute(mg_row_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((n + 1023) / 1024, (i64)ctx->sm_count * (privatise ? 1 : 2)));
+            mg_row_hist_kernel<<<blocks, 1024, smem, ctx->stream>>>(n, R.dv[d], m.height, m.qpx, m.gh, dhist[d], privatise);
             ctx->launches++;
             MG_CUDA(d, cudaGetLastError());
         }
-        MG_CUDA(d, cudaMemcpyAsync(hist[d].data(), dhist[d], (size_t)m.height * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        MG_CUDA(d, cudaMemcpyAsync(hist[d], dhist[d], (size_t)m.height * 4, cudaMemcpyDeviceToHost, ctx->stream));  // pinned: no host stall
     }
     for (int d = 0; d < P; ++d) { MG_CUDA(d, cudaSetDevice(m.ctx(d)->device)); MG_CUDA(d, cudaStreamSynchronize(m.ctx(d)->stream)); }
+    mg_trace(m, "shard H2D + row histogram");
     {   // (b) slab bounds at the k/P quantiles of the summed histogram; every slab keeps at least one row
         std::vector<i64> cum((size_t)m.height);
         i64 run = 0;
@@ -472,6 +516,17 @@ int mg_route(Mg &m, Route &R, const double *u, const double *v, const int64_t *w
         }
         R.B.b[P] = m.height;
     }
+    // the owners' slabs of the caller's grid travel on the copy streams while the routing below runs
+    for (int g = 0; g < P; ++g) {
+        skagrid_ctx *ctx = m.ctx(g);
+        MG_CUDA(g, cudaSetDevice(ctx->device));
+        const i64 r0 = R.B.b[g], r1 = R.B.b[g + 1];
+        const size_t slab_bytes = (size_t)((r1 - r0) * m.width) * 16;
+        ctx->resident_h = ctx->resident_w = 0;  // the "grid" scratch now holds a slab, not a resident full grid
+        MG_TRY(g, sk_scratch(ctx, "grid", slab_bytes, (void **)&R.slab[g]));
+        MG_CUDA(g, cudaMemcpyAsync(R.slab[g], grid + 2 * r0 * m.width, slab_bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+        MG_CUDA(g, cudaEventRecord(ctx->ev_copy[0], ctx->copy_stream));
+    }
     // (c) records per destination
     for (int d = 0; d < P; ++d) {
         skagrid_ctx *ctx = m.ctx(d);
@@ -482,9 +537,14 @@ int mg_route(Mg &m, Route &R, const double *u, const double *v, const int64_t *w
             ctx->launches++;
             MG_CUDA(d, cudaGetLastError());
         }
-        MG_CUDA(d, cudaMemcpyAsync(R.counts[d].data(), dcnt[d], MG_MAX * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        MG_CUDA(d, cudaMemcpyAsync(hist[d], dcnt[d], MG_MAX * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
-    for (int d = 0; d < P; ++d) { MG_CUDA(d, cudaSetDevice(m.ctx(d)->device)); MG_CUDA(d, cudaStreamSynchronize(m.ctx(d)->stream)); }
+    for (int d = 0; d < P; ++d) {
+        MG_CUDA(d, cudaSetDevice(m.ctx(d)->device));
+        MG_CUDA(d, cudaStreamSynchronize(m.ctx(d)->stream));
+        for (int g = 0; g < MG_MAX; ++g) R.counts[d][g] = hist[d][g];
+    }
+    mg_trace(m, "count (+ slab H2D)");
     for (int s = 0; s < P; ++s) {
         for (int g = 0; g < P; ++g) {
             R.seg[s][g + 1] = R.seg[s][g] + R.counts[s][g];
@@ -514,10 +574,10 @@ int mg_route(Mg &m, Route &R, const double *u, const double *v, const int64_t *w
         MG_TRY(s, sk_scratch(ctx, "mg_swb", n * 8, (void **)&R.swb[s]));
         if (vis) MG_TRY(s, sk_scratch(ctx, "mg_svis", n * 16, (void **)&R.svis[s]));
         if (keep_index) MG_TRY(s, sk_scratch(ctx, "mg_sidx", n * 4, (void **)&R.sidx[s]));
-        uint32_t start[MG_MAX] = {0};
-        for (int g = 0; g < P; ++g) start[g] = (uint32_t)R.seg[s][g];
+        uint32_t *start = hist[s] + MG_MAX;  // pinned; the counts in [0, MG_MAX) were consumed above
+        for (int g = 0; g < MG_MAX; ++g) start[g] = g < P ? (uint32_t)R.seg[s][g] : 0u;
         uint32_t *cursor = dcnt[s] + MG_MAX;
-        MG_CUDA(s, cudaMemcpyAsync(cursor, start, MG_MAX * 4, cudaMemcpyHostToDevice, ctx->stream));  // `start` is pageable: staged before return
+        MG_CUDA(s, cudaMemcpyAsync(cursor, start, MG_MAX * 4, cudaMemcpyHostToDevice, ctx->stream));
         if (R.cnt[s] > 0) {
             mg_route_kernel<<<mg_blocks(ctx, R.cnt[s]), 256, 0, ctx->stream>>>(R.cnt[s], R.du[s], R.dv[s], R.dwb[s], (const double2 *)R.dvis[s],
                                                                                m.height, m.qpx, m.gh, R.B, nullptr, cursor, R.su[s], R.sv[s], R.swb[s],
@@ -540,7 +600,9 @@ int mg_route(Mg &m, Route &R, const double *u, const double *v, const int64_t *w
         MG_CUDA(g, cudaSetDevice(m.ctx(g)->device));
         for (int s = 0; s < P; ++s)
             if (s != g) MG_CUDA(g, cudaStreamWaitEvent(m.ctx(g)->stream, m.ctx(s)->ev_mg[0], 0));
+        MG_CUDA(g, cudaStreamWaitEvent(m.ctx(g)->stream, m.ctx(g)->ev_copy[0], 0));
     }
+    mg_trace(m, "scatter + peer copies");
 done:
     return rc;
 }
@@ -559,16 +621,13 @@ extern "C" int skagrid_convgrid2_mgpu_tile(skagrid_ctx *const *ctxs, int nctx, i
     Route R;
     cudaSetDevice(m.ctx(0)->device);
     cudaEventRecord(m.ctx(0)->ev0, m.ctx(0)->stream);
-    MG_TRY(failed, mg_route(m, R, u, v, wbin, vis, false, failed));
+    MG_TRY(failed, mg_route(m, R, u, v, wbin, vis, false, grid, failed));
     for (int g = 0; g < nctx; ++g) {
         skagrid_ctx *ctx = m.ctx(g);
         MG_CUDA(g, cudaSetDevice(ctx->device));
         const i64 r0 = R.B.b[g], r1 = R.B.b[g + 1];
         const size_t slab_bytes = (size_t)((r1 - r0) * width) * 16;
-        double *slab;
-        ctx->resident_h = ctx->resident_w = 0;  // the "grid" scratch now holds a slab, not a resident full grid
-        MG_TRY(g, sk_scratch(ctx, "grid", slab_bytes, (void **)&slab));
-        MG_CUDA(g, cudaMemcpyAsync(slab, grid + 2 * r0 * width, slab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        double *slab = R.slab[g];
         if (R.recv[g] > 0) {
             skagrid_geom geom = {height, width, r0, r1, nw, qpx, gh, gw};
             skagrid_plan *plan = nullptr;
@@ -579,6 +638,7 @@ extern "C" int skagrid_convgrid2_mgpu_tile(skagrid_ctx *const *ctxs, int nctx, i
         MG_CUDA(g, cudaMemcpyAsync(grid + 2 * r0 * width, slab, slab_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         MG_CUDA(g, cudaEventRecord(ctx->ev_mg[1], ctx->stream));
     }
+    mg_trace(m, "plan + grid + slab D2H");
     if (bounds_out) for (int g = 0; g <= nctx; ++g) bounds_out[g] = R.B.b[g];
 done:
     return mg_finish(m, rc, failed, "convgrid2_mgpu_tile", m.ctx(0)->ev0);
@@ -597,17 +657,13 @@ extern "C" int skagrid_convdegrid2_mgpu_tile(skagrid_ctx *const *ctxs, int nctx,
     std::vector<double *> partial(nctx, nullptr);
     cudaSetDevice(m.ctx(0)->device);
     cudaEventRecord(m.ctx(0)->ev0, m.ctx(0)->stream);
-    MG_TRY(failed, mg_route(m, R, u, v, wbin, nullptr, true, failed));
+    MG_TRY(failed, mg_route(m, R, u, v, wbin, nullptr, true, grid, failed));
     // owners: degrid the taps on their rows of the model grid
     for (int g = 0; g < nctx; ++g) {
         skagrid_ctx *ctx = m.ctx(g);
         MG_CUDA(g, cudaSetDevice(ctx->device));
         const i64 r0 = R.B.b[g], r1 = R.B.b[g + 1];
-        const size_t slab_bytes = (size_t)((r1 - r0) * width) * 16;
-        double *slab;
-        ctx->resident_h = ctx->resident_w = 0;
-        MG_TRY(g, sk_scratch(ctx, "grid", slab_bytes, (void **)&slab));
-        MG_CUDA(g, cudaMemcpyAsync(slab, grid + 2 * r0 * width, slab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        double *slab = R.slab[g];
         MG_TRY(g, sk_scratch(ctx, "mg_part", (size_t)std::max<i64>(R.recv[g], 1) * 16, (void **)&partial[g]));
         if (R.recv[g] > 0) {
             skagrid_geom geom = {height, width, r0, r1, nw, qpx, gh, gw};
@@ -618,6 +674,7 @@ extern "C" int skagrid_convdegrid2_mgpu_tile(skagrid_ctx *const *ctxs, int nctx,
         }
         MG_CUDA(g, cudaEventRecord(ctx->ev_mg[1], ctx->stream));
     }
+    mg_trace(m, "plan + degrid");
     // sources: pull the partial sums back (send order), add them per visibility, ship the share home
     for (int s = 0; s < nctx; ++s) {
         skagrid_ctx *ctx = m.ctx(s);
@@ -645,6 +702,7 @@ extern "C" int skagrid_convdegrid2_mgpu_tile(skagrid_ctx *const *ctxs, int nctx,
         MG_CUDA(s, cudaSetDevice(m.ctx(s)->device));
         MG_CUDA(s, cudaEventRecord(m.ctx(s)->ev_mg[1], m.ctx(s)->stream));
     }
+    mg_trace(m, "return + accumulate + D2H");
     if (bounds_out) for (int g = 0; g <= nctx; ++g) bounds_out[g] = R.B.b[g];
 done:
     return mg_finish(m, rc, failed, "convdegrid2_mgpu_tile", m.ctx(0)->ev0);
