@@ -89,6 +89,38 @@ class Context {
     skagrid_ctx *h_ = nullptr;
 };
 
+// Several devices driven by this one host thread (include/skagrid.h "multi-GPU, single process"): one context per
+// entry of `devices`.  Errors of any device are reported through the first context.
+class MultiContext {
+   public:
+    explicit MultiContext(const std::vector<int> &devices) {
+        if (devices.empty()) throw Error(SKAGRID_EINVAL, "MultiContext: no devices");
+        for (int d : devices) {
+            skagrid_ctx *h = nullptr;
+            const int rc = skagrid_create(d, &h);
+            if (rc != SKAGRID_OK) {
+                const std::string msg = skagrid_last_error(nullptr);
+                for (skagrid_ctx *c : h_) skagrid_destroy(c);
+                throw Error(rc, msg);
+            }
+            h_.push_back(h);
+        }
+    }
+    ~MultiContext() { for (skagrid_ctx *c : h_) skagrid_destroy(c); }
+    MultiContext(const MultiContext &) = delete;
+    MultiContext &operator=(const MultiContext &) = delete;
+    skagrid_ctx *const *get() const { return h_.data(); }
+    int size() const { return (int)h_.size(); }
+    void check(int rc) const {
+        if (rc != SKAGRID_OK) throw Error(rc, skagrid_last_error(h_[0]));
+    }
+
+   private:
+    std::vector<skagrid_ctx *> h_;
+};
+
+enum class Sharding { Visibilities, UvTiles };  // BASELINE config 4 (shares of the visibilities + reduce) / config 5 (row slabs + routing)
+
 inline const double *cptr(const std::vector<Visibility> &v) { return reinterpret_cast<const double *>(v.data()); }
 inline double *cptr(std::vector<Visibility> &v) { return reinterpret_cast<double *>(v.data()); }
 
@@ -178,6 +210,29 @@ inline std::vector<Visibility> convdegrid2(const Context &ctx, const NdArray<Vis
     std::vector<Visibility> out(p.size());
     ctx.check(skagrid_convdegrid2(ctx.get(), gcf.dim(0), gcf.dim(1), gcf.dim(3), gcf.dim(4), cptr(gcf.data), a.height, a.width, cptr(a.data),
                                   (Index)p.size(), p.u.data(), p.v.data(), wbin.data(), cptr(out)));
+    return out;
+}
+// convgrid2 / convdegrid2 over several devices
+inline Matrix<Visibility> convgrid2(const MultiContext &ctxs, Sharding mode, const NdArray<Visibility> &gcf, Matrix<Visibility> a,
+                                    const BaseLines &p, const std::vector<Index> &wbin, const std::vector<Visibility> &v) {
+    if (gcf.shape.size() != 5 || gcf.dim(1) != gcf.dim(2)) throw Error(SKAGRID_EINVAL, "convgrid2: gcf must be [nw,qpx,qpx,gh,gw]");
+    if (mode == Sharding::Visibilities)
+        ctxs.check(skagrid_convgrid2_mgpu_vis(ctxs.get(), ctxs.size(), gcf.dim(0), gcf.dim(1), gcf.dim(3), gcf.dim(4), cptr(gcf.data), a.height,
+                                              a.width, cptr(a.data), (Index)p.size(), p.u.data(), p.v.data(), wbin.data(), cptr(v)));
+    else
+        ctxs.check(skagrid_convgrid2_mgpu_tile(ctxs.get(), ctxs.size(), gcf.dim(0), gcf.dim(1), gcf.dim(3), gcf.dim(4), cptr(gcf.data), a.height,
+                                               a.width, cptr(a.data), (Index)p.size(), p.u.data(), p.v.data(), wbin.data(), cptr(v), nullptr));
+    return a;
+}
+inline std::vector<Visibility> convdegrid2(const MultiContext &ctxs, Sharding mode, const NdArray<Visibility> &gcf, const Matrix<Visibility> &a,
+                                           const BaseLines &p, const std::vector<Index> &wbin) {
+    std::vector<Visibility> out(p.size());
+    if (mode == Sharding::Visibilities)
+        ctxs.check(skagrid_convdegrid2_mgpu_vis(ctxs.get(), ctxs.size(), gcf.dim(0), gcf.dim(1), gcf.dim(3), gcf.dim(4), cptr(gcf.data), a.height,
+                                                a.width, cptr(a.data), (Index)p.size(), p.u.data(), p.v.data(), wbin.data(), cptr(out)));
+    else
+        ctxs.check(skagrid_convdegrid2_mgpu_tile(ctxs.get(), ctxs.size(), gcf.dim(0), gcf.dim(1), gcf.dim(3), gcf.dim(4), cptr(gcf.data), a.height,
+                                                 a.width, cptr(a.data), (Index)p.size(), p.u.data(), p.v.data(), wbin.data(), cptr(out), nullptr));
     return out;
 }
 inline std::vector<Visibility> convdegrid3(const Context &ctx, const NdArray<Visibility> &wkerns, const NdArray<Visibility> &akerns,

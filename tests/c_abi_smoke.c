@@ -64,6 +64,25 @@ int main(void) {
     const int64_t bad[1] = {7};
     rc = skagrid_convgrid2(ctx, 1, 1, 3, 3, gcf, 8, 8, g8, 1, u, v, bad, vis);
     if (rc != SKAGRID_ERANGE) { fprintf(stderr, "expected SKAGRID_ERANGE, got %d\n", rc); return 1; }
+    /* 5. two contexts driven by this thread (both on device 0 here): same grid, same visibility */
+    {
+        skagrid_ctx *two[2] = {ctx, NULL};
+        if (skagrid_create(0, &two[1]) != 0) { fprintf(stderr, "second skagrid_create: %s\n", skagrid_last_error(NULL)); return 1; }
+        double g2[8 * 8 * 2], out2[2];
+        int64_t bounds[3];
+        for (int tile = 0; tile < 2; ++tile) {
+            memset(g2, 0, sizeof g2);
+            if (tile) { CHECK(skagrid_convgrid2_mgpu_tile(two, 2, 1, 1, 3, 3, gcf, 8, 8, g2, 1, u, v, wb, vis, bounds), "skagrid_convgrid2_mgpu_tile"); }
+            else { CHECK(skagrid_convgrid2_mgpu_vis(two, 2, 1, 1, 3, 3, gcf, 8, 8, g2, 1, u, v, wb, vis), "skagrid_convgrid2_mgpu_vis"); }
+            for (int t = 0; t < 8 * 8 * 2; ++t)
+                if (fabs(g2[t] - g8[t]) > 1e-14) { fprintf(stderr, "mgpu grid mismatch (tile=%d) at %d\n", tile, t); return 1; }
+            if (tile) { CHECK(skagrid_convdegrid2_mgpu_tile(two, 2, 1, 1, 3, 3, gcf, 8, 8, g8, 1, u, v, wb, out2, bounds), "skagrid_convdegrid2_mgpu_tile"); }
+            else { CHECK(skagrid_convdegrid2_mgpu_vis(two, 2, 1, 1, 3, 3, gcf, 8, 8, g8, 1, u, v, wb, out2), "skagrid_convdegrid2_mgpu_vis"); }
+            if (fabs(out2[0] - 90.0) > 1e-12 || fabs(out2[1] + 45.0) > 1e-12) { fprintf(stderr, "mgpu degrid (tile=%d): got %g%+gi\n", tile, out2[0], out2[1]); return 1; }
+        }
+        if (bounds[0] != 0 || bounds[2] != 8 || bounds[1] <= 0 || bounds[1] >= 8) { fprintf(stderr, "mgpu tile bounds %lld %lld %lld\n", (long long)bounds[0], (long long)bounds[1], (long long)bounds[2]); return 1; }
+        skagrid_destroy(two[1]);
+    }
     double mx = 0.0;
     CHECK(skagrid_grid_to_image(ctx, 8, g8, NULL, &mx), "skagrid_grid_to_image");
     printf("c_abi_smoke ok (%s, %lld kernel launches, image max %.6g)\n", skagrid_version(), (long long)skagrid_launch_count(ctx), mx);

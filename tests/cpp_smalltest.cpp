@@ -80,6 +80,34 @@ int main() {
         }
         if (!threw) return fail("out-of-range antenna index must raise");
 
+        // several contexts driven by this thread (here: two on device 0) give the single-context grid and visibilities
+        {
+            MultiContext two({0, 0});
+            NdArray<Visibility> gcf({2, 2, 2, 5, 5});
+            for (size_t i = 0; i < gcf.data.size(); ++i) gcf.data[i] = Visibility(std::cos(0.37 * i), std::sin(0.11 * i));
+            BaseLines q;
+            std::vector<Index> wb;
+            std::vector<Visibility> vv;
+            for (int k = 0; k < 500; ++k) {
+                q.u.push_back(0.45 * std::sin(1.7 * k));
+                q.v.push_back(0.45 * std::cos(0.9 * k));
+                q.w.push_back(0.0);
+                wb.push_back(k % 2);
+                vv.emplace_back(std::sin(0.3 * k), std::cos(0.2 * k));
+            }
+            Matrix<Visibility> zero(48, 48);
+            const Matrix<Visibility> one = Gridding::convgrid2(ctx, gcf, zero, q, wb, vv);
+            const std::vector<Visibility> d1 = Gridding::convdegrid2(ctx, gcf, one, q, wb);
+            for (Sharding mode : {Sharding::Visibilities, Sharding::UvTiles}) {
+                const Matrix<Visibility> many = Gridding::convgrid2(two, mode, gcf, zero, q, wb, vv);
+                for (size_t i = 0; i < one.data.size(); ++i)
+                    if (std::abs(one.data[i] - many.data[i]) > 1e-11) return fail("multi-context convgrid2");
+                const std::vector<Visibility> dm = Gridding::convdegrid2(two, mode, gcf, one, q, wb);
+                for (size_t k = 0; k < d1.size(); ++k)
+                    if (std::abs(d1[k] - dm[k]) > 1e-10) return fail("multi-context convdegrid2");
+            }
+        }
+
         auto [img, mx] = Gridding::grid_to_image(ctx, conv3);
         std::printf("cpp_smalltest ok: sum %.6f%+.6fi, peak %.11f at [%lld,%lld], image max %.9g\n", sum.real(), sum.imag(), peak, (long long)py,
                     (long long)px, mx);
