@@ -35,6 +35,11 @@
  * is none of that shape).  A chain conv_imaging2 -> grid_to_image -> convdegrid2 then moves only visibilities
  * over PCIe, as the reference's single fused Accelerate program does.  skagrid_grid_to_image transforms in
  * place, so afterwards the resident buffer holds the (complex) image plane.
+ * Resident coordinates: the same four table functions (and the _mgpu_vis forms) keep the (u, v, wbin) they uploaded on
+ * the device (up to 2^28 visibilities; for skagrid_conv_imaging2 the coordinates after the division by lam).  The next
+ * call may pass u == v == wbin == NULL with the same count, meaning "at the coordinates of the previous call": an imaging
+ * major cycle grids and degrids the same uvw, and then moves 16 instead of 40 bytes per visibility over PCIe
+ * (SKAGRID_EINVAL if the count differs or nothing is resident).
  * Device-pointer functions ("skagrid_dev_<name>") work on device-resident buffers on a caller
  * stream and never synchronise the host unless documented (used by bench.py, the multi-GPU host
  * layer, and callers that keep kernels/grids resident across calls).

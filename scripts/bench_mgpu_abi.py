@@ -68,7 +68,8 @@ def main():
         if a.mode == "vis":
             md._check(lib.skagrid_convgrid2_mgpu_vis(hs, P, NW, Q, S, S, p(htab), N, N, None, V, p(hu), p(hv), p(hwb), p(hvis)))
             t1 = time.perf_counter()
-            md._check(lib.skagrid_convdegrid2_mgpu_vis(hs, P, NW, Q, S, S, p(htab), N, N, None, V, p(hu), p(hv), p(hwb), p(hout)))
+            # grid and coordinates: what the gridding call left on the devices
+            md._check(lib.skagrid_convdegrid2_mgpu_vis(hs, P, NW, Q, S, S, p(htab), N, N, None, V, None, None, None, p(hout)))
             t2 = time.perf_counter()
             # last, because grid_to_image transforms context 0's resident copy in place
             md._check(lib.skagrid_grid_to_image(md.ctxs[0].h, N, None, None, hmax.ctypes.data))
@@ -99,7 +100,7 @@ def main():
         "grid_vis_per_s": V / float(np.mean(parts["grid"])), "degrid_vis_per_s": V / float(np.mean(parts["degrid"])),
         "bounds": bounds.tolist() if a.mode == "tile" else None, "max_pixel": float(hmax[0]), "out_checksum": float(hout.real.sum()),
         "steps": a.steps, "warmup": a.warmup,
-        "h2d_bytes_per_step": int(V * 40 + V * 24 + (2 * N * N * 16 if a.mode == "tile" else 0)),
+        "h2d_bytes_per_step": int(V * 40 + (V * 24 + 2 * N * N * 16 if a.mode == "tile" else 0)),
         "d2h_bytes_per_step": int(V * 16 + (N * N * 16 if a.mode == "tile" else 8)),
     }))
     md.close()

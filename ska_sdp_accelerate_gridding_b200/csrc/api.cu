@@ -12,6 +12,7 @@
 #include "common.cuh"
 
 static const i64 VIS_CHUNK = (i64)1 << 23;  // visibilities per pipelined chunk of the table gridders
+static const i64 RES_MAX = (i64)1 << 28;   // at most this many coordinates are kept resident between calls (24 B each)
 static const i64 AW_CHUNK = (i64)1 << 15;   // visibilities per chunk of the AW path (one S x S kernel each)
 
 static inline int up(skagrid_ctx *ctx, const char *name, const void *host, size_t bytes, void **dev) { return sk_api_up(ctx, name, host, bytes, dev); }
@@ -212,19 +213,49 @@ extern "C" int skagrid_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int
 // sk_api_stream_enqueue only enqueues (events order the three streams; no host synchronisation), so one host thread can
 // keep several devices busy (mgpu.cu); sk_api_stream_wait drains the context's streams.
 int sk_api_stream_enqueue(skagrid_ctx *ctx, const skagrid_geom *geom, const double *d_table, double *d_grid, i64 count, const double *u,
-                          const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam) {
+                          const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam, int want_wbin) {
     if (count <= 0) return SKAGRID_OK;
     const i64 chunk = std::min<i64>(count, VIS_CHUNK);
+    // Resident coordinates: the uploaded (u, v, wbin) stay on the device in per-context arrays, so the next call may pass
+    // u == v == wbin == NULL ("the coordinates of the previous call", include/skagrid.h) and skip 24 of its 40 bytes per
+    // visibility of PCIe traffic -- an imaging major cycle grids and degrids the same uvw.
+    const bool reuse = !u && !v;
+    bool resident = false;
+    double *ru = nullptr, *rv = nullptr;
+    i64 *rwb = nullptr;
+    if (reuse) {
+        if (ctx->res_count != count)
+            return sk_fail(ctx, SKAGRID_EINVAL, "coordinates are NULL but the context holds %lld resident ones, not %lld", (long long)ctx->res_count,
+                           (long long)count);
+        if (want_wbin && !ctx->res_has_wbin) return sk_fail(ctx, SKAGRID_EINVAL, "coordinates are NULL but the resident ones carry no w-plane indices");
+        if (lam > 0.0) return sk_fail(ctx, SKAGRID_EINVAL, "resident coordinates are already divided by lam");
+        resident = true;
+    } else {
+        ctx->res_count = 0;
+        resident = count <= RES_MAX;
+    }
+    if (resident) {
+        int ra = sk_scratch(ctx, "res_u", (size_t)count * 8, (void **)&ru);
+        if (!ra) ra = sk_scratch(ctx, "res_v", (size_t)count * 8, (void **)&rv);
+        if (!ra && want_wbin) ra = sk_scratch(ctx, "res_wb", (size_t)count * 8, (void **)&rwb);
+        if (ra) {  // no room for the resident copy: plain double-buffered chunks
+            if (reuse) return ra;
+            resident = false;
+            ctx->err.clear();
+        }
+    }
     skagrid_plan *plan = nullptr;
     SK_TRY(plan_acquire(ctx, geom, chunk, 0, &plan));
-    double *du[2], *dv[2], *dvis[2];
+    double *du[2] = {nullptr, nullptr}, *dv[2] = {nullptr, nullptr}, *dvis[2];
     i64 *dwb[2] = {nullptr, nullptr};
     int rc = SKAGRID_OK;
     for (int b = 0; b < 2 && !rc; ++b) {
         const char *nu = b ? "st_u1" : "st_u0", *nv = b ? "st_v1" : "st_v0", *nwb = b ? "st_w1" : "st_w0", *nvis = b ? "st_vis1" : "st_vis0";
-        rc = sk_scratch(ctx, nu, (size_t)chunk * 8, (void **)&du[b]);
-        if (!rc) rc = sk_scratch(ctx, nv, (size_t)chunk * 8, (void **)&dv[b]);
-        if (!rc && wbin) rc = sk_scratch(ctx, nwb, (size_t)chunk * 8, (void **)&dwb[b]);
+        if (!resident) {
+            rc = sk_scratch(ctx, nu, (size_t)chunk * 8, (void **)&du[b]);
+            if (!rc) rc = sk_scratch(ctx, nv, (size_t)chunk * 8, (void **)&dv[b]);
+            if (!rc && want_wbin) rc = sk_scratch(ctx, nwb, (size_t)chunk * 8, (void **)&dwb[b]);
+        }
         if (!rc) rc = sk_scratch(ctx, nvis, (size_t)chunk * 16, (void **)&dvis[b]);
     }
     if (rc) { plan_release(ctx, plan); return rc; }
@@ -238,10 +269,14 @@ int sk_api_stream_enqueue(skagrid_ctx *ctx, const skagrid_geom *geom, const doub
     for (i64 off = 0; off < count && e == cudaSuccess && !rc; off += chunk, ++ci) {
         const int b = (int)(ci & 1);
         const i64 n = std::min<i64>(chunk, count - off);
+        double *cu = resident ? ru + off : du[b], *cv = resident ? rv + off : dv[b];
+        i64 *cwb = !want_wbin ? nullptr : (resident ? rwb + off : dwb[b]);
         e = cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[b], 0);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(du[b], u + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(dv[b], v + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
-        if (e == cudaSuccess && wbin) e = cudaMemcpyAsync(dwb[b], wbin + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
+        if (!reuse) {
+            if (e == cudaSuccess) e = cudaMemcpyAsync(cu, u + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(cv, v + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
+            if (e == cudaSuccess && cwb) e = cudaMemcpyAsync(cwb, wbin + off, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->copy_stream);
+        }
         if (e == cudaSuccess && !degrid) e = cudaMemcpyAsync(dvis[b], vis + 2 * off, (size_t)n * 16, cudaMemcpyHostToDevice, ctx->copy_stream);
         if (e == cudaSuccess) e = cudaEventRecord(ctx->ev_copy[b], ctx->copy_stream);
         if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[b], 0);
@@ -249,10 +284,10 @@ int sk_api_stream_enqueue(skagrid_ctx *ctx, const skagrid_geom *geom, const doub
         if (lam > 0.0) {  // div3 (src/Gridding.hs:838-839) on u and v; w does not enter the table gridders
             void *dscr;
             rc = sk_scratch(ctx, "st_wscr", (size_t)chunk * 8, &dscr);
-            if (!rc) { cudaMemsetAsync(dscr, 0, (size_t)n * 8, ctx->stream); rc = sk_scale3_dev(ctx, n, du[b], dv[b], (double *)dscr, lam, 1, ctx->stream); }
+            if (!rc) { cudaMemsetAsync(dscr, 0, (size_t)n * 8, ctx->stream); rc = sk_scale3_dev(ctx, n, cu, cv, (double *)dscr, lam, 1, ctx->stream); }
             if (rc) break;
         }
-        rc = sk_plan_fill(ctx, plan, n, du[b], dv[b], wbin ? dwb[b] : nullptr, degrid ? nullptr : dvis[b], ctx->stream);
+        rc = sk_plan_fill(ctx, plan, n, cu, cv, cwb, degrid ? nullptr : dvis[b], ctx->stream);
         if (!rc) {
             if (degrid) {
                 // dvis[b] still holds the results of chunk c-2 until their D2H copy (on the third stream) is done
@@ -276,6 +311,7 @@ int sk_api_stream_enqueue(skagrid_ctx *ctx, const skagrid_geom *geom, const doub
     plan_release(ctx, plan);
     if (rc) return rc;
     if (e != cudaSuccess) return sk_fail(ctx, SKAGRID_ECUDA, "table gridder: %s", cudaGetErrorString(e));
+    if (resident && !reuse) { ctx->res_count = count; ctx->res_has_wbin = want_wbin ? 1 : 0; }
     return SKAGRID_OK;
 }
 
@@ -290,8 +326,8 @@ int sk_api_stream_wait(skagrid_ctx *ctx) {
 }
 
 static int stream_table(skagrid_ctx *ctx, const skagrid_geom *geom, const double *d_table, double *d_grid, i64 count, const double *u,
-                        const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam = 0.0) {
-    const int rc = sk_api_stream_enqueue(ctx, geom, d_table, d_grid, count, u, v, wbin, vis, vis_out, degrid, lam);
+                        const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, int want_wbin, double lam = 0.0) {
+    const int rc = sk_api_stream_enqueue(ctx, geom, d_table, d_grid, count, u, v, wbin, vis, vis_out, degrid, lam, want_wbin);
     const int rw = sk_api_stream_wait(ctx);  // always drain, also after a failed enqueue
     return rc ? rc : rw;
 }
@@ -304,18 +340,23 @@ static int check_table_args(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 gh, i64 gw, i
 }
 
 static int table_host(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 gh, i64 gw, const double *gcf, i64 height, i64 width, double *grid, i64 count,
-                      const double *u, const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, const char *what) {
+                      const double *u, const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, int want_wbin,
+                      const char *what) {
     SK_TRY(sk_api_enter(ctx));
     SK_TRY(check_table_args(ctx, nw, qpx, gh, gw, height, width, count));
     NEED(ctx, gcf, "NULL kernel table");
-    if (count > 0) NEED(ctx, u && v && (degrid ? vis_out != nullptr : vis != nullptr), "NULL visibility array");
+    if (count > 0) {
+        // u == v == wbin == NULL: the coordinates the previous call left on the device (sk_api_stream_enqueue)
+        const bool given = u && v && (wbin || !want_wbin), resident = !u && !v && !wbin;
+        NEED(ctx, (given || resident) && (degrid ? vis_out != nullptr : vis != nullptr), "NULL visibility array");
+    }
     Timer t(ctx);
     void *dtab, *dgrid;
     const size_t tab_bytes = (size_t)(nw * qpx * qpx * gh * gw) * 16, grid_bytes = (size_t)(height * width) * 16;
     SK_TRY(up(ctx, "tab", gcf, tab_bytes, &dtab));
     SK_TRY(grid_in(ctx, grid, height, width, &dgrid, what));
     skagrid_geom geom = {height, width, 0, height, nw, qpx, gh, gw};
-    SK_TRY(stream_table(ctx, &geom, (double *)dtab, (double *)dgrid, count, u, v, wbin, vis, vis_out, degrid));
+    SK_TRY(stream_table(ctx, &geom, (double *)dtab, (double *)dgrid, count, u, v, wbin, vis, vis_out, degrid, want_wbin));
     if (!degrid && grid) SK_TRY(down(ctx, grid, dgrid, grid_bytes));
     SK_TRY(t.finish());
     return check_flags(ctx, what);
@@ -323,26 +364,24 @@ static int table_host(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 gh, i64 gw, const d
 
 extern "C" int skagrid_convgrid(skagrid_ctx *ctx, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, int64_t height, int64_t width,
                                 double *grid, int64_t count, const double *u, const double *v, const double *vis) {
-    return table_host(ctx, 1, qpx, gh, gw, gcf, height, width, grid, count, u, v, nullptr, vis, nullptr, 0, "convgrid");
+    return table_host(ctx, 1, qpx, gh, gw, gcf, height, width, grid, count, u, v, nullptr, vis, nullptr, 0, 0, "convgrid");
 }
 
 extern "C" int skagrid_convgrid2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, int64_t height,
                                  int64_t width, double *grid, int64_t count, const double *u, const double *v, const int64_t *wbin,
                                  const double *vis) {
-    if (ctx && count > 0 && !wbin) return sk_fail(ctx, SKAGRID_EINVAL, "convgrid2: wbin is NULL");
-    return table_host(ctx, nw, qpx, gh, gw, gcf, height, width, grid, count, u, v, wbin, vis, nullptr, 0, "convgrid2");
+    return table_host(ctx, nw, qpx, gh, gw, gcf, height, width, grid, count, u, v, wbin, vis, nullptr, 0, 1, "convgrid2");
 }
 
 extern "C" int skagrid_convdegrid(skagrid_ctx *ctx, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, int64_t height, int64_t width,
                                   const double *grid, int64_t count, const double *u, const double *v, double *vis_out) {
-    return table_host(ctx, 1, qpx, gh, gw, gcf, height, width, const_cast<double *>(grid), count, u, v, nullptr, nullptr, vis_out, 1, "convdegrid");
+    return table_host(ctx, 1, qpx, gh, gw, gcf, height, width, const_cast<double *>(grid), count, u, v, nullptr, nullptr, vis_out, 1, 0, "convdegrid");
 }
 
 extern "C" int skagrid_convdegrid2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, int64_t gh, int64_t gw, const double *gcf, int64_t height,
                                    int64_t width, const double *grid, int64_t count, const double *u, const double *v, const int64_t *wbin,
                                    double *vis_out) {
-    if (ctx && count > 0 && !wbin) return sk_fail(ctx, SKAGRID_EINVAL, "convdegrid2: wbin is NULL");
-    return table_host(ctx, nw, qpx, gh, gw, gcf, height, width, const_cast<double *>(grid), count, u, v, wbin, nullptr, vis_out, 1, "convdegrid2");
+    return table_host(ctx, nw, qpx, gh, gw, gcf, height, width, const_cast<double *>(grid), count, u, v, wbin, nullptr, vis_out, 1, 1, "convdegrid2");
 }
 
 extern "C" int skagrid_grid(skagrid_ctx *ctx, int64_t height, int64_t width, double *grid, int64_t count, const double *u, const double *v,
@@ -621,7 +660,7 @@ extern "C" int skagrid_conv_imaging2(skagrid_ctx *ctx, int64_t nw, int64_t qpx, 
     SK_TRY(up(ctx, "tab", gcf, (size_t)(nw * qpx * qpx * gh * gw) * 16, &dtab));
     SK_TRY(grid_fresh(ctx, n, n, &dgrid));
     skagrid_geom geom = {n, n, 0, n, nw, qpx, gh, gw};
-    SK_TRY(stream_table(ctx, &geom, (double *)dtab, (double *)dgrid, count, u, v, wbin, vis, nullptr, 0, (double)lam));
+    SK_TRY(stream_table(ctx, &geom, (double *)dtab, (double *)dgrid, count, u, v, wbin, vis, nullptr, 0, 1, (double)lam));
     if (grid_out) SK_TRY(down(ctx, grid_out, dgrid, (size_t)(n * n) * 16));
     SK_TRY(t.finish());
     return check_flags(ctx, "conv_imaging2");

@@ -105,6 +105,8 @@ struct skagrid_ctx {
     std::map<i64, DevBuf> fft_work;
     i64 resident_h = 0, resident_w = 0;   // shape of the grid the last host-pointer call left in the "grid" scratch (0: none)
     std::set<const void *> smem_configured;  // kernels whose dynamic shared-memory limit was raised on this device
+    i64 res_count = 0;                    // visibilities whose (u, v, wbin) the last table call left in the res_* scratch (0: none)
+    int res_has_wbin = 0;
     void *h_pinned = nullptr;             // pinned host staging of the multi-device calls (sk_host_scratch)
     size_t h_pinned_bytes = 0;
     skagrid_plan *cached_plan = nullptr;  // plan kept between host-pointer calls (api.cu plan_acquire)
@@ -190,7 +192,7 @@ int sk_api_up(skagrid_ctx *ctx, const char *name, const void *host, size_t bytes
 int sk_api_check_flags(skagrid_ctx *ctx, const char *what);
 int sk_api_plan_acquire(skagrid_ctx *ctx, const skagrid_geom *geom, i64 capacity, int slice_override, skagrid_plan **out);
 int sk_api_stream_enqueue(skagrid_ctx *ctx, const skagrid_geom *geom, const double *d_table, double *d_grid, i64 count, const double *u,
-                          const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam);
+                          const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam, int want_wbin);
 int sk_api_stream_wait(skagrid_ctx *ctx);
 
 // ---------------------------------------------------------------------------------------------

@@ -309,7 +309,11 @@ extern "C" int skagrid_convgrid2_mgpu_vis(skagrid_ctx *const *ctxs, int nctx, in
                                           const int64_t *wbin, const double *vis) {
     Mg m;
     SK_TRY(mg_init(m, ctxs, nctx, nw, qpx, gh, gw, gcf, height, width, count, "convgrid2_mgpu_vis"));
-    if (count > 0 && !(u && v && vis && (wbin || nw == 1))) return sk_fail(ctxs[0], SKAGRID_EINVAL, "convgrid2_mgpu_vis: NULL visibility array");
+    // u == v == wbin == NULL: every context reuses the coordinates of its share from the previous _mgpu_vis call (same count, same contexts)
+    const bool coords_resident = !u && !v && !wbin;
+    const int want_wbin = coords_resident ? (nw > 1 ? 1 : ctxs[0]->res_has_wbin) : (wbin != nullptr);
+    if (count > 0 && !(vis && (coords_resident || (u && v && (wbin || nw == 1)))))
+        return sk_fail(ctxs[0], SKAGRID_EINVAL, "convgrid2_mgpu_vis: NULL visibility array");
     SK_TRY(mg_tables(m));
     int rc = SKAGRID_OK, failed = 0;
     std::vector<double *> dgrid(nctx, nullptr);
@@ -330,8 +334,8 @@ extern "C" int skagrid_convgrid2_mgpu_vis(skagrid_ctx *const *ctxs, int nctx, in
                                        ctx->stream));
         i64 first, n;
         m.shard(d, first, n);
-        MG_TRY(d, sk_api_stream_enqueue(ctx, &geom, m.dtab[d], dgrid[d], n, u + first, v + first, wbin ? wbin + first : nullptr, vis + 2 * first,
-                                        nullptr, 0, 0.0));
+        MG_TRY(d, sk_api_stream_enqueue(ctx, &geom, m.dtab[d], dgrid[d], n, u ? u + first : nullptr, v ? v + first : nullptr,
+                                        wbin ? wbin + first : nullptr, vis + 2 * first, nullptr, 0, 0.0, want_wbin));
         MG_CUDA(d, cudaEventRecord(ctx->ev_mg[0], ctx->stream));
     }
     // phase 2: reduce-scatter over peer memory -- device d sums row slab d of every peer into its own, then ships it home
@@ -392,7 +396,10 @@ extern "C" int skagrid_convdegrid2_mgpu_vis(skagrid_ctx *const *ctxs, int nctx, 
                                             const double *v, const int64_t *wbin, double *vis_out) {
     Mg m;
     SK_TRY(mg_init(m, ctxs, nctx, nw, qpx, gh, gw, gcf, height, width, count, "convdegrid2_mgpu_vis"));
-    if (count > 0 && !(u && v && vis_out && (wbin || nw == 1))) return sk_fail(ctxs[0], SKAGRID_EINVAL, "convdegrid2_mgpu_vis: NULL visibility array");
+    const bool coords_resident = !u && !v && !wbin;
+    const int want_wbin = coords_resident ? (nw > 1 ? 1 : ctxs[0]->res_has_wbin) : (wbin != nullptr);
+    if (count > 0 && !(vis_out && (coords_resident || (u && v && (wbin || nw == 1)))))
+        return sk_fail(ctxs[0], SKAGRID_EINVAL, "convdegrid2_mgpu_vis: NULL visibility array");
     if (!grid)
         for (int d = 0; d < nctx; ++d)
             if (ctxs[d]->resident_h != height || ctxs[d]->resident_w != width)
@@ -425,8 +432,8 @@ extern "C" int skagrid_convdegrid2_mgpu_vis(skagrid_ctx *const *ctxs, int nctx, 
         MG_CUDA(d, cudaSetDevice(ctx->device));
         i64 first, n;
         m.shard(d, first, n);
-        MG_TRY(d, sk_api_stream_enqueue(ctx, &geom, m.dtab[d], dgrid[d], n, u + first, v + first, wbin ? wbin + first : nullptr, nullptr,
-                                        vis_out + 2 * first, 1, 0.0));
+        MG_TRY(d, sk_api_stream_enqueue(ctx, &geom, m.dtab[d], dgrid[d], n, u ? u + first : nullptr, v ? v + first : nullptr,
+                                        wbin ? wbin + first : nullptr, nullptr, vis_out + 2 * first, 1, 0.0, want_wbin));
         MG_CUDA(d, cudaEventRecord(ctx->ev_mg[1], ctx->stream));
     }
 done:

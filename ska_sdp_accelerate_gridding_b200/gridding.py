@@ -157,11 +157,10 @@ def convgrid2(gcf, a, p, wbin, v, ctx=None):
     if gcf.ndim != 5 or gcf.shape[1] != gcf.shape[2]:
         raise ValueError("convgrid2: gcf must be [nw,qpx,qpx,gh,gw]")
     a = c128(a).copy()
-    u, vv = _uv(p)
     vis = c128(v)
-    wbin = int64(wbin)
+    u, vv, wbin, n = _coords(p, wbin, vis.size)  # p=None: grid new values (weights, residuals) at the previous call's coordinates
     nw, qpx, _, gh, gw = gcf.shape
-    ctx.check(ctx.lib.skagrid_convgrid2(ctx.h, nw, qpx, gh, gw, ptr(gcf), a.shape[0], a.shape[1], ptr(a), u.size, ptr(u), ptr(vv),
+    ctx.check(ctx.lib.skagrid_convgrid2(ctx.h, nw, qpx, gh, gw, ptr(gcf), a.shape[0], a.shape[1], ptr(a), n, ptr(u), ptr(vv),
                                         ptr(wbin), ptr(vis)))
     return a
 
@@ -191,24 +190,35 @@ convgrid4 = convgrid3  # src/Gridding.hs:318-377: same semantics, different (bat
 
 
 # degridding: not in the reference; exact adjoints of the gridders above
-def convdegrid(gcf, a, p, ctx=None):
+def _coords(p, wbin, count):
+    """(u, v, wbin, n); p=None: the coordinates the previous table gridder / degridder call left on the device
+    (`count` of them; include/skagrid.h "resident coordinates")."""
+    if p is None:
+        if count is None:
+            raise ValueError("p=None (resident coordinates) needs count")
+        return None, None, None, int(count)
+    u, vv = _uv(p)
+    return u, vv, (None if wbin is None else int64(wbin)), u.size
+
+
+def convdegrid(gcf, a, p, ctx=None, count=None):
     ctx = ctx or get_context()
     gcf, a = c128(gcf), c128(a)
-    u, vv = _uv(p)
-    out = np.empty(u.size, np.complex128)
+    u, vv, _, n = _coords(p, None, count)
+    out = np.empty(n, np.complex128)
     qpx, _, gh, gw = gcf.shape
-    ctx.check(ctx.lib.skagrid_convdegrid(ctx.h, qpx, gh, gw, ptr(gcf), a.shape[0], a.shape[1], ptr(a), u.size, ptr(u), ptr(vv), ptr(out)))
+    ctx.check(ctx.lib.skagrid_convdegrid(ctx.h, qpx, gh, gw, ptr(gcf), a.shape[0], a.shape[1], ptr(a), n, ptr(u), ptr(vv), ptr(out)))
     return out
 
 
-def convdegrid2(gcf, a, p, wbin, ctx=None):
+def convdegrid2(gcf, a, p, wbin, ctx=None, count=None):
+    """Adjoint of convgrid2.  p=None, wbin=None, count=n: degrid at the coordinates of the previous call (no re-upload)."""
     ctx = ctx or get_context()
     gcf, a = c128(gcf), c128(a)
-    u, vv = _uv(p)
-    wbin = int64(wbin)
-    out = np.empty(u.size, np.complex128)
+    u, vv, wbin, n = _coords(p, wbin, count)
+    out = np.empty(n, np.complex128)
     nw, qpx, _, gh, gw = gcf.shape
-    ctx.check(ctx.lib.skagrid_convdegrid2(ctx.h, nw, qpx, gh, gw, ptr(gcf), a.shape[0], a.shape[1], ptr(a), u.size, ptr(u), ptr(vv),
+    ctx.check(ctx.lib.skagrid_convdegrid2(ctx.h, nw, qpx, gh, gw, ptr(gcf), a.shape[0], a.shape[1], ptr(a), n, ptr(u), ptr(vv),
                                           ptr(wbin), ptr(out)))
     return out
 

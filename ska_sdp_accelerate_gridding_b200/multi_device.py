@@ -66,11 +66,19 @@ class MultiDevice:
             raise ValueError("mode must be 'vis' or 'tile'")
         return a
 
-    def convdegrid2(self, gcf, a, p, wbin, mode="vis"):
-        """Adjoint of convgrid2.  a=None (mode 'vis' only): the grid the previous 'vis' call left on the devices."""
+    def convdegrid2(self, gcf, a, p, wbin, mode="vis", count=None):
+        """Adjoint of convgrid2.  Mode 'vis' only: a=None = the grid the previous 'vis' call left on the devices;
+        p=None, wbin=None, count=n = at the coordinates that call uploaded (nothing but the results crosses PCIe)."""
         gcf = self._table(gcf)
-        u, vv = _uv(p)
-        wb = None if wbin is None else int64(wbin)
+        if p is None:
+            if mode != "vis" or count is None:
+                raise ValueError("p=None needs mode 'vis' and count")
+            u = vv = wb = None
+            n = int(count)
+        else:
+            u, vv = _uv(p)
+            wb = None if wbin is None else int64(wbin)
+            n = u.size
         nw, qpx, _, gh, gw = gcf.shape
         if a is None:
             if mode != "vis":
@@ -79,8 +87,8 @@ class MultiDevice:
         else:
             a = c128(a)
             shape, pa = a.shape, ptr(a)
-        out = np.empty(u.size, np.complex128)
-        args = (self.handles, len(self.ctxs), nw, qpx, gh, gw, ptr(gcf), shape[0], shape[1], pa, u.size, ptr(u), ptr(vv), ptr(wb), ptr(out))
+        out = np.empty(n, np.complex128)
+        args = (self.handles, len(self.ctxs), nw, qpx, gh, gw, ptr(gcf), shape[0], shape[1], pa, n, ptr(u), ptr(vv), ptr(wb), ptr(out))
         if mode == "vis":
             self._check(self.lib.skagrid_convdegrid2_mgpu_vis(*args))
             self._resident_shape = tuple(shape)

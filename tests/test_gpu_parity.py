@@ -609,6 +609,8 @@ def test_mgpu_abi_resident_chain_and_errors(G, orc):
         md.conv_grid_resident(gcf, (n, n), (u, v), wb, vis)
         d = md.convdegrid2(gcf, None, (u, v), wb)
         assert rel_err(d, orc.convdegrid(gcf, og, u, v, wbin=wb)) < TOL
+        d = md.convdegrid2(gcf, None, None, None, count=count)  # ... and at the coordinates each context still holds
+        assert rel_err(d, orc.convdegrid(gcf, og, u, v, wbin=wb)) < TOL
         for c in md.ctxs:  # every context holds the full sum
             img, mx = G.grid_to_image(None, ctx=c, n=n)
             assert rel_err(img, oimg) < TOL and abs(mx - oimg.max()) <= TOL * abs(oimg.max())
@@ -629,3 +631,45 @@ def test_mgpu_abi_resident_chain_and_errors(G, orc):
         assert rel_err(md.convgrid2(gcf, np.zeros((n, n), complex), (u, v), wb, vis), og) < TOL
     finally:
         md.close()
+
+
+def test_resident_coordinates(G, orc):
+    """u == v == wbin == NULL: the next table call works at the coordinates the previous one uploaded."""
+    import ctypes as C
+    from ska_sdp_accelerate_gridding_b200 import _lib
+    from ska_sdp_accelerate_gridding_b200.context import Context
+    rng = np.random.default_rng(123)
+    n, s, qpx, nw, count = 192, 7, 4, 3, 20000
+    gcf = _rand_c(rng, (nw, qpx, qpx, s, s))
+    u, v = rng.uniform(-0.5, 0.5, count), rng.uniform(-0.5, 0.5, count)
+    wb = rng.integers(0, nw, count)
+    vis, vis2 = _rand_c(rng, count), _rand_c(rng, count)
+    ctx = Context(0)
+    try:
+        with pytest.raises(_lib.SkagridError) as e:  # nothing resident on a fresh context
+            G.convdegrid2(gcf, np.zeros((n, n), complex), None, None, ctx=ctx, count=count)
+        assert e.value.code == -1
+        g = G.convgrid2(gcf, np.zeros((n, n), complex), (u, v), wb, vis, ctx=ctx)
+        og = orc.convgrid(gcf, np.zeros((n, n), complex), u, v, vis, wbin=wb)
+        assert rel_err(g, og) < TOL
+        d = G.convdegrid2(gcf, og, None, None, ctx=ctx, count=count)          # same coordinates, nothing re-uploaded
+        assert rel_err(d, orc.convdegrid(gcf, og, u, v, wbin=wb)) < TOL
+        g2 = G.convgrid2(gcf, og, None, None, vis2, ctx=ctx)                   # new values at the resident coordinates
+        assert rel_err(g2, orc.convgrid(gcf, og, u, v, vis2, wbin=wb)) < TOL
+        d0 = G.convdegrid(gcf[0], og, None, ctx=ctx, count=count)              # 4-D table: the resident w-plane indices are not used
+        assert rel_err(d0, orc.convdegrid(gcf[:1], og, u, v, wbin=np.zeros(count, np.int64))) < TOL
+        with pytest.raises(_lib.SkagridError) as e:                            # another count is not what is resident
+            G.convdegrid2(gcf, og, None, None, ctx=ctx, count=count - 1)
+        assert e.value.code == -1
+        # conv_imaging2 keeps the coordinates after the division by lam
+        theta, lam = 0.01, n * 100
+        G.conv_imaging2(gcf, theta, lam, (u * lam, v * lam, np.zeros(count)), wb, vis, ctx=ctx)
+        d = G.convdegrid2(gcf, og, None, None, ctx=ctx, count=count)
+        pu, pv = (u * lam) / lam, (v * lam) / lam
+        assert rel_err(d, orc.convdegrid(gcf, og, pu, pv, wbin=wb)) < TOL
+        # a 4-D call leaves no w-plane indices behind: the 5-D form must refuse them
+        G.convgrid(gcf[0], np.zeros((n, n), complex), (u, v), vis, ctx=ctx)
+        with pytest.raises(_lib.SkagridError):
+            G.convdegrid2(gcf, og, None, None, ctx=ctx, count=count)
+    finally:
+        ctx.close()
