@@ -382,15 +382,22 @@ def main():
         hu_wl, hv_wl = (hu * float(E2E_LAM)).pin_memory(), (hv * float(E2E_LAM)).pin_memory()
         nu_wl, nv_wl = hu_wl.numpy(), hv_wl.numpy()
 
+        e2e_parts = []
+
         def e2e_step():
+            tp = [time.perf_counter()]
             # grid pointers are NULL: the grid stays resident in the context between the three calls (include/skagrid.h),
             # so only visibilities, w-plane indices and the kernel table cross PCIe -- what the reference's single fused
             # Accelerate program does (`use` the inputs, return the result)
             ctx.check(lib.skagrid_conv_imaging2(h, NW, QPX, SUPPORT, SUPPORT, p(ntab), E2E_THETA, E2E_LAM, Ve, p(nu_wl), p(nv_wl), p(nu_wl),
                                                 p(nwb), p(nvis), None))
+            tp.append(time.perf_counter())
             ctx.check(lib.skagrid_grid_to_image(h, N_GRID, None, None, p(hmax)))
+            tp.append(time.perf_counter())
             # ... and the coordinates too (u = v = wbin = NULL: those conv_imaging2 uploaded, already divided by lam)
             ctx.check(lib.skagrid_convdegrid2(h, NW, QPX, SUPPORT, SUPPORT, p(ntab), N_GRID, N_GRID, None, Ve, None, None, None, p(nout)))
+            tp.append(time.perf_counter())
+            e2e_parts.append([1e3 * (b - a) for a, b in zip(tp, tp[1:])])
 
         for _ in range(min(args.warmup, 2)):
             e2e_step()
@@ -407,7 +414,9 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             te = float(t.item())
         grid_b = N_GRID * N_GRID * 16
+        parts = np.mean(np.array(e2e_parts[-ksteps:]), axis=0)
         out["e2e"] = {"value": world * Ve / te, "unit": "vis/s", "ms_per_step": te * 1e3, "vis_per_gpu_per_step": Ve,
+                      "calls_ms": {"conv_imaging2": float(parts[0]), "grid_to_image": float(parts[1]), "convdegrid2": float(parts[2])},
                       "h2d_bytes_per_step": int(Ve * 40 + 2 * ntab.nbytes), "d2h_bytes_per_step": int(Ve * 16 + 8),
                       "api": "skagrid_conv_imaging2 (vis -> grid) + skagrid_grid_to_image (grid -> max) + skagrid_convdegrid2 (grid -> vis): host pointers "
                              "(pinned) for visibilities / indices / table / results; the grid and the uploaded coordinates stay resident in the "

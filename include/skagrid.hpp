@@ -212,6 +212,13 @@ inline std::vector<Visibility> convdegrid2(const Context &ctx, const NdArray<Vis
                                   (Index)p.size(), p.u.data(), p.v.data(), wbin.data(), cptr(out)));
     return out;
 }
+// ... at the coordinates (and w-plane indices) the previous table call on ctx uploaded ("resident coordinates", include/skagrid.h)
+inline std::vector<Visibility> convdegrid2(const Context &ctx, const NdArray<Visibility> &gcf, const Matrix<Visibility> &a, Index count) {
+    std::vector<Visibility> out((size_t)count);
+    ctx.check(skagrid_convdegrid2(ctx.get(), gcf.dim(0), gcf.dim(1), gcf.dim(3), gcf.dim(4), cptr(gcf.data), a.height, a.width, cptr(a.data), count,
+                                  nullptr, nullptr, nullptr, cptr(out)));
+    return out;
+}
 // convgrid2 / convdegrid2 over several devices
 inline Matrix<Visibility> convgrid2(const MultiContext &ctxs, Sharding mode, const NdArray<Visibility> &gcf, Matrix<Visibility> a,
                                     const BaseLines &p, const std::vector<Index> &wbin, const std::vector<Visibility> &v) {

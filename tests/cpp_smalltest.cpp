@@ -98,6 +98,9 @@ int main() {
             Matrix<Visibility> zero(48, 48);
             const Matrix<Visibility> one = Gridding::convgrid2(ctx, gcf, zero, q, wb, vv);
             const std::vector<Visibility> d1 = Gridding::convdegrid2(ctx, gcf, one, q, wb);
+            const std::vector<Visibility> d1r = Gridding::convdegrid2(ctx, gcf, one, (Index)q.size());  // resident coordinates
+            for (size_t k = 0; k < d1.size(); ++k)
+                if (std::abs(d1[k] - d1r[k]) > 1e-12) return fail("convdegrid2 at the resident coordinates");
             for (Sharding mode : {Sharding::Visibilities, Sharding::UvTiles}) {
                 const Matrix<Visibility> many = Gridding::convgrid2(two, mode, gcf, zero, q, wb, vv);
                 for (size_t i = 0; i < one.data.size(); ++i)
