@@ -42,7 +42,21 @@ def main():
         times.append((time.perf_counter() - t0, ctx.last_device_ms))
     wall, devms = min(t[0] for t in times[1:]), min(t[1] for t in times[1:])
     out = {"workload": "R' stand-in for configs 1-3: AW gridding + image, N=2400, S=15, Q=8, nw=64, nant=64", "vis": V, "wall_ms": wall * 1e3,
-           "device_ms": devms, "vis_per_s_e2e": V / wall, "image_max": mx}
+           "device_ms": devms, "vis_per_s_e2e": V / wall, "image_max": mx,
+           "note": "wall/device: pageable numpy buffers (what a plain caller passes); *_pinned: w-kernels and image in page-locked memory"}
+    # the same call with the two large buffers (14.7 MB of w-kernels in, 46 MB of image out) page-locked
+    import torch
+    wk_pin = torch.from_numpy(wk).pin_memory().numpy()
+    side = int(np.floor(theta * lam + 0.5))
+    img_pin = torch.empty((side, side), dtype=torch.float64).pin_memory().numpy()
+    times = []
+    for i in range(4):
+        t0 = time.perf_counter()
+        mxp, _, _ = D.aw_gridding_arrays(theta, lam, wk_pin, wbins, ak, uvw_m, a1, a2, freq, vis, out_image=img_pin)
+        times.append((time.perf_counter() - t0, ctx.last_device_ms))
+    wallp, devp = min(t[0] for t in times[1:]), min(t[1] for t in times[1:])
+    out.update({"wall_ms_pinned": wallp * 1e3, "device_ms_pinned": devp, "vis_per_s_e2e_pinned": V / wallp,
+                "pinned_image_matches": bool(np.array_equal(img_pin, img)) and mxp == mx})
     if "--oracle" in sys.argv:
         from oracle import oracle as orc
         n = min(V, 2000)

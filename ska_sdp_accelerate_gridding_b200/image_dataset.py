@@ -78,9 +78,10 @@ def getAKernels(store, theta, t0, f0):
 
 
 def aw_gridding_arrays(theta, lam, wkernels, wbins, akernels, uvw_m, a1, a2, freq, vis, n=None, want_image=True, want_grid=False,
-                       ctx=None):
+                       ctx=None, out_image=None):
     """src/ImageDataset.hs:47-77 from the loaded arrays on: uvw in metres ([rows,3] or (u,v,w)), `n` = take
-    the first n visibilities (Maybe Int of the reference).  Returns (max, image or None, uvgrid or None)."""
+    the first n visibilities (Maybe Int of the reference).  Returns (max, image or None, uvgrid or None).
+    out_image: a caller-owned [side, side] float64 array to receive the image (e.g. page-locked memory)."""
     ctx = ctx or get_context()
     if isinstance(uvw_m, (tuple, list)):
         u, v, w = (f64(a) for a in uvw_m)
@@ -94,7 +95,12 @@ def aw_gridding_arrays(theta, lam, wkernels, wbins, akernels, uvw_m, a1, a2, fre
     wkernels, akernels, wbins = c128(wkernels), c128(akernels), f64(wbins)
     nw, qpx, _, s, _ = wkernels.shape
     side = int(np.floor(theta * float(lam) + 0.5))
-    img = np.empty((side, side), np.float64) if want_image else None
+    if out_image is not None:
+        if out_image.shape != (side, side) or out_image.dtype != np.float64 or not out_image.flags.c_contiguous:
+            raise ValueError("out_image must be a C-contiguous float64 array of shape (%d, %d)" % (side, side))
+        img = out_image
+    else:
+        img = np.empty((side, side), np.float64) if want_image else None
     grd = np.empty((side, side), np.complex128) if want_grid else None
     mx = np.empty(1, np.float64)
     ctx.check(ctx.lib.skagrid_aw_gridding(ctx.h, float(theta), int(lam), nw, qpx, s, ptr(wkernels), ptr(wbins), akernels.shape[0],

@@ -226,17 +226,23 @@ def test_row_slab_ownership(orc):
 # ------------------------------------------------------------------------------------------------ AW path
 def test_convolve2d_and_aw_kernel(G, orc):
     rng = np.random.default_rng(21)
-    for n in (3, 8, 15, 31):
+    for n in (1, 3, 5, 7, 8, 9, 11, 13, 15, 16, 17, 19, 31):  # register-tiled kernel for odd n in 5..17, generic one otherwise
         a, b = _rand_c(rng, (n, n)), _rand_c(rng, (n, n))
         assert rel_err(G.convolve2d(a, b), orc.convolve2d(a, b)) < 1e-12
-    nw, q, s, nant = 3, 4, 15, 5
-    wk, ak = _rand_c(rng, (nw, q, q, s, s)), _rand_c(rng, (nant, s, s))
-    cnt = 40
-    wb, yf, xf = rng.integers(0, nw, cnt), rng.integers(0, q, cnt), rng.integers(0, q, cnt)
-    a1, a2 = rng.integers(0, nant, cnt), rng.integers(0, nant, cnt)
-    out = G.aw_kernel_fn2(yf, xf, wk, ak, wb, a1, a2)
-    for k in range(cnt):
-        assert rel_err(out[k], orc.aw_kernel(wk[wb[k]], yf[k], xf[k], ak[a1[k]], ak[a2[k]])) < 1e-12
+    # aw_kernel_fn2 in batches: distinct antenna pairs are convolved once (more visibilities than pairs, and fewer)
+    for nw, q, s, nant, cnt in ((3, 4, 15, 5, 200), (2, 2, 15, 40, 60), (2, 2, 9, 3, 50), (1, 1, 19, 4, 30)):
+        wk, ak = _rand_c(rng, (nw, q, q, s, s)), _rand_c(rng, (nant, s, s))
+        wb, yf, xf = rng.integers(0, nw, cnt), rng.integers(0, q, cnt), rng.integers(0, q, cnt)
+        a1, a2 = rng.integers(0, nant, cnt), rng.integers(0, nant, cnt)
+        out = G.aw_kernel_fn2(yf, xf, wk, ak, wb, a1, a2)
+        for k in range(cnt):
+            assert rel_err(out[k], orc.aw_kernel(wk[wb[k]], yf[k], xf[k], ak[a1[k]], ak[a2[k]])) < 1e-12
+    from ska_sdp_accelerate_gridding_b200 import _lib
+    bad = a1.copy()
+    bad[3] = nant
+    with pytest.raises(_lib.SkagridError) as e:
+        G.aw_kernel_fn2(yf, xf, wk, ak, wb, bad, a2)
+    assert e.value.code == -5
 
 
 def test_smalltest_fixture(G):
