@@ -13,7 +13,7 @@
 
 static const i64 VIS_CHUNK = (i64)1 << 23;  // visibilities per pipelined chunk of the table gridders
 static const i64 RES_MAX = (i64)1 << 28;   // at most this many coordinates are kept resident between calls (24 B each)
-static const i64 AW_CHUNK = (i64)1 << 15;   // visibilities per chunk of the AW path (one S x S kernel each)
+static const i64 AW_CHUNK = (i64)1 << 17;   // most visibilities per chunk of the AW path (aw_core_dev)
 
 static inline int up(skagrid_ctx *ctx, const char *name, const void *host, size_t bytes, void **dev) { return sk_api_up(ctx, name, host, bytes, dev); }
 static inline int check_flags(skagrid_ctx *ctx, const char *what) { return sk_api_check_flags(ctx, what); }
@@ -409,7 +409,8 @@ static int aw_core_dev(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 s, const double *d
                        double *d_grid, i64 count, const double *du, const double *dv, const i64 *dwb, const i64 *da1, const i64 *da2,
                        double *dvis, int degrid) {
     if (count <= 0) return SKAGRID_OK;
-    const i64 chunk = std::min<i64>(count, AW_CHUNK);
+    // one S x S kernel per visibility: at most ~0.5 GB of them per chunk (131072 visibilities at S = 15, 8455 at S = 63)
+    const i64 chunk = std::min<i64>(count, std::max<i64>(4096, std::min<i64>(AW_CHUNK, ((i64)512 << 20) / (s * s * 16))));
     skagrid_geom geom = {height, width, 0, height, 1, qpx, s, s};  // slice_override: the table has one slice per visibility
     skagrid_plan *plan = nullptr;
     SK_TRY(plan_acquire(ctx, &geom, chunk, 1, &plan));
