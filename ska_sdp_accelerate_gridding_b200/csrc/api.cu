@@ -7,11 +7,22 @@
 // make the copy truly asynchronous; pageable ones still work).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 
-static const i64 VIS_CHUNK = (i64)1 << 23;  // visibilities per pipelined chunk of the table gridders
+// visibilities per pipelined chunk of the table gridders (SKAGRID_VIS_CHUNK_LOG2 overrides the exponent: tuning experiments)
+// Gridding from host coordinates is bound by the upload (40 B per visibility): small chunks shorten the pipeline fill and
+// the per-chunk kernels hide behind the copies anyway.  Degridding, and gridding at resident coordinates, are bound by
+// the kernels, which lose efficiency on small batches (every chunk zeroes / stages every non-empty uv tile again).
+// B200, 1e8 visibilities, e2e step of bench.py: 2^22 / 2^23 / 2^24 / 2^25 -> gridding call 75.5 / 77.0 / 78.7 / 82.8 ms,
+// degridding call 60.8 / 45.3 / 40.1 / 42.0 ms.
+static i64 vis_chunk(bool kernel_bound) {
+    static const int forced = getenv("SKAGRID_VIS_CHUNK_LOG2") ? atoi(getenv("SKAGRID_VIS_CHUNK_LOG2")) : 0;
+    if (forced >= 10 && forced <= 30) return (i64)1 << forced;
+    return (i64)1 << (kernel_bound ? 24 : 22);
+}
 static const i64 RES_MAX = (i64)1 << 28;   // at most this many coordinates are kept resident between calls (24 B each)
 static const i64 AW_CHUNK = (i64)1 << 17;   // most visibilities per chunk of the AW path (aw_core_dev)
 
@@ -215,7 +226,7 @@ extern "C" int skagrid_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int
 int sk_api_stream_enqueue(skagrid_ctx *ctx, const skagrid_geom *geom, const double *d_table, double *d_grid, i64 count, const double *u,
                           const double *v, const int64_t *wbin, const double *vis, double *vis_out, int degrid, double lam, int want_wbin) {
     if (count <= 0) return SKAGRID_OK;
-    const i64 chunk = std::min<i64>(count, VIS_CHUNK);
+    const i64 chunk = std::min<i64>(count, vis_chunk(degrid || (!u && !v)));
     // Resident coordinates: the uploaded (u, v, wbin) stay on the device in per-context arrays, so the next call may pass
     // u == v == wbin == NULL ("the coordinates of the previous call", include/skagrid.h) and skip 24 of its 40 bytes per
     // visibility of PCIe traffic -- an imaging major cycle grids and degrids the same uvw.
