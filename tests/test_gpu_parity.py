@@ -679,3 +679,31 @@ def test_resident_coordinates(G, orc):
             G.convdegrid2(gcf, og, None, None, ctx=ctx, count=count)
     finally:
         ctx.close()
+
+
+def test_command_line_on_a_standin_dataset(G, orc, tmp_path, capsys):
+    """app/Main.hs through `python -m ska_sdp_accelerate_gridding_b200`: loaders + aw_gridding on files."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    from make_standin_dataset import make
+    from ska_sdp_accelerate_gridding_b200 import __main__ as cli
+    from ska_sdp_accelerate_gridding_b200 import image_dataset as D
+    d = make(str(tmp_path / "data"), vis=3000, nw=6, nant=5)
+    out = str(tmp_path / "result.npz")
+    assert cli.main(["-gpu", "-n", "2000", "-i", d, "-o", out]) == 0
+    printed = float(capsys.readouterr().out.strip().splitlines()[-1])
+    dat = np.load(os.path.join(d, "SKA1_Low_quick.npz"))
+    wk, wbins = D.getWKernels(np.load(os.path.join(d, "SKA1_Low_wkern2.npz")), 0.008)
+    ak = D.getAKernels(np.load(os.path.join(d, "SKA1_Low_akern3.npz")), 0.008, float(dat["/vis/time"][0]), float(dat["/vis/frequency"][0]))
+    assert wk.shape == (6, 8, 8, 15, 15) and ak.shape == (5, 15, 15) and abs(np.abs(ak[0]).sum() - 1.0) < 1e-12  # closest time/frequency picked
+    uvw, vis = dat["/vis/uvw"], dat["/vis/vis"].reshape(-1)
+    n = 2000
+    oimg, omx, _ = orc.aw_gridding(0.008, 300000, wk, wbins, ak, uvw[:n, 0], uvw[:n, 1], uvw[:n, 2], dat["/vis/antenna1"][:n],
+                                   dat["/vis/antenna2"][:n], float(dat["/vis/frequency"][0]), vis[:n])
+    assert abs(printed - omx) <= TOL * abs(omx)
+    assert rel_err(np.load(out)["/img"], oimg) < TOL
+    assert cli.main(["-old", "-i", d]) == 0  # default: the first visibility only (app/Main.hs:26)
+    one = float(capsys.readouterr().out.strip().splitlines()[-1])
+    _, omx1, _ = orc.aw_gridding(0.008, 300000, wk, wbins, ak, uvw[:1, 0], uvw[:1, 1], uvw[:1, 2], dat["/vis/antenna1"][:1],
+                                 dat["/vis/antenna2"][:1], float(dat["/vis/frequency"][0]), vis[:1])
+    assert abs(one - omx1) <= TOL * abs(omx1)
