@@ -421,7 +421,11 @@ static int aw_core_dev(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 s, const double *d
                        double *dvis, int degrid) {
     if (count <= 0) return SKAGRID_OK;
     // one S x S kernel per visibility: at most ~0.5 GB of them per chunk (131072 visibilities at S = 15, 8455 at S = 63)
-    const i64 chunk = std::min<i64>(count, std::max<i64>(4096, std::min<i64>(AW_CHUNK, ((i64)512 << 20) / (s * s * 16))));
+    i64 chunk = std::min<i64>(count, std::max<i64>(4096, std::min<i64>(AW_CHUNK, ((i64)512 << 20) / (s * s * 16))));
+    if (const char *e = getenv("SKAGRID_AW_CHUNK")) {  // tests: force several chunks on a small input
+        const i64 forced = atoll(e);
+        if (forced > 0) chunk = std::min<i64>(count, forced);
+    }
     skagrid_geom geom = {height, width, 0, height, 1, qpx, s, s};  // slice_override: the table has one slice per visibility
     skagrid_plan *plan = nullptr;
     SK_TRY(plan_acquire(ctx, &geom, chunk, 1, &plan));

@@ -272,6 +272,13 @@ def test_aw_gridding_end_to_end(G, orc):
     assert rel_err(grd, ogrid) < TOL
     assert rel_err(img, oimg) < TOL
     assert abs(mx - omx) <= TOL * abs(omx)
+    # the same through several chunks of the per-visibility kernel pipeline (pair ids are per chunk)
+    os.environ["SKAGRID_AW_CHUNK"] = "700"
+    try:
+        mx2, img2, grd2 = D.aw_gridding_arrays(theta, lam, wk, wbins, ak, uvw_m, a1, a2, freq, vis, want_grid=True)
+    finally:
+        del os.environ["SKAGRID_AW_CHUNK"]
+    assert rel_err(grd2, ogrid) < TOL and rel_err(img2, oimg) < TOL
     # aw_imaging alone, and its adjoint against the dot-product identity
     u, v, w = orc.uvw_lambda(freq, uvw_m[:, 0], uvw_m[:, 1], uvw_m[:, 2])
     g = G.aw_imaging(G.noArgs, G.noOtherArgs, theta, lam, wk, wbins, ak, (u, v, w), (a1, a2, None, None), vis)
