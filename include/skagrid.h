@@ -288,6 +288,13 @@ int skagrid_dev_find_closest(skagrid_ctx *ctx, int64_t nw, const double *d_wbins
                              int64_t *d_out, void *stream);
 int skagrid_dev_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u,
                          const double *d_v, double *d_vis, void *stream);
+/* doweight in two phases, for visibilities sharded over devices (the weight grid is a sum, src/Gridding.hs:580):
+ * every device adds the cell counts of its share to d_hist (n x n int32, n = round(theta*lam), zeroed by the caller), the
+ * caller sums the histograms across devices (one all-reduce), then every device divides its share by the summed counts. */
+int skagrid_dev_weight_count(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u,
+                             const double *d_v, int32_t *d_hist, void *stream);
+int skagrid_dev_weight_apply(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u,
+                             const double *d_v, const int32_t *d_hist, double *d_vis, void *stream);
 int skagrid_dev_take_error(skagrid_ctx *ctx, void *stream, int *flags_out);
 /* frac_coord (src/Gridding.hs:126-140) on device arrays. */
 int skagrid_dev_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, int64_t count, const double *d_p,

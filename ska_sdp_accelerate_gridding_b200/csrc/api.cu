@@ -823,6 +823,26 @@ extern "C" int skagrid_dev_doweight(skagrid_ctx *ctx, double theta, int64_t lam,
     return sk_doweight_dev(ctx, n, (double)lam, count, d_u, d_v, d_vis, ctx->d_flags, sk_stream(ctx, stream));
 }
 
+extern "C" int skagrid_dev_weight_count(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u, const double *d_v,
+                                        int32_t *d_hist, void *stream) {
+    SK_TRY(sk_api_enter(ctx));
+    if (count <= 0) return SKAGRID_OK;
+    NEED(ctx, d_u && d_v && d_hist, "dev_weight_count: NULL pointer");
+    const i64 n = grid_side(theta, lam);
+    NEED(ctx, n > 0, "dev_weight_count: round(theta*lam) must be positive");
+    return sk_weight_count_dev(ctx, n, (double)lam, count, d_u, d_v, reinterpret_cast<uint32_t *>(d_hist), ctx->d_flags, sk_stream(ctx, stream));
+}
+
+extern "C" int skagrid_dev_weight_apply(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u, const double *d_v,
+                                        const int32_t *d_hist, double *d_vis, void *stream) {
+    SK_TRY(sk_api_enter(ctx));
+    if (count <= 0) return SKAGRID_OK;
+    NEED(ctx, d_u && d_v && d_hist && d_vis, "dev_weight_apply: NULL pointer");
+    const i64 n = grid_side(theta, lam);
+    NEED(ctx, n > 0, "dev_weight_apply: round(theta*lam) must be positive");
+    return sk_weight_apply_dev(ctx, n, (double)lam, count, d_u, d_v, reinterpret_cast<const uint32_t *>(d_hist), d_vis, sk_stream(ctx, stream));
+}
+
 extern "C" int skagrid_dev_take_error(skagrid_ctx *ctx, void *stream, int *flags_out) {
     SK_TRY(sk_api_enter(ctx));
     uint32_t f = 0;

@@ -166,6 +166,10 @@ int sk_scale3_dev(skagrid_ctx *ctx, i64 count, double *u, double *v, double *w, 
 int sk_mirror_dev(skagrid_ctx *ctx, i64 count, double *u, double *v, double *w, double *vis, cudaStream_t st);
 int sk_doweight_dev(skagrid_ctx *ctx, i64 n, double lam, i64 count, const double *u, const double *v,
                     double *vis, uint32_t *err_flag, cudaStream_t st);
+int sk_weight_count_dev(skagrid_ctx *ctx, i64 n, double lam, i64 count, const double *u, const double *v, uint32_t *hist, uint32_t *err_flag,
+                        cudaStream_t st);
+int sk_weight_apply_dev(skagrid_ctx *ctx, i64 n, double lam, i64 count, const double *u, const double *v, const uint32_t *hist, double *vis,
+                        cudaStream_t st);
 int sk_grid_simple_dev(skagrid_ctx *ctx, i64 h, i64 w, double *grid, i64 count, const double *u,
                        const double *v, const double *vis, cudaStream_t st);
 int sk_cmul_dev(skagrid_ctx *ctx, i64 count, double *a, const double *b, cudaStream_t st);

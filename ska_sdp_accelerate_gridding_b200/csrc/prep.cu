@@ -106,6 +106,26 @@ int sk_doweight_dev(skagrid_ctx *ctx, i64 n, double lam, i64 count, const double
     return SKAGRID_OK;
 }
 
+// The two phases of doweight on their own, for visibilities sharded over devices: every device counts its share into
+// hist (n x n uint32, accumulated), the counts are summed across devices (doweight's `permute (+)` is a sum,
+// src/Gridding.hs:580), then every device divides its share.
+int sk_weight_count_dev(skagrid_ctx *ctx, i64 n, double lam, i64 count, const double *u, const double *v, uint32_t *hist, uint32_t *err_flag,
+                        cudaStream_t st) {
+    if (count <= 0) return SKAGRID_OK;
+    if (n <= 0 || n > 65536) return sk_fail(ctx, SKAGRID_EINVAL, "doweight: grid side %lld out of range", n);
+    weight_hist_kernel<<<blocks_for(ctx, count), 256, 0, st>>>(n, lam, count, u, v, hist, err_flag);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+int sk_weight_apply_dev(skagrid_ctx *ctx, i64 n, double lam, i64 count, const double *u, const double *v, const uint32_t *hist, double *vis,
+                        cudaStream_t st) {
+    if (count <= 0) return SKAGRID_OK;
+    if (n <= 0 || n > 65536) return sk_fail(ctx, SKAGRID_EINVAL, "doweight: grid side %lld out of range", n);
+    weight_apply_kernel<<<blocks_for(ctx, count), 256, 0, st>>>(n, lam, count, u, v, hist, vis);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
 // grid (src/Gridding.hs:95-112): n = number of rows for BOTH coordinates; cell = n/2 + floor(0.5 + n*p).
 __global__ void __launch_bounds__(256) grid_simple_kernel(i64 h, i64 w, double *__restrict__ grid, i64 count, const double *__restrict__ u,
                                                           const double *__restrict__ v, const double *__restrict__ vis) {

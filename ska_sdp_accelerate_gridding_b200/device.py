@@ -98,6 +98,24 @@ def doweight_(theta, lam, u, v, vis, ctx=None):
         raise _lib.SkagridError(-5, "doweight: a visibility falls outside the weight grid")
 
 
+def weight_count_(theta, lam, u, v, hist, ctx=None):
+    """First phase of doweight for sharded visibilities: hist (n x n int32, n = round(theta*lam)) += cell counts of (u, v)."""
+    ctx = ctx or context_for_current_device()
+    _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(hist, torch.int32, "hist")
+    ctx.check(ctx.lib.skagrid_dev_weight_count(ctx.h, float(theta), int(lam), u.numel(), _p(u), _p(v), _p(hist), _stream()))
+
+
+def weight_apply_(theta, lam, u, v, hist, vis, ctx=None):
+    """Second phase: vis /= hist[cell of (u, v)], in place.  Raises if a visibility fell outside the weight grid."""
+    ctx = ctx or context_for_current_device()
+    _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(hist, torch.int32, "hist"); _chk(vis, torch.complex128, "vis")
+    ctx.check(ctx.lib.skagrid_dev_weight_apply(ctx.h, float(theta), int(lam), u.numel(), _p(u), _p(v), _p(hist), _p(vis), _stream()))
+    flags = C.c_int()
+    ctx.check(ctx.lib.skagrid_dev_take_error(ctx.h, _stream(), C.byref(flags)))
+    if flags.value & 2:
+        raise _lib.SkagridError(-5, "doweight: a visibility falls outside the weight grid")
+
+
 def w_kernel_table(theta, ws, npixff, npixkern, qpx, conjugate=True, ctx=None):
     """w_kernel (src/Gridding.hs:610-728) for every w in `ws`, built in device memory -> [nw,qpx,qpx,s,s]."""
     ctx = ctx or context_for_current_device()

@@ -121,6 +121,20 @@ def allreduce_grid(grid: torch.Tensor, group=None, dst: int | None = None):
     return grid
 
 
+def doweight_sharded_(theta, lam, u, v, vis, group=None):
+    """doweight (src/Gridding.hs:564-583) for visibilities sharded over ranks, in place on this rank's `vis`: the weight
+    of a visibility is the number of visibilities of ALL ranks in its cell, so the per-rank cell counts are summed with
+    one all-reduce of the n x n count grid (n = round(theta*lam)) between counting and dividing."""
+    from . import device as dv
+    n = int(round(theta * lam))
+    hist = torch.zeros((n, n), dtype=torch.int32, device=u.device)
+    dv.weight_count_(theta, lam, u, v, hist)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    dv.weight_apply_(theta, lam, u, v, hist, vis)
+    return vis
+
+
 class VisShardedGridder:
     """Visibility-sharded gridding / degridding on CUDA tensors (config 4)."""
 

@@ -49,10 +49,17 @@ def main():
     err_td = np.abs(dt - od).max() / np.abs(od).max()
     slab2 = ts.grid(lu, lv, lwb, lvis).cpu().numpy()
     err_t = max(err_t, np.abs(slab2 - full[r0:r1]).max() / peak, err_td)
+    # doweight over sharded visibilities: counts all-reduced between the two phases (bit-exact: integer counts, one division)
+    theta, lam = 0.01, n * 100
+    uw, vw = u * lam * 0.9, v * lam * 0.9
+    wvis = t(vis[first:first + m].copy())
+    D.doweight_sharded_(theta, lam, t(uw[first:first + m]), t(vw[first:first + m]), wvis)
+    ow = orc.doweight(theta, lam, uw, vw, vis)[first:first + m]
+    err_t = max(err_t, 0.0 if np.array_equal(wvis.cpu().numpy(), ow) else 1.0)
     res = torch.tensor([err_v, err_d, err_t], dtype=torch.float64, device="cuda")
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"world={world} vis-sharded grid err {res[0]:.2e}, degrid err {res[1]:.2e}, tile-sharded (grid, balanced grid, degrid) err {res[2]:.2e}")
+        print(f"world={world} vis-sharded grid err {res[0]:.2e}, degrid err {res[1]:.2e}, tile-sharded (grid, balanced grid, degrid) + sharded doweight err {res[2]:.2e}")
     dist.destroy_process_group()
     sys.exit(0 if float(res.max()) < 1e-10 else 1)
 

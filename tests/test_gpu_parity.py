@@ -714,3 +714,28 @@ def test_command_line_on_a_standin_dataset(G, orc, tmp_path, capsys):
     _, omx1, _ = orc.aw_gridding(0.008, 300000, wk, wbins, ak, uvw[:1, 0], uvw[:1, 1], uvw[:1, 2], dat["/vis/antenna1"][:1],
                                  dat["/vis/antenna2"][:1], float(dat["/vis/frequency"][0]), vis[:1])
     assert abs(one - omx1) <= TOL * abs(omx1)
+
+
+def test_sharded_doweight_two_phase(orc):
+    """doweight split into count / (all-reduce) / apply equals the one-call form; with the visibilities cut into two
+    shares whose counts are added by hand it still equals the oracle on the whole set (bit-exact)."""
+    import torch
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    from ska_sdp_accelerate_gridding_b200 import distributed as D
+    rng = np.random.default_rng(9)
+    theta, lam, cnt = 0.01, 20000, 50000   # n = 200: many visibilities per cell
+    u, v = rng.uniform(-0.45, 0.45, cnt) * lam, rng.uniform(-0.45, 0.45, cnt) * lam
+    vis = _rand_c(rng, cnt)
+    ow = orc.doweight(theta, lam, u, v, vis)
+    one = _t(vis.copy())
+    D.doweight_sharded_(theta, lam, _t(u), _t(v), one)  # no process group: a single share
+    assert np.array_equal(one.cpu().numpy(), ow)
+    h = cnt // 3
+    hist = torch.zeros((200, 200), dtype=torch.int32, device="cuda")
+    shares = [(_t(u[:h]), _t(v[:h]), _t(vis[:h].copy())), (_t(u[h:]), _t(v[h:]), _t(vis[h:].copy()))]
+    for su, sv, _ in shares:
+        dv.weight_count_(theta, lam, su, sv, hist)     # what the all-reduce produces: the sum of the shares' counts
+    assert int(hist.sum().item()) == cnt
+    for su, sv, svis in shares:
+        dv.weight_apply_(theta, lam, su, sv, hist, svis)
+    assert np.array_equal(torch.cat([s[2] for s in shares]).cpu().numpy(), ow)
