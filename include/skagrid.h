@@ -288,6 +288,16 @@ int skagrid_dev_find_closest(skagrid_ctx *ctx, int64_t nw, const double *d_wbins
                              int64_t *d_out, void *stream);
 int skagrid_dev_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u,
                          const double *d_v, double *d_vis, void *stream);
+/* Grid -> image when the n x n grid (n even) is spread over devices as row slabs (uv-tile-sharded gridding), without
+ * gathering it.  Stage 1, in place on this device's rows [row0, row0+nrows): the hermitian weighting (real(ifft(
+ * make_grid_hermitian g)) == real(ifft(g scaled by 2 except on row 0 and column 0)), so no mirrored rows are exchanged),
+ * the centring factor and the inverse FFT along x.  The caller then transposes across devices (all-to-all: device h
+ * receives columns [col0, col0+ncols) of every row) into an [n, ncols] row-major array.  Stage 2, in place on that array:
+ * inverse FFT along y; d_image[n, ncols] (may be NULL) = real part, centred, 1/n^2; d_max (1 double, may be NULL) = the
+ * maximum pixel of this column slab.  src/Gridding.hs:585-605, :828-829; src/ImageDataset.hs:74-77. */
+int skagrid_dev_slab_fft_rows(skagrid_ctx *ctx, int64_t n, int64_t row0, int64_t nrows, double *d_slab, void *stream);
+int skagrid_dev_slab_fft_cols(skagrid_ctx *ctx, int64_t n, int64_t col0, int64_t ncols, double *d_cols,
+                              double *d_image, double *d_max, void *stream);
 /* doweight in two phases, for visibilities sharded over devices (the weight grid is a sum, src/Gridding.hs:580):
  * every device adds the cell counts of its share to d_hist (n x n int32, n = round(theta*lam), zeroed by the caller), the
  * caller sums the histograms across devices (one all-reduce), then every device divides its share by the summed counts. */

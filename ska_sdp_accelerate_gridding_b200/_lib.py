@@ -74,6 +74,8 @@ _SIGS = {
     "skagrid_dev_mirror_uvw": [vp, i64, vp, vp, vp, vp, vp],
     "skagrid_dev_find_closest": [vp, i64, vp, i64, vp, vp, vp],
     "skagrid_dev_doweight": [vp, dbl, i64, i64, vp, vp, vp, vp],
+    "skagrid_dev_slab_fft_rows": [vp, i64, i64, i64, vp, vp],
+    "skagrid_dev_slab_fft_cols": [vp, i64, i64, i64, vp, vp, vp, vp],
     "skagrid_dev_weight_count": [vp, dbl, i64, i64, vp, vp, vp, vp],
     "skagrid_dev_weight_apply": [vp, dbl, i64, i64, vp, vp, vp, vp, vp],
     "skagrid_dev_take_error": [vp, vp, C.POINTER(C.c_int)],

@@ -823,6 +823,19 @@ extern "C" int skagrid_dev_doweight(skagrid_ctx *ctx, double theta, int64_t lam,
     return sk_doweight_dev(ctx, n, (double)lam, count, d_u, d_v, d_vis, ctx->d_flags, sk_stream(ctx, stream));
 }
 
+extern "C" int skagrid_dev_slab_fft_rows(skagrid_ctx *ctx, int64_t n, int64_t row0, int64_t nrows, double *d_slab, void *stream) {
+    SK_TRY(sk_api_enter(ctx));
+    NEED(ctx, d_slab || nrows == 0, "dev_slab_fft_rows: NULL slab");
+    return sk_slab_fft_rows_dev(ctx, n, row0, nrows, d_slab, sk_stream(ctx, stream));
+}
+
+extern "C" int skagrid_dev_slab_fft_cols(skagrid_ctx *ctx, int64_t n, int64_t col0, int64_t ncols, double *d_cols, double *d_image,
+                                         double *d_max, void *stream) {
+    SK_TRY(sk_api_enter(ctx));
+    NEED(ctx, d_cols || ncols == 0, "dev_slab_fft_cols: NULL column slab");
+    return sk_slab_fft_cols_dev(ctx, n, col0, ncols, d_cols, d_image, d_max, sk_stream(ctx, stream));
+}
+
 extern "C" int skagrid_dev_weight_count(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u, const double *d_v,
                                         int32_t *d_hist, void *stream) {
     SK_TRY(sk_api_enter(ctx));

@@ -186,6 +186,8 @@ int sk_hermitian_dev(skagrid_ctx *ctx, i64 n, const double *g, double *out, cuda
 int sk_fft2c_dev(skagrid_ctx *ctx, i64 n, const double *in, double *out, int inverse, cudaStream_t st);
 int sk_grid_to_image_dev(skagrid_ctx *ctx, i64 n, double *grid, double *image, double *max_out,
                          cudaStream_t st);
+int sk_slab_fft_rows_dev(skagrid_ctx *ctx, i64 n, i64 row0, i64 nrows, double *slab, cudaStream_t st);
+int sk_slab_fft_cols_dev(skagrid_ctx *ctx, i64 n, i64 col0, i64 ncols, double *cols, double *image, double *max_out, cudaStream_t st);
 int sk_pad_crop_dev(skagrid_ctx *ctx, i64 n_in, const double *in, i64 n_out, double *out, cudaStream_t st);
 int sk_w_kernels_dev(skagrid_ctx *ctx, double theta, i64 nw, const double *w, i64 npixff, i64 npixkern,
                      i64 qpx, int conjugate, double *out, cudaStream_t st);

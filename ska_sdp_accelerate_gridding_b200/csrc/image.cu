@@ -219,6 +219,116 @@ int sk_grid_to_image_dev(skagrid_ctx *ctx, i64 n, double *grid, double *image, d
     return SKAGRID_OK;
 }
 
+// ---------------------------------------------------------------------------------------- slab-distributed grid -> image
+// When the grid is spread over devices as row slabs (uv-tile-sharded gridding, or a reduce-scatter of visibility-sharded
+// grids), the image is formed without gathering it: per device 1-D inverse FFTs along x of its rows, an all-to-all
+// transpose (done by the caller: torch.distributed / peer copies), 1-D inverse FFTs along y of its column slab.
+//
+// make_grid_hermitian needs no exchange of mirrored rows when only real(ifft) is wanted (src/ImageDataset.hs:74-76):
+// for even n, H = g + conj(R g') with g' = g with row 0 and column 0 zeroed and (R a)[y,x] = a[(n-y) mod n, (n-x) mod n];
+// ifft(conj(R a)) = conj(ifft(a)), so real(ifft(H)) = real(ifft(g + g')) -- the grid scaled by 2 except on row 0 and
+// column 0.  The centring factor M = (-1)^(x+y) commutes with R, so the same holds for the centred transform.
+static int get_fft1d_plan(skagrid_ctx *ctx, i64 n, i64 batch, int strided, cufftHandle *out) {
+    if (n <= 0 || n > (1 << 17) || batch <= 0 || batch > (1 << 17)) return sk_fail(ctx, SKAGRID_EINVAL, "fft1d: size %lld x %lld out of range", n, batch);
+    const i64 key = ((i64)(strided ? 2 : 1) << 40) | (n << 20) | batch;  // 2-D plans use the bare n as key
+    auto it = ctx->fft_plans.find(key);
+    if (it != ctx->fft_plans.end()) { *out = it->second; return SKAGRID_OK; }
+    cufftHandle h;
+    SK_CUFFT(ctx, cufftCreate(&h));
+    size_t ws = 0;
+    int dims[1] = {(int)n};
+    // contiguous: `batch` rows of n; strided: `batch` columns of an [n, batch] row-major array
+    int inembed[1] = {(int)n};
+    cufftResult r = cufftSetAutoAllocation(h, 0);
+    if (r == CUFFT_SUCCESS)
+        r = strided ? cufftMakePlanMany(h, 1, dims, inembed, (int)batch, 1, inembed, (int)batch, 1, CUFFT_Z2Z, (int)batch, &ws)
+                    : cufftMakePlanMany(h, 1, dims, inembed, 1, (int)n, inembed, 1, (int)n, CUFFT_Z2Z, (int)batch, &ws);
+    if (r != CUFFT_SUCCESS) { cufftDestroy(h); return sk_fail(ctx, SKAGRID_ECUDA, "cufftMakePlanMany(%lld x %lld): %s", n, batch, cufft_str(r)); }
+    DevBuf wb;
+    if (ws > 0) {
+        if (cudaMalloc(&wb.p, ws) != cudaSuccess) {
+            cudaGetLastError();
+            cufftDestroy(h);
+            return sk_fail(ctx, SKAGRID_ENOMEM, "fft1d: work area of %zu bytes", ws);
+        }
+        wb.bytes = ws;
+        r = cufftSetWorkArea(h, wb.p);
+        if (r != CUFFT_SUCCESS) { cudaFree(wb.p); cufftDestroy(h); return sk_fail(ctx, SKAGRID_ECUDA, "cufftSetWorkArea: %s", cufft_str(r)); }
+    }
+    ctx->fft_plans[key] = h;
+    ctx->fft_work[key] = wb;
+    *out = h;
+    return SKAGRID_OK;
+}
+
+// slab[y - row0, x] *= (x == 0 || y == 0 ? 1 : 2) * (-1)^(x+y)
+__global__ void __launch_bounds__(256) slab_prescale_kernel(i64 n, i64 row0, i64 nrows, double2 *__restrict__ slab) {
+    const i64 total = nrows * n;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += stride) {
+        const i64 y = row0 + c / n, x = c % n;
+        double f = (x == 0 || y == 0) ? 1.0 : 2.0;
+        if ((x + y) & 1) f = -f;
+        double2 v = slab[c];
+        v.x *= f; v.y *= f;
+        slab[c] = v;
+    }
+}
+
+// image[y, x - col0] = real(cols[y, x - col0]) * (-1)^(x+y) / n^2; block maximum into max_out
+__global__ void __launch_bounds__(256) slab_finish_kernel(i64 n, i64 col0, i64 ncols, const double2 *__restrict__ cols, double *__restrict__ image,
+                                                          double scale, double *__restrict__ max_out) {
+    __shared__ double wmax[8];
+    const i64 total = n * ncols;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    double m = -INFINITY;
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += stride) {
+        const i64 y = c / ncols, x = col0 + c % ncols;
+        const double r = (((x + y) & 1) ? -scale : scale) * cols[c].x;
+        if (image) image[c] = r;
+        m = fmax(m, r);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) m = fmax(m, wmax[i]);
+        if (max_out) atomic_max_double(max_out, m);
+    }
+}
+
+// Stage 1, in place on rows [row0, row0 + nrows) of an n x n grid (n even): hermitian weighting + centring + inverse FFT along x.
+int sk_slab_fft_rows_dev(skagrid_ctx *ctx, i64 n, i64 row0, i64 nrows, double *slab, cudaStream_t st) {
+    if (n <= 0 || (n & 1)) return sk_fail(ctx, SKAGRID_EINVAL, "slab grid_to_image: the grid side must be even (n = %lld)", n);
+    if (row0 < 0 || nrows < 0 || row0 + nrows > n) return sk_fail(ctx, SKAGRID_EINVAL, "slab grid_to_image: rows [%lld, %lld) outside the grid", row0, row0 + nrows);
+    if (nrows == 0) return SKAGRID_OK;
+    slab_prescale_kernel<<<nblocks(ctx, nrows * n), 256, 0, st>>>(n, row0, nrows, (double2 *)slab);
+    SK_LAUNCH_CHECK(ctx);
+    cufftHandle plan;
+    SK_TRY(get_fft1d_plan(ctx, n, nrows, 0, &plan));
+    SK_CUFFT(ctx, cufftSetStream(plan, st));
+    SK_CUFFT(ctx, cufftExecZ2Z(plan, (cufftDoubleComplex *)slab, (cufftDoubleComplex *)slab, CUFFT_INVERSE));
+    ctx->launches++;
+    return SKAGRID_OK;
+}
+
+// Stage 2, on columns [col0, col0 + ncols) held as an [n, ncols] row-major array (transformed in place): inverse FFT along
+// y, then image = real part, centred and normalised; max_out (may be NULL) receives the maximum pixel of this column slab.
+int sk_slab_fft_cols_dev(skagrid_ctx *ctx, i64 n, i64 col0, i64 ncols, double *cols, double *image, double *max_out, cudaStream_t st) {
+    if (n <= 0 || (n & 1)) return sk_fail(ctx, SKAGRID_EINVAL, "slab grid_to_image: the grid side must be even (n = %lld)", n);
+    if (col0 < 0 || ncols < 0 || col0 + ncols > n) return sk_fail(ctx, SKAGRID_EINVAL, "slab grid_to_image: columns [%lld, %lld) outside the grid", col0, col0 + ncols);
+    if (max_out) { set_double_kernel<<<1, 1, 0, st>>>(max_out, -INFINITY); SK_LAUNCH_CHECK(ctx); }
+    if (ncols == 0) return SKAGRID_OK;
+    cufftHandle plan;
+    SK_TRY(get_fft1d_plan(ctx, n, ncols, 1, &plan));
+    SK_CUFFT(ctx, cufftSetStream(plan, st));
+    SK_CUFFT(ctx, cufftExecZ2Z(plan, (cufftDoubleComplex *)cols, (cufftDoubleComplex *)cols, CUFFT_INVERSE));
+    ctx->launches++;
+    slab_finish_kernel<<<nblocks(ctx, n * ncols), 256, 0, st>>>(n, col0, ncols, (const double2 *)cols, image, 1.0 / ((double)n * (double)n), max_out);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
 // ---------------------------------------------------------------------------------------- pad / crop
 // Centre-pad (n_out > n_in; pad_mid src/Gridding.hs:682-691 incl. the padder transpose when transpose != 0)
 // or centre-crop (n_out < n_in; extract_mid :694-707).  n_out == n_in copies.

@@ -98,6 +98,27 @@ def doweight_(theta, lam, u, v, vis, ctx=None):
         raise _lib.SkagridError(-5, "doweight: a visibility falls outside the weight grid")
 
 
+def slab_fft_rows_(n, row0, slab, ctx=None):
+    """Stage 1 of the slab-distributed grid -> image (include/skagrid.h), in place on rows [row0, row0 + slab.shape[0])."""
+    ctx = ctx or context_for_current_device()
+    _chk(slab, torch.complex128, "slab")
+    if slab.dim() != 2 or slab.shape[1] != n:
+        raise ValueError("slab must be [rows, n]")
+    ctx.check(ctx.lib.skagrid_dev_slab_fft_rows(ctx.h, int(n), int(row0), slab.shape[0], _p(slab), _stream()))
+
+
+def slab_fft_cols_(n, col0, cols, want_image=True, ctx=None):
+    """Stage 2, in place on the [n, ncols] column slab; returns (image [n, ncols] float64 or None, max as a 1-element tensor)."""
+    ctx = ctx or context_for_current_device()
+    _chk(cols, torch.complex128, "cols")
+    if cols.dim() != 2 or cols.shape[0] != n:
+        raise ValueError("cols must be [n, ncols]")
+    img = torch.empty(cols.shape, dtype=torch.float64, device=cols.device) if want_image else None
+    mx = torch.empty(1, dtype=torch.float64, device=cols.device)
+    ctx.check(ctx.lib.skagrid_dev_slab_fft_cols(ctx.h, int(n), int(col0), cols.shape[1], _p(cols), _p(img), _p(mx), _stream()))
+    return img, mx
+
+
 def weight_count_(theta, lam, u, v, hist, ctx=None):
     """First phase of doweight for sharded visibilities: hist (n x n int32, n = round(theta*lam)) += cell counts of (u, v)."""
     ctx = ctx or context_for_current_device()

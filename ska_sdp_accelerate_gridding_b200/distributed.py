@@ -121,6 +121,49 @@ def allreduce_grid(grid: torch.Tensor, group=None, dst: int | None = None):
     return grid
 
 
+def rows_to_columns(slab: torch.Tensor, bounds: Sequence[int], group=None):
+    """Transpose of the ownership of an n x n array across ranks: in, rank g holds rows [bounds[g], bounds[g+1]) as
+    [rows, n]; out, rank h holds columns [n*h/P, n*(h+1)/P) of every row as [n, cols].  One all-to-all: the block
+    (my rows) x (columns of rank h) goes to rank h, which stacks the blocks in source-rank (= row) order.
+    Backend-agnostic (complex tensors travel as pairs of reals).  Returns (columns, (c0, c1))."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = int(bounds[-1])
+    cb = [n * h // world for h in range(world + 1)]
+    c0, c1 = cb[rank], cb[rank + 1]
+    if world == 1:
+        return slab, (c0, c1)
+    rows = slab.shape[0]
+    send = torch.cat([slab[:, cb[h]:cb[h + 1]].reshape(-1) for h in range(world)])
+    in_splits = [rows * (cb[h + 1] - cb[h]) for h in range(world)]
+    out_splits = [(int(bounds[g + 1]) - int(bounds[g])) * (c1 - c0) for g in range(world)]
+    recv = torch.empty(sum(out_splits), dtype=slab.dtype, device=slab.device)
+    a, b = (torch.view_as_real(recv), torch.view_as_real(send)) if slab.is_complex() else (recv, send)
+    dist.all_to_all_single(a, b, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+    return recv.reshape(n, c1 - c0), (c0, c1)
+
+
+def slab_grid_to_image(slab: torch.Tensor, bounds: Sequence[int], group=None, want_image=True):
+    """Grid -> image (make_grid_hermitian, centred ifft, real, maximum: src/ImageDataset.hs:74-77) for an n x n grid held as
+    row slabs, rank g owning rows [bounds[g], bounds[g+1]) -- the layout uv-tile-sharded gridding produces -- WITHOUT
+    gathering the grid: row transforms on the owners, one all-to-all transpose, column transforms on the column owners.
+    `slab` ([rows, n] complex128) is transformed in place.  Returns (image columns [n, c1-c0] float64 or None,
+    (c0, c1), maximum over the whole image as a float)."""
+    from . import device as dv
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = int(bounds[-1])
+    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+    if tuple(slab.shape) != (r1 - r0, n):
+        raise ValueError("slab must be [bounds[rank+1]-bounds[rank], n]")
+    dv.slab_fft_rows_(n, r0, slab)
+    cols, (c0, c1) = rows_to_columns(slab, bounds, group)
+    img, mx = dv.slab_fft_cols_(n, c0, cols, want_image=want_image)
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    return img, (c0, c1), float(mx.item())
+
+
 def doweight_sharded_(theta, lam, u, v, vis, group=None):
     """doweight (src/Gridding.hs:564-583) for visibilities sharded over ranks, in place on this rank's `vis`: the weight
     of a visibility is the number of visibilities of ALL ranks in its cell, so the per-rank cell counts are summed with

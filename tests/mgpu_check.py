@@ -49,6 +49,10 @@ def main():
     err_td = np.abs(dt - od).max() / np.abs(od).max()
     slab2 = ts.grid(lu, lv, lwb, lvis).cpu().numpy()
     err_t = max(err_t, np.abs(slab2 - full[r0:r1]).max() / peak, err_td)
+    # grid -> image straight from the row slabs of the tile-sharded gridder (no gather): columns of the oracle's image
+    img, (c0, c1), mx = D.slab_grid_to_image(t(full[r0:r1].copy()), ts.bounds)
+    oimg = np.real(orc.ifft(orc.make_grid_hermitian(full)))
+    err_t = max(err_t, np.abs(img.cpu().numpy() - oimg[:, c0:c1]).max() / np.abs(oimg).max(), abs(mx - oimg.max()) / abs(oimg.max()))
     # doweight over sharded visibilities: counts all-reduced between the two phases (bit-exact: integer counts, one division)
     theta, lam = 0.01, n * 100
     uw, vw = u * lam * 0.9, v * lam * 0.9
@@ -59,7 +63,7 @@ def main():
     res = torch.tensor([err_v, err_d, err_t], dtype=torch.float64, device="cuda")
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"world={world} vis-sharded grid err {res[0]:.2e}, degrid err {res[1]:.2e}, tile-sharded (grid, balanced grid, degrid) + sharded doweight err {res[2]:.2e}")
+        print(f"world={world} vis-sharded grid err {res[0]:.2e}, degrid err {res[1]:.2e}, tile-sharded (grid, balanced grid, degrid) + slab grid->image + sharded doweight err {res[2]:.2e}")
     dist.destroy_process_group()
     sys.exit(0 if float(res.max()) < 1e-10 else 1)
 

@@ -132,3 +132,46 @@ def test_balanced_slab_bounds():
     h2 = torch.zeros(64, dtype=torch.int64); h2[10] = 5
     b2 = D.balanced_slab_bounds(h2, 8)
     assert b2[0] == 0 and b2[-1] == 64 and all(b2[i] < b2[i + 1] for i in range(8))
+
+
+def _transpose_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as orc
+        rng = np.random.default_rng(3)
+        n = 48
+        g = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        bounds = [0, 7, 29, n][: world] + [n] if world == 3 else [0, 19, n]   # uneven row slabs
+        r0, r1 = bounds[rank], bounds[rank + 1]
+        # the slab-distributed grid -> image of distributed.slab_grid_to_image, its two device stages restated in numpy:
+        # weight 2 except on row 0 / column 0 (replaces make_grid_hermitian when only the real part is kept), centring, ifft along x
+        yy, xx = np.mgrid[r0:r1, 0:n]
+        slab = g[r0:r1] * np.where((yy == 0) | (xx == 0), 1.0, 2.0) * np.where((yy + xx) % 2 == 1, -1.0, 1.0)
+        slab = np.fft.ifft(slab, axis=1) * n   # cuFFT's inverse transform is unnormalised
+        cols, (c0, c1) = D.rows_to_columns(torch.from_numpy(slab), bounds)
+        assert tuple(cols.shape) == (n, c1 - c0)
+        colsn = np.fft.ifft(cols.numpy(), axis=0) * n
+        yy, xx = np.mgrid[0:n, c0:c1]
+        img = colsn.real * np.where((yy + xx) % 2 == 1, -1.0, 1.0) / (n * n)
+        ref = np.real(orc.ifft(orc.make_grid_hermitian(g)))[:, c0:c1]
+        ret[rank] = ("ok", float(np.abs(img - ref).max() / np.abs(ref).max()), c1 - c0)
+    except Exception as e:  # pragma: no cover
+        ret[rank] = ("fail", repr(e), 0)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_slab_grid_to_image_algorithm_two_rank_gloo():
+    """The all-to-all transpose of slab_grid_to_image on uneven row slabs, and the identity it rests on:
+    real(ifft(make_grid_hermitian g)) == real(ifft(g weighted 2 off row/column 0)), against the oracle."""
+    world = 2
+    port = _free_port()
+    ret = mp.Manager().dict()
+    mp.spawn(_transpose_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert sum(ret[r][2] for r in range(world)) == 48
+    for r in range(world):
+        status, err, _ = ret[r]
+        assert status == "ok", err
+        assert err < 1e-12

@@ -739,3 +739,34 @@ def test_sharded_doweight_two_phase(orc):
     for su, sv, svis in shares:
         dv.weight_apply_(theta, lam, su, sv, hist, svis)
     assert np.array_equal(torch.cat([s[2] for s in shares]).cpu().numpy(), ow)
+
+
+@pytest.mark.parametrize("n", [64, 250, 1024])
+def test_slab_distributed_grid_to_image_stages(G, orc, n):
+    """The two device stages of the slab-distributed grid -> image (row transforms, transpose, column transforms): one slab
+    through distributed.slab_grid_to_image, and three uneven row slabs / two column slabs transposed by hand."""
+    import torch
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    from ska_sdp_accelerate_gridding_b200 import distributed as D
+    rng = np.random.default_rng(n)
+    g = _rand_c(rng, (n, n))
+    oimg = np.real(orc.ifft(orc.make_grid_hermitian(g)))
+    img, (c0, c1), mx = D.slab_grid_to_image(_t(g.copy()), [0, n])
+    assert (c0, c1) == (0, n)
+    assert rel_err(img.cpu().numpy(), oimg) < TOL and abs(mx - oimg.max()) <= TOL * abs(oimg.max())
+    bounds = [0, n // 5, n // 5 + 1, n]   # a one-row slab in the middle
+    slabs = []
+    for r0, r1 in zip(bounds, bounds[1:]):
+        s = _t(g[r0:r1].copy())
+        dv.slab_fft_rows_(n, r0, s)
+        slabs.append(s)
+    rows = torch.cat(slabs)               # what the all-to-all assembles, per column block
+    mxs = []
+    for c0, c1 in ((0, n // 3), (n // 3, n)):
+        cols = rows[:, c0:c1].contiguous()
+        im, m = dv.slab_fft_cols_(n, c0, cols)
+        assert rel_err(im.cpu().numpy(), oimg[:, c0:c1]) < TOL
+        mxs.append(float(m.item()))
+    assert abs(max(mxs) - oimg.max()) <= TOL * abs(oimg.max())
+    with pytest.raises(Exception):
+        dv.slab_fft_rows_(n + 1, 0, _t(_rand_c(rng, (2, n + 1))))  # odd sides are not supported by the slab path
