@@ -121,34 +121,53 @@ def allreduce_grid(grid: torch.Tensor, group=None, dst: int | None = None):
     return grid
 
 
-def rows_to_columns(slab: torch.Tensor, bounds: Sequence[int], group=None):
-    """Transpose of the ownership of an n x n array across ranks: in, rank g holds rows [bounds[g], bounds[g+1]) as
-    [rows, n]; out, rank h holds columns [n*h/P, n*(h+1)/P) of every row as [n, cols].  One all-to-all: the block
-    (my rows) x (columns of rank h) goes to rank h, which stacks the blocks in source-rank (= row) order.
-    Backend-agnostic (complex tensors travel as pairs of reals).  Returns (columns, (c0, c1))."""
+def rows_to_columns(block: torch.Tensor, rows: Sequence[int], n: int, group=None):
+    """Transpose of the ownership of an n x n array across ranks: in, this rank holds rows [rows[0], rows[1]) as
+    [rows[1]-rows[0], n] (the row intervals of the ranks are disjoint and increasing with the rank; rows held by nobody
+    are zero); out, rank h holds columns [n*h/P, n*(h+1)/P) of every row as [n, cols].  One all-to-all: the block
+    (my rows) x (columns of rank h) goes to rank h, which places the blocks at their rows.  Backend-agnostic (complex
+    tensors travel as pairs of reals).  Returns (columns, (c0, c1))."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    n = int(bounds[-1])
+    a, b = int(rows[0]), int(rows[1])
+    if tuple(block.shape) != (b - a, n):
+        raise ValueError("block must be [rows[1]-rows[0], n]")
     cb = [n * h // world for h in range(world + 1)]
     c0, c1 = cb[rank], cb[rank + 1]
     if world == 1:
-        return slab, (c0, c1)
-    rows = slab.shape[0]
-    send = torch.cat([slab[:, cb[h]:cb[h + 1]].reshape(-1) for h in range(world)])
-    in_splits = [rows * (cb[h + 1] - cb[h]) for h in range(world)]
-    out_splits = [(int(bounds[g + 1]) - int(bounds[g])) * (c1 - c0) for g in range(world)]
-    recv = torch.empty(sum(out_splits), dtype=slab.dtype, device=slab.device)
-    a, b = (torch.view_as_real(recv), torch.view_as_real(send)) if slab.is_complex() else (recv, send)
-    dist.all_to_all_single(a, b, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
-    return recv.reshape(n, c1 - c0), (c0, c1)
+        if (a, b) == (0, n):
+            return block, (c0, c1)
+        cols = torch.zeros((n, n), dtype=block.dtype, device=block.device)
+        cols[a:b] = block
+        return cols, (c0, c1)
+    mine = torch.tensor([a, b], dtype=torch.int64, device=block.device)
+    every = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine, group=group)
+    spans = [(int(t[0].item()), int(t[1].item())) for t in every]
+    send = torch.cat([block[:, cb[h]:cb[h + 1]].reshape(-1) for h in range(world)])
+    in_splits = [(b - a) * (cb[h + 1] - cb[h]) for h in range(world)]
+    out_splits = [(hi - lo) * (c1 - c0) for lo, hi in spans]
+    recv = torch.empty(sum(out_splits), dtype=block.dtype, device=block.device)
+    x, y = (torch.view_as_real(recv), torch.view_as_real(send)) if block.is_complex() else (recv, send)
+    dist.all_to_all_single(x, y, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+    if sum(hi - lo for lo, hi in spans) == n:
+        return recv.reshape(n, c1 - c0), (c0, c1)  # the intervals tile the rows: the stacked blocks are the column slab
+    cols = torch.zeros((n, c1 - c0), dtype=block.dtype, device=block.device)
+    off = 0
+    for (lo, hi), cnt in zip(spans, out_splits):
+        cols[lo:hi] = recv[off:off + cnt].reshape(hi - lo, c1 - c0)
+        off += cnt
+    return cols, (c0, c1)
 
 
-def slab_grid_to_image(slab: torch.Tensor, bounds: Sequence[int], group=None, want_image=True):
+def slab_grid_to_image(slab: torch.Tensor, bounds: Sequence[int], group=None, want_image=True, nonzero=None):
     """Grid -> image (make_grid_hermitian, centred ifft, real, maximum: src/ImageDataset.hs:74-77) for an n x n grid held as
     row slabs, rank g owning rows [bounds[g], bounds[g+1]) -- the layout uv-tile-sharded gridding produces -- WITHOUT
     gathering the grid: row transforms on the owners, one all-to-all transpose, column transforms on the column owners.
-    `slab` ([rows, n] complex128) is transformed in place.  Returns (image columns [n, c1-c0] float64 or None,
-    (c0, c1), maximum over the whole image as a float)."""
+    `slab` ([rows, n] complex128) is transformed in place.  nonzero = (lo, hi): only rows [lo, hi) of this rank's slab
+    can be non-zero (e.g. TileShardedGridder.nonzero_rows(): mirrored uv coverage leaves half of the grid empty), the
+    others are neither transformed nor sent.  Returns (image columns [n, c1-c0] float64 or None, (c0, c1), maximum over
+    the whole image as a float)."""
     from . import device as dv
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -156,8 +175,11 @@ def slab_grid_to_image(slab: torch.Tensor, bounds: Sequence[int], group=None, wa
     r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
     if tuple(slab.shape) != (r1 - r0, n):
         raise ValueError("slab must be [bounds[rank+1]-bounds[rank], n]")
-    dv.slab_fft_rows_(n, r0, slab)
-    cols, (c0, c1) = rows_to_columns(slab, bounds, group)
+    lo, hi = (r0, r1) if nonzero is None else (max(r0, int(nonzero[0])), min(r1, int(nonzero[1])))
+    hi = max(hi, lo)
+    block = slab[lo - r0:hi - r0]
+    dv.slab_fft_rows_(n, lo, block)
+    cols, (c0, c1) = rows_to_columns(block, (lo, hi), n, group)
     img, mx = dv.slab_fft_cols_(n, c0, cols, want_image=want_image)
     if world > 1:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
@@ -245,6 +267,7 @@ class TileShardedGridder:
         from . import device as dv
         (ru, rv, rwb, rvis), _ = self.route(u, v, wbin, vis)
         self.last_routed = int(ru.numel())
+        self._last_rv = rv
         if out is None:
             out = torch.zeros((self.rows[1] - self.rows[0], self.w), dtype=torch.complex128, device=u.device)
         if ru.numel() > 0:
@@ -257,6 +280,18 @@ class TileShardedGridder:
                 plan.update(ru, rv, rwb, rvis)
             plan.grid(self.table, out)
         return out
+
+    def nonzero_rows(self):
+        """Rows of this rank's slab the last `grid` call (into a zeroed slab) can have touched: [lo, hi) in grid rows."""
+        from . import device as dv
+        r0, r1 = self.rows
+        rv = getattr(self, "_last_rv", None)
+        if rv is None or rv.numel() == 0:
+            return (r0, r0)
+        gh = self.table.shape[-2]
+        y, _ = dv.frac_coord(self.h, self.table.shape[-3], rv)
+        lo, hi = int(y.min().item()) - gh // 2, int(y.max().item()) - gh // 2 + gh
+        return (min(max(lo, r0), r1), min(max(hi, r0), r1))
 
     def degrid(self, slab, u, v, wbin):
         """Adjoint of `grid`: `slab` holds this rank's rows of the (model) grid.  Coordinates are routed to the owners,

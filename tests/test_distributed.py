@@ -150,8 +150,15 @@ def _transpose_worker(rank, world, port, ret):
         yy, xx = np.mgrid[r0:r1, 0:n]
         slab = g[r0:r1] * np.where((yy == 0) | (xx == 0), 1.0, 2.0) * np.where((yy + xx) % 2 == 1, -1.0, 1.0)
         slab = np.fft.ifft(slab, axis=1) * n   # cuFFT's inverse transform is unnormalised
-        cols, (c0, c1) = D.rows_to_columns(torch.from_numpy(slab), bounds)
+        cols, (c0, c1) = D.rows_to_columns(torch.from_numpy(slab), (r0, r1), n)
         assert tuple(cols.shape) == (n, c1 - c0)
+        # rows nobody sends are zero: rank 0 keeps back its first three rows, rank 1 its last two
+        lo, hi = (r0 + 3, r1) if rank == 0 else (r0, r1 - 2)
+        part, _ = D.rows_to_columns(torch.from_numpy(slab[lo - r0:hi - r0].copy()), (lo, hi), n)
+        expect = cols.clone()
+        expect[:3] = 0
+        expect[n - 2:] = 0
+        assert torch.equal(part, expect)
         colsn = np.fft.ifft(cols.numpy(), axis=0) * n
         yy, xx = np.mgrid[0:n, c0:c1]
         img = colsn.real * np.where((yy + xx) % 2 == 1, -1.0, 1.0) / (n * n)
