@@ -76,8 +76,16 @@ int skagrid_create(int device, skagrid_ctx **out);
 void skagrid_destroy(skagrid_ctx *ctx);
 const char *skagrid_last_error(const skagrid_ctx *ctx);
 const char *skagrid_version(void);
+/* Grid side N = P.round (theta * lam) (src/Gridding.hs:87, :118, :416, :466, :571): Haskell's round, half to even.  Every
+ * imaging entry point below sizes its grid with this; callers use it to allocate. */
+int64_t skagrid_grid_side(double theta, int64_t lam);
 /* CUDA-event milliseconds of the device work of the last host-pointer call on ctx. */
 double skagrid_last_device_ms(const skagrid_ctx *ctx);
+/* Device pointer and shape of the grid the last host-pointer call left resident in the context (see "Context-resident
+ * grid" above; SKAGRID_EINVAL if there is none).  For one-process-per-GPU callers that sum the per-process grids
+ * themselves (an NCCL all-reduce on this buffer between skagrid_conv_imaging2 and skagrid_grid_to_image /
+ * skagrid_convdegrid2 with NULL grids); the pointer stays valid until the next call that replaces the resident grid. */
+int skagrid_resident_grid(skagrid_ctx *ctx, double **d_grid, int64_t *height, int64_t *width);
 /* Number of kernels launched by this context since creation (bench.py "gpu_launches"). */
 int64_t skagrid_launch_count(const skagrid_ctx *ctx);
 /* Measures the FP64 FMA peak of the device with a register-resident DFMA loop (TFLOP/s). */
@@ -252,6 +260,13 @@ void skagrid_dev_plan_destroy(skagrid_ctx *ctx, skagrid_plan *plan);
  * allocation, no host synchronisation). */
 int skagrid_dev_plan_update(skagrid_ctx *ctx, skagrid_plan *plan, int64_t count, const double *u,
                             const double *v, const int64_t *wbin, const double *vis, void *stream);
+/* An empty plan with room for `capacity` visibilities, and the update from records of `width` doubles
+ * {u, v, wbin (int64 bits), [re, im]} (width 5; 3 for a degrid-only plan) -- the layout skagrid_dev_route_pack produces,
+ * so routed visibilities are binned where the exchange left them. */
+int skagrid_dev_plan_alloc(skagrid_ctx *ctx, const skagrid_geom *geom, int64_t capacity, int slice_override,
+                           skagrid_plan **out);
+int skagrid_dev_plan_update_packed(skagrid_ctx *ctx, skagrid_plan *plan, int64_t count, const double *d_rec,
+                                   int width, void *stream);
 /* Plan statistics: [0] visibilities kept, [1] dropped (no tap on the owned rows), [2] work items,
  * [3] uv tiles, [4] non-empty tiles.  Synchronises `stream`. */
 int skagrid_dev_plan_stats(skagrid_ctx *ctx, skagrid_plan *plan, void *stream, int64_t stats[5]);
@@ -306,6 +321,25 @@ int skagrid_dev_weight_count(skagrid_ctx *ctx, double theta, int64_t lam, int64_
 int skagrid_dev_weight_apply(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *d_u,
                              const double *d_v, const int32_t *d_hist, double *d_vis, void *stream);
 int skagrid_dev_take_error(skagrid_ctx *ctx, void *stream, int *flags_out);
+/* uv-tile-sharded mode with one process per GPU (the exchange itself is the caller's: NCCL all-to-all).
+ * A visibility covers grid rows [y - gh/2, y - gh/2 + gh), y = frac_coord(height, qpx, v) bit-exact (src/Gridding.hs:126-140),
+ * and goes to every rank g whose slab [bounds[g], bounds[g+1]) (host array, nranks + 1 entries from 0 to height)
+ * intersects them; the owner clips taps to its slab (fixoutofbounds, src/Gridding.hs:883-891).
+ *   row_hist     d_hist[row of the footprint centre] += 1 (uint32, height entries): the slab balance
+ *   route_count  d_counts[g] (uint32, nranks entries, zeroed by the call) = records this device sends to rank g
+ *   route_pack   appends the records, destination-major, to d_send: rank g's segment starts at record seg[g] (host array);
+ *                a record is 5 doubles {u, v, wbin, re, im}, or 3 when d_vis == NULL; d_sidx (may be NULL) receives
+ *                the source index of every record
+ *   scatter_add  d_out[d_sidx[i]] += d_back[i] (complex): returned degridding partial sums, one per routed record */
+int skagrid_dev_row_hist(skagrid_ctx *ctx, int64_t height, int64_t qpx, int64_t gh, int64_t count, const double *d_v,
+                         uint32_t *d_hist, void *stream);
+int skagrid_dev_route_count(skagrid_ctx *ctx, int64_t height, int64_t qpx, int64_t gh, int nranks, const int64_t *bounds,
+                            int64_t count, const double *d_v, uint32_t *d_counts, void *stream);
+int skagrid_dev_route_pack(skagrid_ctx *ctx, int64_t height, int64_t qpx, int64_t gh, int nranks, const int64_t *bounds,
+                           int64_t count, const double *d_u, const double *d_v, const int64_t *d_wbin, const double *d_vis,
+                           const int64_t *seg, double *d_send, uint32_t *d_sidx, void *stream);
+int skagrid_dev_scatter_add(skagrid_ctx *ctx, int64_t n, const uint32_t *d_sidx, const double *d_back, double *d_out,
+                            void *stream);
 /* frac_coord (src/Gridding.hs:126-140) on device arrays. */
 int skagrid_dev_frac_coord(skagrid_ctx *ctx, int64_t n, int64_t qpx, int64_t count, const double *d_p,
                            int64_t *d_fl, int64_t *d_frac, int flags, void *stream);

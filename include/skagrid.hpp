@@ -276,7 +276,7 @@ inline Matrix<Visibility> fft(const Context &ctx, const Matrix<Visibility> &g) {
     return out;
 }
 
-inline Index grid_side(F theta, Index lam) { return (Index)std::llround(theta * (F)lam); }
+inline Index grid_side(F theta, Index lam) { return (Index)skagrid_grid_side(theta, lam); }  // P.round: half to even
 
 // simple_imaging (src/Gridding.hs:84-93), conv_imaging (:115-124), aw_imaging (:452-478): ImagingFunction argument order
 inline Matrix<Visibility> simple_imaging(const Context &ctx, F theta, Index lam, const BaseLines &uvw, const SourceInfo &, const std::vector<Visibility> &vis) {

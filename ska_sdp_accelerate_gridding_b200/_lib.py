@@ -26,8 +26,10 @@ _SIGS = {
     "skagrid_destroy": [vp],
     "skagrid_last_error": [vp],
     "skagrid_version": [],
+    "skagrid_grid_side": [dbl, i64],
     "skagrid_last_device_ms": [vp],
     "skagrid_launch_count": [vp],
+    "skagrid_resident_grid": [vp, C.POINTER(vp), C.POINTER(i64), C.POINTER(i64)],
     "skagrid_measure_fp64_tflops": [vp, C.POINTER(dbl)],
     "skagrid_measure_l2_read_tbs": [vp, i64, C.POINTER(dbl)],
     "skagrid_measure_l2_pattern_tbs": [vp, i64, ip, C.POINTER(dbl)],
@@ -63,6 +65,12 @@ _SIGS = {
     "skagrid_dev_plan_create": [vp, C.POINTER(Geom), i64, vp, vp, vp, vp, ip, vp, C.POINTER(vp)],
     "skagrid_dev_plan_destroy": [vp, vp],
     "skagrid_dev_plan_update": [vp, vp, i64, vp, vp, vp, vp, vp],
+    "skagrid_dev_plan_alloc": [vp, C.POINTER(Geom), i64, ip, C.POINTER(vp)],
+    "skagrid_dev_plan_update_packed": [vp, vp, i64, vp, ip, vp],
+    "skagrid_dev_row_hist": [vp, i64, i64, i64, i64, vp, vp, vp],
+    "skagrid_dev_route_count": [vp, i64, i64, i64, ip, vp, i64, vp, vp, vp],
+    "skagrid_dev_route_pack": [vp, i64, i64, i64, ip, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
+    "skagrid_dev_scatter_add": [vp, i64, vp, vp, vp, vp],
     "skagrid_dev_plan_stats": [vp, vp, vp, C.POINTER(i64 * 5)],
     "skagrid_dev_grid": [vp, vp, vp, vp, ip, vp],
     "skagrid_dev_degrid": [vp, vp, vp, vp, vp, vp],
@@ -86,6 +94,7 @@ _RESTYPES = {
     "skagrid_version": C.c_char_p,
     "skagrid_last_device_ms": dbl,
     "skagrid_launch_count": i64,
+    "skagrid_grid_side": i64,
     "skagrid_dev_plan_destroy": None,
 }
 

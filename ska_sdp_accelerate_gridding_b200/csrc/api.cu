@@ -197,7 +197,10 @@ extern "C" int skagrid_mirror_uvw(skagrid_ctx *ctx, int64_t count, double *u, do
     return t.finish();
 }
 
-static i64 grid_side(double theta, i64 lam) { return (i64)llround(theta * (double)lam); }
+// N = P.round (theta * lam) (src/Gridding.hs:87, :118, :416, :466, :571): Haskell's round is half-to-even, which is what
+// nearbyint does in the default rounding mode.  The one definition every layer (C++ mirror, Python, Haskell shim) uses.
+extern "C" int64_t skagrid_grid_side(double theta, int64_t lam) { return (int64_t)nearbyint(theta * (double)lam); }
+static i64 grid_side(double theta, i64 lam) { return (i64)skagrid_grid_side(theta, lam); }
 
 extern "C" int skagrid_doweight(skagrid_ctx *ctx, double theta, int64_t lam, int64_t count, const double *u, const double *v, double *vis) {
     SK_TRY(sk_api_enter(ctx));
@@ -854,6 +857,20 @@ extern "C" int skagrid_dev_weight_apply(skagrid_ctx *ctx, double theta, int64_t 
     const i64 n = grid_side(theta, lam);
     NEED(ctx, n > 0, "dev_weight_apply: round(theta*lam) must be positive");
     return sk_weight_apply_dev(ctx, n, (double)lam, count, d_u, d_v, reinterpret_cast<const uint32_t *>(d_hist), d_vis, sk_stream(ctx, stream));
+}
+
+// Device pointer and shape of the grid the last host-pointer call left resident (NULL grid pointers, include/skagrid.h).
+// For callers that run one process per GPU and reduce the per-process grids themselves (NCCL all-reduce on this buffer
+// between skagrid_conv_imaging2 and skagrid_grid_to_image / skagrid_convdegrid2): the library does no inter-process exchange.
+extern "C" int skagrid_resident_grid(skagrid_ctx *ctx, double **d_grid, int64_t *height, int64_t *width) {
+    SK_TRY(sk_api_enter(ctx));
+    NEED(ctx, d_grid && height && width, "resident_grid: NULL output pointer");
+    *d_grid = nullptr; *height = *width = 0;
+    if (ctx->resident_h <= 0 || ctx->resident_w <= 0) return sk_fail(ctx, SKAGRID_EINVAL, "resident_grid: the context holds no resident grid");
+    void *p = nullptr;
+    SK_TRY(sk_scratch(ctx, "grid", (size_t)(ctx->resident_h * ctx->resident_w) * 16, &p));  // existing buffer: never grows here
+    *d_grid = (double *)p; *height = ctx->resident_h; *width = ctx->resident_w;
+    return SKAGRID_OK;
 }
 
 extern "C" int skagrid_dev_take_error(skagrid_ctx *ctx, void *stream, int *flags_out) {

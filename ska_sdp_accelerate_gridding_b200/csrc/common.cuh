@@ -56,6 +56,11 @@ struct Geom {
     int SG;              // shared-memory subgrid edge = tile - MT + R
     int kpitch;          // row pitch (taps) of the padded copy of the kernel table the kernels read: gw rounded up to 16
                          // (rows start on 256-byte boundaries: a 15-tap row is 2 L1 lines instead of up to 3); gw if R == 0
+    int krows;           // rows per slice of the padded copy: gh, or R in the dense layout
+    int dense;           // dense layout: every slice is R x R taps (zero beyond gh x gw) behind one leading all-zero slice, so a
+                         // thread of the tiled gridder can load the tap of ANY of its residues without a validity test -- taps
+                         // outside the footprint read zeros of this or the previous slice (grid_dense_kernel).  Chosen when the
+                         // padding costs <= 15 % more L2 traffic (S = 14, 15, 30, 31; the headline configurations)
     int kpt;             // bucket keys per uv tile: MTR*MTR (micro-tile buckets) or tile*tile (cell buckets, `cellsort`)
     int cellsort;        // records are additionally grouped by exact footprint origin inside each micro-tile (lets the
                          // degridder keep its grid column in registers across a run of same-cell visibilities)

@@ -290,6 +290,180 @@ __global__ void __launch_bounds__(16 * TY, (R == 16 ? (TY == 8 ? 8 : 6) : (R == 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Dense-layout gridder (Geom::dense: slices of R x R taps, zero outside the footprint, one leading zero slice).
+// Same ownership scheme as grid_tiled_kernel, with the per-record bookkeeping stripped to what the arithmetic needs:
+//   * no validity test and no zeroing per residue: every residue loads a tap, the ones outside the footprint read a
+//     zero of this slice's padding (or of the previous slice's last rows / columns) and add +0;
+//   * the tap address is ONE instruction per residue: a 64-bit per-residue pointer, set up once per micro-tile, plus the
+//     record's 32-bit table offset (IMAD.WIDE.U32);
+//   * no trip-count tests inside the three-slot rotation: the last batch of an item is padded to a multiple of three
+//     with dummy records (vis = 0, offset 0 = the leading zero slice).
+// r01 SASS of grid_tiled_kernel<16,2,3,8>: ~43 instructions per record and thread for 8 DFMA + 2 LDG; this kernel:
+// see profiles/r02_sass_grid_dense.txt.
+template <int R, int TY> struct DenseCfg {
+    static constexpr int rec_batch = R == 16 ? 48 : 126;  // multiples of 3
+    static constexpr int min_blocks = R == 16 ? (TY == 8 ? 8 : (TY == 4 ? 10 : 4)) : 2;
+};
+
+template <int R, int MT, int TY>
+__global__ void __launch_bounds__(16 * TY, DenseCfg<R, TY>::min_blocks) grid_dense_kernel(const GridArgs A) {
+    constexpr int CY = R / TY, CX = R / 16;  // residues per thread
+    constexpr int NT = 16 * TY;
+    constexpr int REC_BATCH = DenseCfg<R, TY>::rec_batch;
+    static_assert(REC_BATCH % 3 == 0 && REC_BATCH <= NT, "one staging thread per record, batches in threes");
+    extern __shared__ double2 sg[];
+    __shared__ __align__(16) uint4 s_rec[2][REC_BATCH * 2];
+    __shared__ uint32_t s_item;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int ncell = A.SG * A.SG;
+    const uint32_t n_items = A.counters[0];
+    constexpr uint32_t mtkey_mask = (uint32_t)(~(MT - 1) & 255) * 0x0101u;
+    const uint4 *recq = reinterpret_cast<const uint4 *>(A.rec);
+
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(&A.counters[A.queue], 1u);
+        __syncthreads();
+        const uint32_t item = s_item;
+        if (item >= n_items) break;
+        const WorkItem it = A.items[item];
+        const uint32_t nrec = it.end - it.begin;
+        const uint32_t nbatch = (nrec + REC_BATCH - 1) / REC_BATCH;
+
+        // stages batch `bi` into buffer bi & 1: cp.async for real records, plain stores of dummies up to the next multiple of 3
+        auto stage = [&](uint32_t bi) {
+            const uint32_t r = bi * REC_BATCH + (uint32_t)tid;
+            uint4 *dst = &s_rec[bi & 1][2 * tid];
+            if (tid < REC_BATCH) {
+                if (r < nrec) {
+                    cp_async16(dst, recq + 2 * (size_t)(it.begin + r));
+                    cp_async16(dst + 1, recq + 2 * (size_t)(it.begin + r) + 1);
+                } else if (r < (nrec + 2u) / 3u * 3u) {
+                    dst[0] = make_uint4(0u, 0u, 0u, 0u);         // vis = 0
+                    dst[1] = make_uint4(0u, 0x00010000u, 0u, 0u);  // table offset 0 (leading zero slice), micro-tile (0,0)
+                }
+            }
+            cp_async_commit();
+        };
+        stage(0);
+        for (int c = tid; c < ncell; c += NT) sg[c] = make_double2(0.0, 0.0);
+
+        double2 acc[CY][CX];
+        int cell_cur[CY][CX];
+        const double2 *tp[CY][CX];  // table + (tap offset of residue (a,b) inside the R x R slice) for the micro-tile issued last
+        uint32_t key_cur = 0xFFFFFFFFu;
+#pragma unroll
+        for (int a = 0; a < CY; ++a)
+#pragma unroll
+            for (int b = 0; b < CX; ++b) { acc[a][b] = make_double2(0.0, 0.0); cell_cur[a][b] = 0; tp[a][b] = A.table; }
+
+        struct Slot { double2 k[CY][CX]; int cell[CY][CX]; bool sw; };
+        auto issue = [&](const uint4 *buf, uint32_t j, Slot &s) {
+            const uint2 m = *reinterpret_cast<const uint2 *>(&buf[2 * j + 1]);  // table offset, loc (broadcast read)
+            const uint32_t key = m.y & mtkey_mask;
+            s.sw = key != key_cur;
+            if (s.sw) {  // block-uniform: all threads walk the same records
+                key_cur = key;
+                const int mx = (int)(key & 255u), my = (int)((key >> 8) & 255u);
+#pragma unroll
+                for (int a = 0; a < CY; ++a) {
+                    const int roty = (ty + TY * a - my) & (R - 1);
+#pragma unroll
+                    for (int b = 0; b < CX; ++b) {
+                        const int rotx = (tx + 16 * b - mx) & (R - 1);
+                        tp[a][b] = A.table + (roty * R + rotx);  // kpitch == R in the dense layout
+                        s.cell[a][b] = (my + roty) * A.SG + mx + rotx;
+                    }
+                }
+            }
+#pragma unroll
+            for (int a = 0; a < CY; ++a)
+#pragma unroll
+                for (int b = 0; b < CX; ++b) s.k[a][b] = ldg2(tp[a][b] + m.x);
+        };
+        auto consume = [&](const uint4 *buf, uint32_t j, const Slot &s) {
+            const double2 vis = *reinterpret_cast<const double2 *>(&buf[2 * j]);
+            if (s.sw) {  // fold the register accumulators into the thread's own subgrid cells and retarget them
+#pragma unroll
+                for (int a = 0; a < CY; ++a)
+#pragma unroll
+                    for (int b = 0; b < CX; ++b) {
+                        if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
+                            double2 t = sg[cell_cur[a][b]];
+                            t.x += acc[a][b].x; t.y += acc[a][b].y;
+                            sg[cell_cur[a][b]] = t;
+                            acc[a][b] = make_double2(0.0, 0.0);
+                        }
+                        cell_cur[a][b] = s.cell[a][b];
+                    }
+            }
+#pragma unroll
+            for (int a = 0; a < CY; ++a)
+#pragma unroll
+                for (int b = 0; b < CX; ++b) {  // (vr + i vi)(kr + i ki)
+                    acc[a][b].x = fma(vis.x, s.k[a][b].x, acc[a][b].x);
+                    acc[a][b].x = fma(-vis.y, s.k[a][b].y, acc[a][b].x);
+                    acc[a][b].y = fma(vis.x, s.k[a][b].y, acc[a][b].y);
+                    acc[a][b].y = fma(vis.y, s.k[a][b].x, acc[a][b].y);
+                }
+        };
+
+        for (uint32_t bi = 0; bi < nbatch; ++bi) {
+            if (bi + 1 < nbatch) stage(bi + 1); else cp_async_commit();
+            cp_async_wait<1>();   // batch bi has landed (for this thread); the barrier publishes it block-wide
+            __syncthreads();      // (first iteration: also orders the subgrid zeroing before any fold)
+            const uint4 *buf = s_rec[bi & 1];
+            const uint32_t m = min((uint32_t)REC_BATCH, nrec - bi * REC_BATCH);
+            const uint32_t m3 = (m + 2u) / 3u * 3u;  // records incl. dummies
+            Slot s0, s1, s2;
+            issue(buf, 0, s0);
+            issue(buf, 1, s1);
+            uint32_t j = 0;
+            for (; j + 3 < m3; j += 3) {
+                issue(buf, j + 2, s2);
+                consume(buf, j, s0);
+                issue(buf, j + 3, s0);
+                consume(buf, j + 1, s1);
+                issue(buf, j + 4, s1);
+                consume(buf, j + 2, s2);
+            }
+            issue(buf, j + 2, s2);
+            consume(buf, j, s0);
+            consume(buf, j + 1, s1);
+            consume(buf, j + 2, s2);
+            __syncthreads();  // every warp is done with buf before it is refilled
+        }
+#pragma unroll
+        for (int a = 0; a < CY; ++a)
+#pragma unroll
+            for (int b = 0; b < CX; ++b) {
+                if (acc[a][b].x != 0.0 || acc[a][b].y != 0.0) {
+                    double2 t = sg[cell_cur[a][b]];
+                    t.x += acc[a][b].x; t.y += acc[a][b].y;
+                    sg[cell_cur[a][b]] = t;
+                }
+            }
+        __syncthreads();
+
+        // subgrid -> grid.  Cells outside the owned rows / the grid are dropped (fixoutofbounds).
+        const int tyi = (int)(it.tile / (uint32_t)A.ntx), txi = (int)(it.tile % (uint32_t)A.ntx);
+        const int gx0 = (txi << A.tshift) - (A.gw - 1), gy0 = (tyi << A.tshift) - (A.gh - 1);
+        for (int c = tid; c < ncell; c += NT) {
+            const double2 v = sg[c];
+            if (v.x == 0.0 && v.y == 0.0) continue;
+            const int cy = c / A.SG, cx = c - cy * A.SG;
+            const int gx = gx0 + cx, gy = gy0 + cy;
+            if ((unsigned)gx < (unsigned)A.width && (unsigned)gy < (unsigned)A.nrows) {
+                double *g = reinterpret_cast<double *>(A.grid + (size_t)gy * A.width + gx);
+                red_add(g, v.x);
+                red_add(g + 1, v.y);
+            }
+        }
+        cp_async_wait<0>();
+        // the next iteration's first barrier orders these reads before the subgrid is zeroed again
+    }
+}
+
 // Variant 1: the literal unordered scatter.  One thread per (record, tap).
 __global__ void __launch_bounds__(256) grid_atomic_kernel(const GridArgs A) {
     const i64 total = (i64)A.counters[2] * A.s2;  // counters[2] = records kept by the plan
@@ -466,72 +640,92 @@ __global__ void __launch_bounds__(NT, MINB) degrid_reg_kernel(const GridArgs A) 
         const uint32_t nrec = it.end - it.begin;
         const uint32_t chunk = (nrec + (uint32_t)NHW - 1u) / (uint32_t)NHW;  // contiguous records per half-warp
         const uint32_t r0 = (uint32_t)hw * chunk;
+        const uint32_t r1 = min(nrec, r0 + chunk);  // this half-warp's run is [r0, r1)
         double2 g[GH];
 #pragma unroll
         for (int i = 0; i < GH; ++i) g[i] = make_double2(0.0, 0.0);
         uint32_t cur = 0xFFFFFFFFu;
-        for (uint32_t q = 0; q < chunk; ++q) {  // both halves of a warp run the same trip count (shuffles below)
-            const uint32_t r = r0 + q;
-            const bool live = r < nrec;
-            double ar = 0.0, ai = 0.0;
-            uint32_t out_index = 0;
-            if (live) {
-                const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(A.rec + it.begin + r) + 1);
-                out_index = meta.z;
-                const uint32_t origin = meta.y & 0xFFFFu;
-                if (origin != cur) {  // half-warp-uniform: (re)load this lane's column of the footprint
-                    cur = origin;
+        // The run is walked in blocks of 16 records: lane l of the half-warp loads the second half (table offset, loc, output
+        // index, tile) of record l of the block with ONE coalesced request -- the next block's while the current one is
+        // processed -- and the 16 records are then broadcast by shuffle.  (r01: one dependent global load per record in
+        // front of its tap loads; ncu long_scoreboard 5.0, 25 % occupancy.)  Lane l also keeps the result of record l,
+        // so a block ends with one 16-byte store per lane instead of two 8-byte stores per record.
+        const uint4 *recm = reinterpret_cast<const uint4 *>(A.rec + it.begin) + 1;
+        auto load_meta = [&](uint32_t q0) {
+            const uint32_t r = r0 + q0 + (uint32_t)hl;
+            return r < r1 ? __ldg(recm + 2 * (size_t)r) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        uint4 meta_next = load_meta(0);
+        for (uint32_t q0 = 0; q0 < chunk; q0 += 16) {  // both halves of a warp run the same trip count (shuffles below)
+            const uint4 meta = meta_next;
+            if (q0 + 16 < chunk) meta_next = load_meta(q0 + 16);
+            double2 res = make_double2(0.0, 0.0);
+#pragma unroll 1
+            for (int qq = 0; qq < 16; ++qq) {
+                const uint32_t kb = __shfl_sync(0xffffffffu, meta.x, qq, 16);
+                const uint32_t origin = __shfl_sync(0xffffffffu, meta.y, qq, 16) & 0xFFFFu;
+                const bool live = r0 + q0 + (uint32_t)qq < r1;
+                double ar = 0.0, ai = 0.0;
+                if (live) {
+                    if (origin != cur) {  // half-warp-uniform: (re)load this lane's column of the footprint
+                        cur = origin;
+                        const int lx = (int)(origin & 255u), ly = (int)(origin >> 8);
+                        const double2 *gp = sg + ly * SGW + lx + hl;
+#pragma unroll
+                        for (int i = 0; i < GH; ++i) g[i] = (col && (EXACT || i < A.gh)) ? gp[i * SGW] : make_double2(0.0, 0.0);
+                    }
                     const int lx = (int)(origin & 255u), ly = (int)(origin >> 8);
-                    const double2 *gp = sg + ly * SGW + lx + hl;
+                    const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
+                    const double2 *kp = A.table + (uint32_t)(kb + dy * (uint32_t)A.kpitch + dx + (uint32_t)hl);
+                    double2 k[GH];
 #pragma unroll
-                    for (int i = 0; i < GH; ++i) g[i] = (col && (EXACT || i < A.gh)) ? gp[i * SGW] : make_double2(0.0, 0.0);
+                    for (int i = 0; i < GH; ++i) k[i] = (EXACT || i < A.gh) ? ldg2(kp + i * 16) : make_double2(0.0, 0.0);  // kpitch == 16 here: immediate offsets
+#pragma unroll
+                    for (int i = 0; i < GH; ++i) {  // conj(k) * g
+                        ar = fma(k[i].x, g[i].x, ar); ar = fma(k[i].y, g[i].y, ar);
+                        ai = fma(k[i].x, g[i].y, ai); ai = fma(-k[i].y, g[i].x, ai);
+                    }
                 }
-                const int lx = (int)(origin & 255u), ly = (int)(origin >> 8);
-                const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
-                const double2 *kp = A.table + (uint32_t)(meta.x + dy * (uint32_t)A.kpitch + dx + (uint32_t)hl);
-                double2 k[GH];
-#pragma unroll
-                for (int i = 0; i < GH; ++i) k[i] = (EXACT || i < A.gh) ? ldg2(kp + i * 16) : make_double2(0.0, 0.0);  // kpitch == 16 here: immediate offsets
-#pragma unroll
-                for (int i = 0; i < GH; ++i) {  // conj(k) * g
-                    ar = fma(k[i].x, g[i].x, ar); ar = fma(k[i].y, g[i].y, ar);
-                    ai = fma(k[i].x, g[i].y, ai); ai = fma(-k[i].y, g[i].x, ai);
-                }
-            }
-            // 16-lane reduction of (ar, ai) with half the shuffles: after the first exchange the lanes with bit 3 clear
-            // carry only the real sum and the others only the imaginary one, so the remaining three steps move one double
-            {
+                // 16-lane reduction of (ar, ai) with half the shuffles: after the first exchange the lanes with bit 3 clear
+                // carry only the real sum and the others only the imaginary one, so the remaining three steps move one double;
+                // a last exchange gives every lane both
                 const bool hi = (hl & 8) != 0;
                 const double send = hi ? ar : ai, keep = hi ? ai : ar;
                 double sum = keep + __shfl_xor_sync(0xffffffffu, send, 8);
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                // lane 0 of the half-warp holds the real part, lane 8 the imaginary part
-                if (live && (hl & 7) == 0) reinterpret_cast<double *>(A.vis_out + out_index)[hi ? 1 : 0] = sum;
+                const double other = __shfl_xor_sync(0xffffffffu, sum, 8);
+                if (hl == qq) res = hi ? make_double2(other, sum) : make_double2(sum, other);
             }
+            if (r0 + q0 + (uint32_t)hl < r1) A.vis_out[meta.z] = res;
         }
     }
 }
 
-// Padded copy of the caller's kernel table: [slice][gh][kpitch], zero in the pad columns.  A few MB for a w-kernel
-// table (microseconds), one S x S kernel per visibility on the AW path.
+// Padded copy of the caller's kernel table: [lead + slice][krows][kpitch], zero outside the gh x gw taps (and in the
+// `lead` leading slices of the dense layout).  A few MB for a w-kernel table (microseconds), one S x S kernel per
+// visibility on the AW path.
 __global__ void __launch_bounds__(256) pad_table_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, i64 nslices, int gh, int gw,
-                                                        int kpitch) {
-    const i64 total = nslices * gh * kpitch;
+                                                        int krows, int kpitch, int lead) {
+    const i64 per = (i64)krows * kpitch;
+    const i64 total = (nslices + lead) * per;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += stride) {
         const int j = (int)(c % kpitch);
-        const i64 row = c / kpitch;  // slice * gh + i
-        out[c] = j < gw ? in[row * gw + j] : make_double2(0.0, 0.0);
+        const i64 row = c / kpitch;
+        const int i = (int)(row % krows);
+        const i64 sl = row / krows - lead;
+        out[c] = (sl >= 0 && i < gh && j < gw) ? in[(sl * gh + i) * gw + j] : make_double2(0.0, 0.0);
     }
 }
 
 static int prepare_table(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, cudaStream_t st, const double **out) {
     const Geom &g = plan->g;
-    if (g.kpitch == (int)g.gw) { *out = table; return SKAGRID_OK; }
+    if (!g.dense && g.kpitch == (int)g.gw) { *out = table; return SKAGRID_OK; }
+    const int lead = g.dense ? 1 : 0;
     const i64 nslices = plan->slice_override ? plan->count : g.nw * g.qpx * g.qpx;
     const i64 cap_slices = plan->slice_override ? plan->capacity : nslices;
-    const size_t need = (size_t)(cap_slices * g.gh * g.kpitch) * sizeof(double2);
+    const size_t need = (size_t)((cap_slices + lead) * g.krows * g.kpitch) * sizeof(double2);
     if (plan->table_bytes < need) {
         if (plan->d_table) { SK_CUDA(ctx, cudaStreamSynchronize(st)); cudaFree(plan->d_table); plan->d_table = nullptr; plan->table_bytes = 0; }
         if (cudaMalloc(&plan->d_table, need) != cudaSuccess) {
@@ -541,9 +735,10 @@ static int prepare_table(skagrid_ctx *ctx, skagrid_plan *plan, const double *tab
         plan->table_bytes = need;
     }
     if (nslices > 0) {
-        i64 b = (nslices * g.gh * g.kpitch + 255) / 256;
+        i64 b = ((nslices + lead) * g.krows * g.kpitch + 255) / 256;
         if (b > (i64)ctx->sm_count * 16) b = (i64)ctx->sm_count * 16;
-        pad_table_kernel<<<(unsigned)b, 256, 0, st>>>(reinterpret_cast<const double2 *>(table), plan->d_table, nslices, (int)g.gh, (int)g.gw, g.kpitch);
+        pad_table_kernel<<<(unsigned)b, 256, 0, st>>>(reinterpret_cast<const double2 *>(table), plan->d_table, nslices, (int)g.gh, (int)g.gw, g.krows,
+                                                       g.kpitch, lead);
         SK_LAUNCH_CHECK(ctx);
     }
     *out = reinterpret_cast<const double *>(plan->d_table);
@@ -581,6 +776,20 @@ static int launch_tiled(skagrid_ctx *ctx, const GridArgs &A, cudaStream_t st) {
     return SKAGRID_OK;
 }
 
+template <int R, int MT, int TY>
+static int launch_dense(skagrid_ctx *ctx, const GridArgs &A, cudaStream_t st) {
+    constexpr int NT = 16 * TY;
+    const size_t smem = (size_t)A.SG * A.SG * sizeof(double2);
+    if (ctx->smem_configured.insert((const void *)grid_dense_kernel<R, MT, TY>).second)
+        SK_CUDA(ctx, cudaFuncSetAttribute(grid_dense_kernel<R, MT, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int per_sm = 0;
+    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_dense_kernel<R, MT, TY>, NT, smem));
+    if (per_sm < 1) return sk_fail(ctx, SKAGRID_ECUDA, "dense gridder does not fit on an SM (smem %zu)", smem);
+    grid_dense_kernel<R, MT, TY><<<ctx->sm_count * per_sm, NT, smem, st>>>(A);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
 extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, double *grid, int variant, void *stream) {
     if (!ctx || !plan || !table || !grid) return SKAGRID_EINVAL;
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -598,6 +807,18 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
     }
     SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 1, 0, sizeof(uint32_t), st));
     const int MT = plan->g.MT;
+    if (plan->g.dense && variant != 2 && variant != 3 && variant != 4) {
+        // dense layout (S = 14, 15, 29..31).  B200, r02 (profiles/r02_gridder_ab.md): R=16, 1e8 visibilities: 8x16 threads with two
+        // residues each 21.3 ms (default), 4x16 threads with four residues 22.5 ms (variant 5), r01 predicated kernel 21.65 ms;
+        // R=32 (S=31), 5e7 visibilities: 16x16 threads with four residues 42.8 ms (default), 32x16 threads with two 44.2 ms
+        // (variant 5), r01 kernel 44.6 ms
+        if (R == 16) {
+            if (variant == 5) return MT == 2 ? launch_dense<16, 2, 4>(ctx, A, st) : launch_dense<16, 4, 4>(ctx, A, st);
+            return MT == 2 ? launch_dense<16, 2, 8>(ctx, A, st) : launch_dense<16, 4, 8>(ctx, A, st);
+        }
+        if (variant == 5) return MT == 2 ? launch_dense<32, 2, 32>(ctx, A, st) : launch_dense<32, 4, 32>(ctx, A, st);
+        return MT == 2 ? launch_dense<32, 2, 16>(ctx, A, st) : launch_dense<32, 4, 16>(ctx, A, st);
+    }
     // variants (A/B measurements on B200; 1e8 visibilities, config 4, per launch):
     //   0  default.  R=16: 8x16 threads, two residues each, three tap slots (22.5 ms)
     //                R=32: 32x16 threads, two residues each, three tap slots (S=31, 5e7 on 32768^2: 62 ms)

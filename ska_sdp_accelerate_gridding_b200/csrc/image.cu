@@ -68,7 +68,7 @@ static int get_fft_plan(skagrid_ctx *ctx, i64 n, cufftHandle *out) {
 // even n: out[y,x] = g[y,x] + (x==0||y==0 ? 0 : conj g[n-y,n-x]);  odd n: g + conj(g[n-1-y,n-1-x]).
 // One thread per unordered pair {cell, mirror}; safe in place (out == g).  modulate != 0 additionally
 // multiplies by (-1)^(x+y) (first half of the centred transform for even n).
-__global__ void __launch_bounds__(256) hermitian_kernel(i64 n, const double2 *__restrict__ g, double2 *__restrict__ out, int modulate) {
+__global__ void __launch_bounds__(256) hermitian_kernel(i64 n, const double2 *g, double2 *out, int modulate)  /* g == out allowed: no __restrict__ */ {
     const i64 total = n * n;
     const int even = (n % 2 == 0);
     const i64 stride = (i64)gridDim.x * blockDim.x;
@@ -106,7 +106,7 @@ int sk_hermitian_dev(skagrid_ctx *ctx, i64 n, const double *g, double *out, cuda
 }
 
 // ---------------------------------------------------------------------------------------- centred FFT
-__global__ void __launch_bounds__(256) modulate_kernel(i64 n, const double2 *__restrict__ in, double2 *__restrict__ out, double scale) {
+__global__ void __launch_bounds__(256) modulate_kernel(i64 n, const double2 *in, double2 *out, double scale)  /* in == out allowed */ {
     const i64 total = n * n;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += stride) {

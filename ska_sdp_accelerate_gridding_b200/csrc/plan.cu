@@ -18,6 +18,7 @@
 struct BinParams {
     double halfwf, wf, halfhf, hf, qpxf, qpxfrac;
     i64 qpx, width, height, row0, row1, gh, gw, halfgh, halfgw, nw, kpitch;
+    uint32_t kstride, klead;  // taps per slice of the padded table; leading all-zero slices (dense layout: 1)
     int ntx, nty, normalise, slice_override;
     int mt_shift, mtr;  // micro-tile edge = 1 << mt_shift; micro-tiles per tile row
     int tshift;         // log2 of the uv tile edge
@@ -35,7 +36,7 @@ static BinParams make_bin_params(const Geom &g, int slice_override) {
     p.qpx = g.qpx; p.width = g.width; p.height = g.height; p.row0 = g.row0; p.row1 = g.row1;
     p.gh = g.gh; p.gw = g.gw; p.halfgh = g.gh / 2; p.halfgw = g.gw / 2; p.nw = g.nw;
     p.ntx = g.ntx; p.nty = g.nty; p.normalise = g.normalise; p.slice_override = slice_override;
-    p.mt_shift = g.MT == 4 ? 2 : 1; p.mtr = g.MTR; p.kpitch = g.kpitch; p.tshift = g.tshift; p.kpt = g.kpt; p.cellsort = g.cellsort;
+    p.mt_shift = g.MT == 4 ? 2 : 1; p.mtr = g.MTR; p.kpitch = g.kpitch; p.kstride = (uint32_t)(g.krows * g.kpitch); p.klead = g.dense ? 1u : 0u; p.tshift = g.tshift; p.kpt = g.kpt; p.cellsort = g.cellsort;
     return p;
 }
 
@@ -68,13 +69,18 @@ int sk_geom_init(skagrid_ctx *ctx, const skagrid_geom *in, i64 capacity, Geom *g
     g->MTR = g->tile / g->MT;
     g->SG = g->tile - g->MT + rr;
     g->kpitch = g->R ? (int)((in->gw + 15) / 16 * 16) : (int)in->gw;
+    g->krows = (int)in->gh;
+    g->dense = 0;
+    if ((g->R == 16 || g->R == 32) && (double)g->R * g->R <= 1.15 * (double)(in->gh * g->kpitch)) g->dense = 1;
+    if (const char *e = getenv("SKAGRID_DENSE")) g->dense = (atoi(e) && (g->R == 16 || g->R == 32)) ? 1 : 0;  // tuning experiments
+    if (g->dense) { g->kpitch = g->R; g->krows = g->R; }
     // cell-granular buckets when the offset table stays small (<= 2^27 keys, 0.5 GB); else micro-tile buckets
     g->cellsort = (ntx * nty * (i64)g->tile * g->tile <= ((i64)1 << 27)) ? 1 : 0;
     if (const char *e = getenv("SKAGRID_CELLSORT")) g->cellsort = atoi(e) ? 1 : 0;  // tuning experiments
     g->kpt = g->cellsort ? g->tile * g->tile : g->MTR * g->MTR;
     const i64 nkeys = ntx * nty * g->kpt;
     if (nkeys >= (i64)0xFFFFFFF0ll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: grid too large for 32-bit bucket keys");
-    if (in->nw * in->qpx * in->qpx * in->gh * g->kpitch >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel table has more than 2^32 taps");
+    if ((in->nw * in->qpx * in->qpx + 1) * g->krows * g->kpitch >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "geom: kernel table has more than 2^32 taps");
     g->ntx = (int)ntx; g->nty = (int)nty; g->nkeys = nkeys; g->normalise = 1;
     return SKAGRID_OK;
 }
@@ -102,12 +108,16 @@ __device__ __forceinline__ bool bin_vis(const BinParams &P, double pu, double pv
     const uint32_t mtm = (1u << P.mt_shift) - 1u, dx = (uint32_t)lx & mtm, dy = (uint32_t)ly & mtm;
     loc = (0x10000u << ((dy << P.mt_shift) | dx)) | ((uint32_t)ly << 8) | (uint32_t)lx;
     // element offset of tap (-dy, -dx) of the slice, modulo 2^32: the gridder adds its per-thread tap offset
-    slice = slice * (uint32_t)(P.gh * P.kpitch) - (dy * (uint32_t)P.kpitch + dx);
+    slice = (slice + P.klead) * P.kstride - (dy * (uint32_t)P.kpitch + dx);
     // micro-tile major; inside the micro-tile optionally by exact origin (dy, dx)
     key = (uint32_t)(ty * P.ntx + tx) * (uint32_t)P.kpt + (P.cellsort ? ((mt << (2 * P.mt_shift)) | (dy << P.mt_shift) | dx) : mt);
     return true;
 }
 
+// ES: distance (in 8-byte elements) between consecutive visibilities in u / v / wbin -- 1 for the reference's structure of
+// arrays, W for records of W doubles {u, v, wbin, [re, im]} as the uv-tile-sharded routing delivers them
+// (skagrid_dev_plan_update_packed); the visibility itself is then two doubles at stride W instead of an aligned double2.
+template <int ES>
 __global__ void __launch_bounds__(256) bin_hist_kernel(BinParams P, i64 count, const double *__restrict__ u,
                                                        const double *__restrict__ v, const i64 *__restrict__ wbin,
                                                        uint32_t *__restrict__ hist, uint32_t *__restrict__ counters,
@@ -116,7 +126,7 @@ __global__ void __launch_bounds__(256) bin_hist_kernel(BinParams P, i64 count, c
     uint32_t kept = 0, dropped = 0, rerr = 0;
     for (i64 k = (i64)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
         uint32_t key, slice, loc; bool re;
-        if (bin_vis(P, u[k], v[k], wbin ? wbin[k] : 0, k, key, slice, loc, re)) { atomicAdd(&hist[key], 1u); ++kept; }
+        if (bin_vis(P, u[k * ES], v[k * ES], wbin ? wbin[k * ES] : 0, k, key, slice, loc, re)) { atomicAdd(&hist[key], 1u); ++kept; }
         else { ++dropped; rerr |= re ? 1u : 0u; }
     }
     // block-level reduction of the statistics: one atomic per warp
@@ -136,6 +146,7 @@ __global__ void __launch_bounds__(256) bin_hist_kernel(BinParams P, i64 count, c
 // stores): the kernel is bound by the latency of random DRAM / L2 accesses at full occupancy (ncu: every warp on the
 // long scoreboard, DRAM at 28 %), so the only lever is more independent accesses in flight per thread.
 constexpr int SCATTER_U = 4;
+template <int ES>
 __global__ void __launch_bounds__(256) bin_scatter_kernel(BinParams P, i64 count, const double *__restrict__ u,
                                                           const double *__restrict__ v, const i64 *__restrict__ wbin,
                                                           const double *__restrict__ vis, uint32_t *__restrict__ offs,
@@ -150,9 +161,9 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(BinParams P, i64 count
         for (int i = 0; i < SCATTER_U; ++i) {
             const i64 k = k0 + (i64)i * blockDim.x;
             ok[i] = k < count;
-            pu[i] = ok[i] ? u[k] : 0.0;
-            pv[i] = ok[i] ? v[k] : 0.0;
-            wb[i] = (ok[i] && wbin) ? wbin[k] : 0;
+            pu[i] = ok[i] ? u[k * ES] : 0.0;
+            pv[i] = ok[i] ? v[k * ES] : 0.0;
+            wb[i] = (ok[i] && wbin) ? wbin[k * ES] : 0;
         }
 #pragma unroll
         for (int i = 0; i < SCATTER_U; ++i) {
@@ -166,7 +177,10 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(BinParams P, i64 count
             if (!ok[i]) continue;
             const i64 k = k0 + (i64)i * blockDim.x;
             double2 vv = make_double2(0.0, 0.0);
-            if (vis) vv = reinterpret_cast<const double2 *>(vis)[k];
+            if (vis) {
+                if constexpr (ES == 1) vv = reinterpret_cast<const double2 *>(vis)[k];
+                else vv = make_double2(vis[k * ES], vis[k * ES + 1]);
+            }
             // one 256-bit store per record (STG.E.ENL2.256 on sm_100a): the destination is a random 32-byte slot, so this
             // halves the store instructions the LSU has to queue compared with two 128-bit stores
             const unsigned long long q0 = (unsigned long long)__double_as_longlong(vv.x), q1 = (unsigned long long)__double_as_longlong(vv.y);
@@ -276,10 +290,17 @@ void sk_plan_free(skagrid_plan *p) {
     delete p;
 }
 
+static int plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double *u, const double *v, const i64 *wbin, const double *vis,
+                     int es, cudaStream_t st);
 int sk_plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double *u, const double *v,
                      const i64 *wbin, const double *vis, cudaStream_t st) {
+    return plan_fill(ctx, p, count, u, v, wbin, vis, 1, st);
+}
+
+static int plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double *u, const double *v, const i64 *wbin, const double *vis,
+                     int es, cudaStream_t st) {
     if (count < 0 || count > p->capacity) return sk_fail(ctx, SKAGRID_EINVAL, "plan: count %lld exceeds capacity %lld", count, p->capacity);
-    if (p->slice_override && count * p->g.gh * p->g.kpitch >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "plan: per-visibility kernel table has more than 2^32 taps");
+    if (p->slice_override && (count + 1) * p->g.krows * p->g.kpitch >= (i64)0xFFFFFFFFll) return sk_fail(ctx, SKAGRID_EINVAL, "plan: per-visibility kernel table has more than 2^32 taps");
     if (count > 0 && (!u || !v)) return sk_fail(ctx, SKAGRID_EINVAL, "plan: u/v is NULL");
     p->count = count;
     p->has_vis = vis != nullptr;
@@ -289,7 +310,9 @@ int sk_plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double *u, 
     SK_CUDA(ctx, cudaMemsetAsync(p->d_counters, 0, 16 * sizeof(uint32_t), st));
     const int blocks = ctx->sm_count * 8;
     if (count > 0) {
-        bin_hist_kernel<<<blocks, 256, 0, st>>>(P, count, u, v, wbin, p->d_offs, p->d_counters, ctx->d_flags);
+        if (es == 1) bin_hist_kernel<1><<<blocks, 256, 0, st>>>(P, count, u, v, wbin, p->d_offs, p->d_counters, ctx->d_flags);
+        else if (es == 3) bin_hist_kernel<3><<<blocks, 256, 0, st>>>(P, count, u, v, wbin, p->d_offs, p->d_counters, ctx->d_flags);
+        else bin_hist_kernel<5><<<blocks, 256, 0, st>>>(P, count, u, v, wbin, p->d_offs, p->d_counters, ctx->d_flags);
         SK_LAUNCH_CHECK(ctx);
     }
     const i64 n = g.nkeys + 1;
@@ -301,7 +324,9 @@ int sk_plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double *u, 
     scan_apply<<<(unsigned)nb, SCAN_T, 0, st>>>(p->d_offs, n, p->d_blocksums);
     SK_LAUNCH_CHECK(ctx);
     if (count > 0) {
-        bin_scatter_kernel<<<blocks, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
+        if (es == 1) bin_scatter_kernel<1><<<blocks, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
+        else if (es == 3) bin_scatter_kernel<3><<<blocks, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
+        else bin_scatter_kernel<5><<<blocks, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
         SK_LAUNCH_CHECK(ctx);
     }
     const int ntiles = g.ntx * g.nty;
@@ -365,6 +390,14 @@ extern "C" int skagrid_dev_plan_create(skagrid_ctx *ctx, const skagrid_geom *geo
     return SKAGRID_OK;
 }
 
+// An empty plan with room for `capacity` visibilities (filled later by skagrid_dev_plan_update / _update_packed).
+extern "C" int skagrid_dev_plan_alloc(skagrid_ctx *ctx, const skagrid_geom *geom, int64_t capacity, int slice_override, skagrid_plan **out) {
+    if (!ctx || !out) return SKAGRID_EINVAL;
+    *out = nullptr;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    return sk_plan_alloc(ctx, geom, capacity, slice_override, out);
+}
+
 extern "C" void skagrid_dev_plan_destroy(skagrid_ctx *ctx, skagrid_plan *plan) {
     if (ctx) cudaSetDevice(ctx->device);
     sk_plan_free(plan);
@@ -375,6 +408,16 @@ extern "C" int skagrid_dev_plan_update(skagrid_ctx *ctx, skagrid_plan *plan, int
     if (!ctx || !plan) return SKAGRID_EINVAL;
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
     return sk_plan_fill(ctx, plan, count, u, v, (const i64 *)wbin, vis, sk_stream(ctx, stream));
+}
+
+// Records of `width` doubles {u, v, wbin (int64 bits), [re, im]}: width 5 with visibilities, 3 for degrid-only plans.
+extern "C" int skagrid_dev_plan_update_packed(skagrid_ctx *ctx, skagrid_plan *plan, int64_t count, const double *d_rec, int width, void *stream) {
+    if (!ctx || !plan) return SKAGRID_EINVAL;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (width != 3 && width != 5) return sk_fail(ctx, SKAGRID_EINVAL, "plan_update_packed: record width must be 3 or 5 doubles");
+    if (count > 0 && !d_rec) return sk_fail(ctx, SKAGRID_EINVAL, "plan_update_packed: NULL records");
+    return plan_fill(ctx, plan, count, d_rec, d_rec + 1, reinterpret_cast<const i64 *>(d_rec + 2), width == 5 ? d_rec + 3 : nullptr, width,
+                     sk_stream(ctx, stream));
 }
 
 extern "C" int skagrid_dev_plan_stats(skagrid_ctx *ctx, skagrid_plan *plan, void *stream, int64_t stats[5]) {

@@ -31,6 +31,21 @@ def context_for_current_device() -> Context:
     return get_context(torch.cuda.current_device())
 
 
+def check_errors(ctx=None):
+    """Reads and clears the context's device error word (synchronises the current stream) and raises on ANY pending bit:
+    bit 0 = a w-plane / sub-cell / antenna index out of range in a plan (those visibilities were dropped), bit 1 = a
+    visibility outside the weight grid.  The asynchronous entry points (Plan.update, weight_count_) only set the bits."""
+    ctx = ctx or context_for_current_device()
+    flags = C.c_int()
+    ctx.check(ctx.lib.skagrid_dev_take_error(ctx.h, _stream(), C.byref(flags)))
+    if flags.value & 1:
+        raise _lib.SkagridError(-5, "plan: a w-plane / oversampling / antenna index is out of range (the visibility was dropped)")
+    if flags.value & 2:
+        raise _lib.SkagridError(-5, "doweight: a visibility falls outside the weight grid")
+    if flags.value:
+        raise _lib.SkagridError(-5, f"device error word {flags.value:#x}")
+
+
 def synth_vis(seed, first, count, n, support, nw, uniform=False, with_vis=True, ctx=None):
     """SURVEY.md 8d synthetic SKA1-Low-shaped visibilities [first, first+count) -> (u, v, wbin, vis) on the device."""
     ctx = ctx or context_for_current_device()
@@ -92,10 +107,7 @@ def doweight_(theta, lam, u, v, vis, ctx=None):
     ctx = ctx or context_for_current_device()
     _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(vis, torch.complex128, "vis")
     ctx.check(ctx.lib.skagrid_dev_doweight(ctx.h, float(theta), int(lam), u.numel(), _p(u), _p(v), _p(vis), _stream()))
-    flags = C.c_int()
-    ctx.check(ctx.lib.skagrid_dev_take_error(ctx.h, _stream(), C.byref(flags)))
-    if flags.value & 2:
-        raise _lib.SkagridError(-5, "doweight: a visibility falls outside the weight grid")
+    check_errors(ctx)
 
 
 def slab_fft_rows_(n, row0, slab, ctx=None):
@@ -119,10 +131,22 @@ def slab_fft_cols_(n, col0, cols, want_image=True, ctx=None):
     return img, mx
 
 
+def grid_side(theta, lam, ctx=None):
+    """N = P.round (theta * lam), half to even (src/Gridding.hs:571): the library's own definition."""
+    return int(_lib.load().skagrid_grid_side(float(theta), int(lam)))
+
+
+def _chk_hist(ctx, theta, lam, hist):
+    n = grid_side(theta, lam)
+    if tuple(hist.shape) != (n, n):
+        raise ValueError(f"hist must be [{n}, {n}] = round(theta*lam) squared, got {tuple(hist.shape)}")
+
+
 def weight_count_(theta, lam, u, v, hist, ctx=None):
     """First phase of doweight for sharded visibilities: hist (n x n int32, n = round(theta*lam)) += cell counts of (u, v)."""
     ctx = ctx or context_for_current_device()
     _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(hist, torch.int32, "hist")
+    _chk_hist(ctx, theta, lam, hist)
     ctx.check(ctx.lib.skagrid_dev_weight_count(ctx.h, float(theta), int(lam), u.numel(), _p(u), _p(v), _p(hist), _stream()))
 
 
@@ -130,11 +154,9 @@ def weight_apply_(theta, lam, u, v, hist, vis, ctx=None):
     """Second phase: vis /= hist[cell of (u, v)], in place.  Raises if a visibility fell outside the weight grid."""
     ctx = ctx or context_for_current_device()
     _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(hist, torch.int32, "hist"); _chk(vis, torch.complex128, "vis")
+    _chk_hist(ctx, theta, lam, hist)
     ctx.check(ctx.lib.skagrid_dev_weight_apply(ctx.h, float(theta), int(lam), u.numel(), _p(u), _p(v), _p(hist), _p(vis), _stream()))
-    flags = C.c_int()
-    ctx.check(ctx.lib.skagrid_dev_take_error(ctx.h, _stream(), C.byref(flags)))
-    if flags.value & 2:
-        raise _lib.SkagridError(-5, "doweight: a visibility falls outside the weight grid")
+    check_errors(ctx)
 
 
 def w_kernel_table(theta, ws, npixff, npixkern, qpx, conjugate=True, ctx=None):
@@ -168,10 +190,50 @@ class Plan:
                                                             int(slice_override), _stream(), C.byref(h)))
         self.h = h
 
-    def update(self, u, v, wbin=None, vis=None):
+    @classmethod
+    def empty(cls, height, width, table_shape, capacity, rows=None, slice_override=False, ctx=None):
+        """A plan with room for `capacity` visibilities and no batch yet (skagrid_dev_plan_alloc)."""
+        self = cls.__new__(cls)
+        self.ctx = ctx or context_for_current_device()
+        if len(table_shape) == 4:
+            table_shape = (1,) + tuple(table_shape)
+        nw, qpx, qpx2, gh, gw = table_shape
+        if qpx != qpx2:
+            raise ValueError("kernel table must be [nw,qpx,qpx,gh,gw]")
+        row0, row1 = rows if rows is not None else (0, height)
+        self.geom = _lib.Geom(height, width, row0, row1, nw, qpx, gh, gw)
+        self.rows, self.width = (row0, row1), width
+        self.count, self.capacity = 0, max(int(capacity), 1)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.skagrid_dev_plan_alloc(self.ctx.h, C.byref(self.geom), self.capacity, int(slice_override), C.byref(h)))
+        self.h = h
+        return self
+
+    def update_packed(self, rec, check=True):
+        """Re-bins records [count, W] of W doubles {u, v, wbin (int64 bits), [re, im]} (W = 5, or 3 for a degrid-only
+        batch): the layout the uv-tile-sharded routing delivers (skagrid_dev_route_pack)."""
+        _chk(rec, torch.float64, "rec")
+        if rec.dim() != 2 or rec.shape[1] not in (3, 5):
+            raise ValueError("rec must be [count, 3] or [count, 5] float64")
+        if rec.shape[0] > self.capacity:
+            raise ValueError("batch exceeds the plan's capacity")
+        self.ctx.check(self.ctx.lib.skagrid_dev_plan_update_packed(self.ctx.h, self.h, int(rec.shape[0]), _p(rec), int(rec.shape[1]), _stream()))
+        self.count = int(rec.shape[0])
+        if check:
+            self.check()
+
+    def update(self, u, v, wbin=None, vis=None, check=True):
+        """Re-bins a new batch into the existing buffers.  check=True (default) reads the device error word afterwards
+        (one stream synchronisation) and raises SKAGRID_ERANGE for an out-of-range w-plane index, exactly as the
+        constructor does; timed loops pass check=False and call `check()` once at the end."""
         _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(wbin, torch.int64, "wbin"); _chk(vis, torch.complex128, "vis")
         self.ctx.check(self.ctx.lib.skagrid_dev_plan_update(self.ctx.h, self.h, int(u.numel()), _p(u), _p(v), _p(wbin), _p(vis), _stream()))
         self.count = int(u.numel())
+        if check:
+            self.check()
+
+    def check(self):
+        check_errors(self.ctx)
 
     def stats(self):
         out = (C.c_int64 * 5)()
@@ -203,6 +265,74 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+class _DevArray:
+    """A device buffer owned by the library, exposed through __cuda_array_interface__ so torch can wrap it without a copy."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def resident_grid(ctx=None):
+    """The grid the last host-pointer call left resident in the context, as a complex128 CUDA tensor VIEW (no copy): lets a
+    one-process-per-GPU caller all-reduce the per-process grids between skagrid_conv_imaging2 and the NULL-grid calls."""
+    ctx = ctx or context_for_current_device()
+    p, h, w = C.c_void_p(), C.c_int64(), C.c_int64()
+    ctx.check(ctx.lib.skagrid_resident_grid(ctx.h, C.byref(p), C.byref(h), C.byref(w)))
+    real = torch.as_tensor(_DevArray(p.value, (h.value, w.value, 2), "<f8"), device=torch.device("cuda", ctx.device))
+    return torch.view_as_complex(real)
+
+
+def _bounds_arg(bounds):
+    b = np.ascontiguousarray(bounds, dtype=np.int64)
+    return b, C.c_void_p(b.ctypes.data)
+
+
+def row_hist_(height, qpx, gh, v, hist, ctx=None):
+    """hist[row of the footprint centre of every visibility] += 1 (int32 [height]): input of the slab balance."""
+    ctx = ctx or context_for_current_device()
+    _chk(v, torch.float64, "v"); _chk(hist, torch.int32, "hist")
+    if hist.numel() != height:
+        raise ValueError("hist must have one entry per grid row")
+    ctx.check(ctx.lib.skagrid_dev_row_hist(ctx.h, int(height), int(qpx), int(gh), v.numel(), _p(v), _p(hist), _stream()))
+
+
+def route_count(height, qpx, gh, bounds, v, ctx=None):
+    """Records this device sends to every rank under the row-slab `bounds` (int32 CUDA tensor [nranks]; no host sync)."""
+    ctx = ctx or context_for_current_device()
+    _chk(v, torch.float64, "v")
+    b, bp = _bounds_arg(bounds)
+    counts = torch.empty(len(b) - 1, dtype=torch.int32, device=v.device)
+    ctx.check(ctx.lib.skagrid_dev_route_count(ctx.h, int(height), int(qpx), int(gh), len(b) - 1, bp, v.numel(), _p(v), _p(counts), _stream()))
+    return counts
+
+
+def route_pack(height, qpx, gh, bounds, u, v, wbin, vis, send_counts, keep_index=False, ctx=None):
+    """Destination-major send buffer [sum(send_counts), W] float64 (W = 5 with vis, 3 without) and, with keep_index, the
+    source index of every record (int32).  send_counts: host list from route_count."""
+    ctx = ctx or context_for_current_device()
+    _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(wbin, torch.int64, "wbin"); _chk(vis, torch.complex128, "vis")
+    b, bp = _bounds_arg(bounds)
+    seg = np.zeros(len(b) - 1, dtype=np.int64)
+    seg[1:] = np.cumsum(np.asarray(send_counts, dtype=np.int64))[:-1]
+    total = int(np.sum(send_counts))
+    w = 3 if vis is None else 5
+    send = torch.empty((total, w), dtype=torch.float64, device=u.device)
+    sidx = torch.empty(total, dtype=torch.int32, device=u.device) if keep_index else None
+    ctx.check(ctx.lib.skagrid_dev_route_pack(ctx.h, int(height), int(qpx), int(gh), len(b) - 1, bp, u.numel(), _p(u), _p(v), _p(wbin), _p(vis),
+                                             C.c_void_p(seg.ctypes.data), _p(send), _p(sidx), _stream()))
+    return send, sidx
+
+
+def scatter_add_(out, sidx, back, ctx=None):
+    """out[sidx[i]] += back[i] (complex128): the degridding partial sums returned by the slab owners."""
+    ctx = ctx or context_for_current_device()
+    _chk(out, torch.complex128, "out"); _chk(sidx, torch.int32, "sidx"); _chk(back, torch.complex128, "back")
+    if sidx.numel() != back.numel():
+        raise ValueError("one index per returned value")
+    ctx.check(ctx.lib.skagrid_dev_scatter_add(ctx.h, sidx.numel(), _p(sidx), _p(back), _p(out), _stream()))
+    return out
 
 
 def grid_to_image(grid, want_image=True, ctx=None):

@@ -121,12 +121,12 @@ def allreduce_grid(grid: torch.Tensor, group=None, dst: int | None = None):
     return grid
 
 
-def rows_to_columns(block: torch.Tensor, rows: Sequence[int], n: int, group=None):
+def rows_to_columns(block: torch.Tensor, rows: Sequence[int], n: int, group=None, spans=None):
     """Transpose of the ownership of an n x n array across ranks: in, this rank holds rows [rows[0], rows[1]) as
     [rows[1]-rows[0], n] (the row intervals of the ranks are disjoint and increasing with the rank; rows held by nobody
     are zero); out, rank h holds columns [n*h/P, n*(h+1)/P) of every row as [n, cols].  One all-to-all: the block
     (my rows) x (columns of rank h) goes to rank h, which places the blocks at their rows.  Backend-agnostic (complex
-    tensors travel as pairs of reals).  Returns (columns, (c0, c1))."""
+    tensors travel as pairs of reals).  spans: the (a, b) of every rank when the caller knows them.  Returns (columns, (c0, c1))."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     a, b = int(rows[0]), int(rows[1])
@@ -140,10 +140,11 @@ def rows_to_columns(block: torch.Tensor, rows: Sequence[int], n: int, group=None
         cols = torch.zeros((n, n), dtype=block.dtype, device=block.device)
         cols[a:b] = block
         return cols, (c0, c1)
-    mine = torch.tensor([a, b], dtype=torch.int64, device=block.device)
-    every = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(every, mine, group=group)
-    spans = [(int(t[0].item()), int(t[1].item())) for t in every]
+    if spans is None:  # every rank's (a, b); callers that know them (regular slabs) pass them and save the exchange + host sync
+        mine = torch.tensor([a, b], dtype=torch.int64, device=block.device)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine, group=group)
+        spans = [(int(t[0].item()), int(t[1].item())) for t in every]
     send = torch.cat([block[:, cb[h]:cb[h + 1]].reshape(-1) for h in range(world)])
     in_splits = [(b - a) * (cb[h + 1] - cb[h]) for h in range(world)]
     out_splits = [(hi - lo) * (c1 - c0) for lo, hi in spans]
@@ -160,30 +161,39 @@ def rows_to_columns(block: torch.Tensor, rows: Sequence[int], n: int, group=None
     return cols, (c0, c1)
 
 
-def slab_grid_to_image(slab: torch.Tensor, bounds: Sequence[int], group=None, want_image=True, nonzero=None):
+def slab_grid_to_image(slab: torch.Tensor, bounds: Sequence[int], group=None, want_image=True, nonzero=None, spans=None, sync_max=True):
     """Grid -> image (make_grid_hermitian, centred ifft, real, maximum: src/ImageDataset.hs:74-77) for an n x n grid held as
     row slabs, rank g owning rows [bounds[g], bounds[g+1]) -- the layout uv-tile-sharded gridding produces -- WITHOUT
     gathering the grid: row transforms on the owners, one all-to-all transpose, column transforms on the column owners.
     `slab` ([rows, n] complex128) is transformed in place.  nonzero = (lo, hi): only rows [lo, hi) of this rank's slab
     can be non-zero (e.g. TileShardedGridder.nonzero_rows(): mirrored uv coverage leaves half of the grid empty), the
-    others are neither transformed nor sent.  Returns (image columns [n, c1-c0] float64 or None, (c0, c1), maximum over
-    the whole image as a float)."""
+    others are neither transformed nor sent.  spans: instead of `bounds` + `nonzero`, the rows [a, b) every rank holds
+    (list of world pairs; rows held by nobody are zero; `slab` is then [b-a, n] of this rank's pair and bounds = n) -- the
+    layout the visibility-sharded reduce-scatter produces.  Returns (image columns [n, c1-c0] float64 or None, (c0, c1), maximum over
+    the whole image as a float -- or, with sync_max=False, as a 1-element CUDA tensor without synchronising the host)."""
     from . import device as dv
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    n = int(bounds[-1])
-    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
-    if tuple(slab.shape) != (r1 - r0, n):
-        raise ValueError("slab must be [bounds[rank+1]-bounds[rank], n]")
-    lo, hi = (r0, r1) if nonzero is None else (max(r0, int(nonzero[0])), min(r1, int(nonzero[1])))
-    hi = max(hi, lo)
-    block = slab[lo - r0:hi - r0]
+    if spans is not None:
+        n = int(bounds)
+        lo, hi = (int(x) for x in spans[rank])
+        if tuple(slab.shape) != (hi - lo, n):
+            raise ValueError("slab must be [spans[rank][1]-spans[rank][0], n]")
+        block = slab
+    else:
+        n = int(bounds[-1])
+        r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
+        if tuple(slab.shape) != (r1 - r0, n):
+            raise ValueError("slab must be [bounds[rank+1]-bounds[rank], n]")
+        lo, hi = (r0, r1) if nonzero is None else (max(r0, int(nonzero[0])), min(r1, int(nonzero[1])))
+        hi = max(hi, lo)
+        block = slab[lo - r0:hi - r0]
     dv.slab_fft_rows_(n, lo, block)
-    cols, (c0, c1) = rows_to_columns(block, (lo, hi), n, group)
+    cols, (c0, c1) = rows_to_columns(block, (lo, hi), n, group, spans=spans)
     img, mx = dv.slab_fft_cols_(n, c0, cols, want_image=want_image)
     if world > 1:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    return img, (c0, c1), float(mx.item())
+    return img, (c0, c1), (float(mx.item()) if sync_max else mx)   # sync_max=False: the 1-element device tensor, no host sync
 
 
 def doweight_sharded_(theta, lam, u, v, vis, group=None):
@@ -191,7 +201,7 @@ def doweight_sharded_(theta, lam, u, v, vis, group=None):
     of a visibility is the number of visibilities of ALL ranks in its cell, so the per-rank cell counts are summed with
     one all-reduce of the n x n count grid (n = round(theta*lam)) between counting and dividing."""
     from . import device as dv
-    n = int(round(theta * lam))
+    n = dv.grid_side(theta, lam)
     hist = torch.zeros((n, n), dtype=torch.int32, device=u.device)
     dv.weight_count_(theta, lam, u, v, hist)
     if dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -200,19 +210,63 @@ def doweight_sharded_(theta, lam, u, v, vis, group=None):
     return vis
 
 
-class VisShardedGridder:
-    """Visibility-sharded gridding / degridding on CUDA tensors (config 4)."""
+def route_cuda(height, qpx, gh, bounds, u, v, wbin, vis=None, keep_index=False, group=None):
+    """The routing of the uv-tile-sharded mode on CUDA tensors, hand-written kernels + ONE packed all-to-all
+    (skagrid_dev_route_count / _route_pack, csrc/route.cu): per-destination counts -> exchange of the counts -> records of
+    W doubles {u, v, wbin, [re, im]} packed destination-major -> all-to-all.  One host synchronisation (NCCL needs the split
+    sizes on the host).  Returns (received records [n, W] float64, route); route = {"sidx", "in_splits", "out_splits"}."""
+    from . import device as dv
+    world = dist.get_world_size(group)
+    counts = dv.route_count(height, qpx, gh, bounds, v)
+    both = torch.empty(2 * world, dtype=torch.int32, device=v.device)
+    both[:world] = counts
+    dist.all_to_all_single(both[world:], counts, group=group)
+    host = both.tolist()
+    in_splits, out_splits = host[:world], host[world:]
+    send, sidx = dv.route_pack(height, qpx, gh, bounds, u, v, wbin, vis, in_splits, keep_index=keep_index)
+    recv = torch.empty((sum(out_splits), send.shape[1]), dtype=torch.float64, device=v.device)
+    dist.all_to_all_single(recv, send, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+    return recv, {"sidx": sidx, "in_splits": in_splits, "out_splits": out_splits}
 
-    def __init__(self, height, width, table, group=None):
+
+def return_cuda(partial: torch.Tensor, route, count: int, group=None):
+    """Inverse of route_cuda for per-record complex results: all-to-all back, then out[sidx[i]] += back[i] (hand-written
+    scatter-add; a footprint straddling slabs has one partial sum per owner)."""
+    from . import device as dv
+    back = torch.empty(sum(route["in_splits"]), dtype=torch.complex128, device=partial.device)
+    dist.all_to_all_single(torch.view_as_real(back), torch.view_as_real(partial), output_split_sizes=route["in_splits"],
+                           input_split_sizes=route["out_splits"], group=group)
+    out = torch.zeros(count, dtype=torch.complex128, device=partial.device)
+    return dv.scatter_add_(out, route["sidx"], back)
+
+
+class VisShardedGridder:
+    """Visibility-sharded gridding / degridding on CUDA tensors (config 4).
+
+    Two forms of the reduction:
+      * `grid`: full local grid + one all-reduce (every rank ends with the sum);
+      * `grid_slabs` / `gather_slabs`: reduce-scatter into equal row slabs of the ACTIVE rows -- the rows any footprint of the
+        data set can touch, fixed by `set_active_rows` (mirrored uv coverage, v >= 0, leaves the lower half of the grid
+        empty) -- which feeds the slab-distributed grid -> image (`slab_grid_to_image(spans=...)`); the all-gather of the
+        reduced slabs (for degridding, every rank needs the grid) can then overlap the image stage.  Half the bytes of the
+        all-reduce on each leg, and no replicated FFT."""
+
+    def __init__(self, height, width, table, group=None, check=True):
         self.h, self.w, self.table, self.group = height, width, table, group
         self.plan = None
+        self.check = check
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.active = None
 
     def _plan(self, u, v, wbin, vis):
         from . import device as dv
-        if self.plan is None or self.plan.count < u.numel():
+        if self.plan is None or self.plan.capacity < u.numel():
+            if self.plan is not None:
+                self.plan.close()
             self.plan = dv.Plan(self.h, self.w, self.table.shape, u, v, wbin, vis)
         else:
-            self.plan.update(u, v, wbin, vis)
+            self.plan.update(u, v, wbin, vis, check=self.check)
         return self.plan
 
     def grid(self, u, v, wbin, vis, out=None, dst=None):
@@ -220,22 +274,85 @@ class VisShardedGridder:
         if out is None:
             out = torch.zeros((self.h, self.w), dtype=torch.complex128, device=u.device)
         self._plan(u, v, wbin, vis).grid(self.table, out)
-        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if dist.is_initialized() and self.world > 1:
             allreduce_grid(out, self.group, dst)
         return out
 
-    def degrid(self, grid, u, v, wbin):
-        """Every rank holds the full (model) grid; each degrids its own visibilities."""
-        return self._plan(u, v, wbin, None).degrid(self.table, grid)
+    def set_active_rows(self, v):
+        """Collective, once per data set (the uv coverage of an observation is known up front): the grid rows any footprint
+        can touch, widened to a multiple of the world size.  Returns (lo, rows per rank)."""
+        from . import device as dv
+        gh, qpx = self.table.shape[-2], self.table.shape[-3]
+        if v.numel() > 0:
+            y, _ = dv.frac_coord(self.h, qpx, v)
+            ext = torch.stack([y.min() - gh // 2, -(y.max() - gh // 2 + gh)])
+        else:
+            ext = torch.tensor([self.h, 0], dtype=torch.int64, device=v.device)
+        if dist.is_initialized() and self.world > 1:
+            dist.all_reduce(ext, op=dist.ReduceOp.MIN, group=self.group)
+        lo, hi = int(ext[0].item()), -int(ext[1].item())
+        self.active = active_row_slabs(self.h, lo, hi, self.world)
+        return self.active
+
+    def spans(self):
+        lo, m = self.active
+        return [(lo + r * m, lo + (r + 1) * m) for r in range(self.world)]
+
+    def grid_slabs(self, u, v, wbin, vis, work, slab):
+        """Grids into `work` (full [h, w] grid, zeroed here where needed) and reduce-scatters the active rows: on return
+        `slab` ([rows per rank, w]) holds this rank's rows spans()[rank] of the SUM over ranks."""
+        lo, m = self.active
+        work[lo:lo + m * self.world].zero_()
+        self._plan(u, v, wbin, vis).grid(self.table, work)
+        act = work[lo:lo + m * self.world]
+        if self.world > 1:
+            dist.reduce_scatter_tensor(torch.view_as_real(slab), torch.view_as_real(act), group=self.group)
+        else:
+            slab.copy_(act)
+        return slab
+
+    def gather_slabs(self, slab, work, async_op=False):
+        """All-gather of the reduced slabs into the active rows of `work`; the other rows of a gridded sum are zero, and are
+        zeroed here.  Returns the work handle when async_op (wait() before reading `work`)."""
+        lo, m = self.active
+        work[:lo].zero_()
+        work[lo + m * self.world:].zero_()
+        act = work[lo:lo + m * self.world]
+        if self.world > 1:
+            return dist.all_gather_into_tensor(torch.view_as_real(act), torch.view_as_real(slab), group=self.group, async_op=async_op)
+        act.copy_(slab)
+        return None
+
+    def degrid(self, grid, u=None, v=None, wbin=None, out=None):
+        """Every rank holds the full (model) grid; each degrids its own visibilities.  u = None: at the coordinates of the
+        last grid / degrid call (the plan is reused as it is)."""
+        plan = self.plan if u is None else self._plan(u, v, wbin, None)
+        return plan.degrid(self.table, grid, out)
+
+
+def active_row_slabs(height: int, lo: int, hi: int, world: int):
+    """Rows [lo, hi) clamped to the grid and widened to `world` equal slabs inside it: (first row, rows per rank)."""
+    lo, hi = max(0, min(lo, height)), max(0, min(hi, height))
+    if hi <= lo:
+        lo, hi = 0, min(height, world)
+    m = -(-(hi - lo) // world)
+    if m * world > height:
+        raise ValueError("grid has fewer rows than ranks")
+    lo = min(lo, height - m * world)
+    return lo, m
 
 
 class TileShardedGridder:
     """uv-tile-sharded gridding on CUDA tensors (config 5): this rank owns rows [bounds[rank], bounds[rank+1])."""
 
-    def __init__(self, height, width, table, group=None):
+    def __init__(self, height, width, table, group=None, check=True):
         self.h, self.w, self.table, self.group = height, width, table, group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.check = check
+        self._plan = None
+        self._route = None
+        self._count = 0
         self.set_bounds(slab_bounds(height, self.world))
 
     def set_bounds(self, bounds):
@@ -245,64 +362,76 @@ class TileShardedGridder:
     def balance(self, v):
         """Choose the slab bounds from this data set's uv coverage (collective): equal visibility counts per rank."""
         from . import device as dv
-        y, _ = dv.frac_coord(self.h, self.table.shape[-3], v)
-        hist = torch.bincount(torch.clamp(y, 0, self.h - 1), minlength=self.h)
+        hist = torch.zeros(self.h, dtype=torch.int32, device=v.device)
+        dv.row_hist_(self.h, self.table.shape[-3], self.table.shape[-2], v, hist)
         if self.world > 1:
             dist.all_reduce(hist, group=self.group)
         self.set_bounds(balanced_slab_bounds(hist, self.world))
         return self.bounds
 
-    def route(self, u, v, wbin, vis=None, return_route=False):
-        from . import device as dv
-        gh = self.table.shape[-2]
-        qpx = self.table.shape[-3]
-        payload = (u, v, wbin) if vis is None else (u, v, wbin, vis)
+    def route(self, u, v, wbin, vis=None, keep_index=False):
+        """Records [n, W] (W = 5 with vis, else 3) of every visibility whose footprint rows intersect this rank's slab, and
+        the route for sending per-record results back."""
+        gh, qpx = self.table.shape[-2], self.table.shape[-3]
         if self.world == 1:
-            return payload, (None if return_route else [u.numel()])
-        y, _ = dv.frac_coord(self.h, qpx, v)
-        return route_by_rows(y - gh // 2, gh, self.bounds, payload, self.group, return_route=return_route)
+            cols = [u, v, wbin.view(torch.float64)] + ([vis.real, vis.imag] if vis is not None else [])
+            return torch.stack(cols, dim=1).contiguous(), None
+        return route_cuda(self.h, qpx, gh, self.bounds, u, v, wbin, vis, keep_index, self.group)
 
-    def grid(self, u, v, wbin, vis, out=None):
-        """Routes, then grids into this rank's slab [rows, width] (no reduction)."""
+    def _fill(self, rec):
         from . import device as dv
-        (ru, rv, rwb, rvis), _ = self.route(u, v, wbin, vis)
-        self.last_routed = int(ru.numel())
-        self._last_rv = rv
+        plan = self._plan
+        if plan is None or plan.capacity < rec.shape[0] or plan.rows != self.rows:
+            if plan is not None:
+                plan.close()
+            self._plan = plan = dv.Plan.empty(self.h, self.w, self.table.shape, int(rec.shape[0] * 1.02) + 1024, rows=self.rows)
+        plan.update_packed(rec, check=self.check)
+        return plan
+
+    def grid(self, u, v, wbin, vis, out=None, keep_route=False):
+        """Routes, then grids into this rank's slab [rows, width] (no reduction).  keep_route: remember where the records came
+        from so that `degrid_routed` can send results back without routing again."""
+        rec, route = self.route(u, v, wbin, vis, keep_index=keep_route)
+        self.last_routed = int(rec.shape[0])
+        self._last_rec, self._route, self._count = rec, (route if keep_route else None), int(u.numel())
         if out is None:
             out = torch.zeros((self.rows[1] - self.rows[0], self.w), dtype=torch.complex128, device=u.device)
-        if ru.numel() > 0:
-            plan = getattr(self, "_plan", None)
-            if plan is None or plan.capacity < ru.numel() or plan.rows != self.rows:
-                if plan is not None:
-                    plan.close()
-                self._plan = plan = dv.Plan(self.h, self.w, self.table.shape, ru, rv, rwb, rvis, rows=self.rows)
-            else:
-                plan.update(ru, rv, rwb, rvis)
-            plan.grid(self.table, out)
+        if rec.shape[0] > 0:
+            self._fill(rec).grid(self.table, out)
         return out
 
     def nonzero_rows(self):
         """Rows of this rank's slab the last `grid` call (into a zeroed slab) can have touched: [lo, hi) in grid rows."""
         from . import device as dv
         r0, r1 = self.rows
-        rv = getattr(self, "_last_rv", None)
-        if rv is None or rv.numel() == 0:
+        rec = getattr(self, "_last_rec", None)
+        if rec is None or rec.shape[0] == 0:
             return (r0, r0)
         gh = self.table.shape[-2]
-        y, _ = dv.frac_coord(self.h, self.table.shape[-3], rv)
+        y, _ = dv.frac_coord(self.h, self.table.shape[-3], rec[:, 1].contiguous())
         lo, hi = int(y.min().item()) - gh // 2, int(y.max().item()) - gh // 2 + gh
         return (min(max(lo, r0), r1), min(max(hi, r0), r1))
+
+    def degrid_routed(self, slab):
+        """Adjoint of the last `grid(..., keep_route=True)` at the same coordinates: the plan of the routed records is reused,
+        every owner degrids the taps on its rows of `slab`, the partial sums travel back (one all-to-all) and are added per
+        source visibility."""
+        if self._plan is None or (self.world > 1 and self._route is None):
+            raise RuntimeError("degrid_routed needs a previous grid(..., keep_route=True)")
+        partial = torch.zeros(self.last_routed, dtype=torch.complex128, device=slab.device)
+        if self.last_routed > 0:
+            self._plan.degrid(self.table, slab, partial)
+        if self.world == 1:
+            return partial
+        return return_cuda(partial, self._route, self._count, self.group)
 
     def degrid(self, slab, u, v, wbin):
         """Adjoint of `grid`: `slab` holds this rank's rows of the (model) grid.  Coordinates are routed to the owners,
         every owner degrids the taps that fall on its rows, the partial sums travel back and are added per visibility."""
-        from . import device as dv
-        (ru, rv, rwb), route = self.route(u, v, wbin, return_route=True)
-        partial = torch.zeros(ru.numel(), dtype=torch.complex128, device=u.device)
-        if ru.numel() > 0:
-            plan = dv.Plan(self.h, self.w, self.table.shape, ru, rv, rwb, None, rows=self.rows)
-            plan.degrid(self.table, slab, partial)
-            plan.close()
+        rec, route = self.route(u, v, wbin, None, keep_index=True)
+        partial = torch.zeros(rec.shape[0], dtype=torch.complex128, device=u.device)
+        if rec.shape[0] > 0:
+            self._fill(rec).degrid(self.table, slab, partial)
         if route is None:
             return partial
-        return return_to_source(partial, route, u.numel(), self.group)
+        return return_cuda(partial, route, u.numel(), self.group)

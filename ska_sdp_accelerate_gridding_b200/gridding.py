@@ -16,6 +16,7 @@ from typing import Callable, Optional
 
 import numpy as np
 
+from . import _lib
 from .context import c128, f64, get_context, int64, ptr
 
 FRAC_RAW = 0
@@ -64,7 +65,8 @@ def _uvw(p):
 
 
 def _grid_side(theta, lam):
-    return int(np.floor(theta * float(lam) + 0.5)) if theta * lam >= 0 else -int(np.floor(-theta * float(lam) + 0.5))
+    """N = P.round (theta * lam) (src/Gridding.hs:466): half to even, the library's one definition."""
+    return int(_lib.load().skagrid_grid_side(float(theta), int(lam)))
 
 
 # ----------------------------------------------------------------------------------------------- binning

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import numpy as np
 
+from . import gridding as G
 from .context import c128, f64, get_context, int64, ptr
 
 
@@ -94,7 +95,7 @@ def aw_gridding_arrays(theta, lam, wkernels, wbins, akernels, uvw_m, a1, a2, fre
     a1, a2 = int64(a1)[:cnt].copy(), int64(a2)[:cnt].copy()
     wkernels, akernels, wbins = c128(wkernels), c128(akernels), f64(wbins)
     nw, qpx, _, s, _ = wkernels.shape
-    side = int(np.floor(theta * float(lam) + 0.5))
+    side = G._grid_side(theta, lam)
     if out_image is not None:
         if out_image.shape != (side, side) or out_image.dtype != np.float64 or not out_image.flags.c_contiguous:
             raise ValueError("out_image must be a C-contiguous float64 array of shape (%d, %d)" % (side, side))

@@ -39,10 +39,31 @@ def main():
     od = orc.convdegrid(gcf, full, u[first:first + m], v[first:first + m], wbin=wb[first:first + m])
     err_d = np.abs(d - od).max() / np.abs(od).max()
 
+    # reduce-scatter form: active rows only, slab-distributed grid -> image from the reduced slabs, all-gather for degridding
+    lo, m_rows = vs.set_active_rows(lv)
+    work = torch.full((n, n), 7.0 + 0j, dtype=torch.complex128, device="cuda")   # garbage: grid_slabs / gather_slabs must zero what they use
+    rslab = torch.empty((m_rows, n), dtype=torch.complex128, device="cuda")
+    vs.grid_slabs(lu, lv, lwb, lvis, work, rslab)
+    a, b = vs.spans()[rank]
+    err_v = max(err_v, np.abs(rslab.cpu().numpy() - full[a:b]).max() / peak)
+    img, (c0, c1), mx = D.slab_grid_to_image(rslab.clone(), n, spans=vs.spans())
+    oimg = np.real(orc.ifft(orc.make_grid_hermitian(full)))
+    err_v = max(err_v, np.abs(img.cpu().numpy() - oimg[:, c0:c1]).max() / np.abs(oimg).max(), abs(mx - oimg.max()) / abs(oimg.max()))
+    h = vs.gather_slabs(rslab, work, async_op=True)
+    if h is not None:
+        h.wait()
+    err_v = max(err_v, np.abs(work.cpu().numpy() - full).max() / peak)
+    d2 = vs.degrid(work).cpu().numpy()   # at the coordinates of the plan grid_slabs filled
+    err_d = max(err_d, np.abs(d2 - od).max() / np.abs(od).max())
+
     ts = D.TileShardedGridder(n, n, table)
-    slab = ts.grid(lu, lv, lwb, lvis).cpu().numpy()
+    slab_t = ts.grid(lu, lv, lwb, lvis, keep_route=True)
+    slab = slab_t.cpu().numpy()
     r0, r1 = ts.rows
     err_t = np.abs(slab - full[r0:r1]).max() / peak
+    # adjoint at the same coordinates, reusing the routed plan: partial sums return to the source ranks
+    dr = ts.degrid_routed(t(full[r0:r1].copy())).cpu().numpy()
+    err_t = max(err_t, np.abs(dr - od).max() / np.abs(od).max())
     ts.balance(lv)   # data-balanced slabs, then the adjoint with partial sums returned to the source ranks
     r0, r1 = ts.rows
     dt = ts.degrid(t(full[r0:r1]), lu, lv, lwb).cpu().numpy()
@@ -51,7 +72,6 @@ def main():
     err_t = max(err_t, np.abs(slab2 - full[r0:r1]).max() / peak, err_td)
     # grid -> image straight from the row slabs of the tile-sharded gridder (no gather): columns of the oracle's image
     img, (c0, c1), mx = D.slab_grid_to_image(t(full[r0:r1].copy()), ts.bounds)
-    oimg = np.real(orc.ifft(orc.make_grid_hermitian(full)))
     err_t = max(err_t, np.abs(img.cpu().numpy() - oimg[:, c0:c1]).max() / np.abs(oimg).max(), abs(mx - oimg.max()) / abs(oimg.max()))
     # the same from the slab the gridder just filled, skipping the rows it cannot have touched (v >= 0 only here: half the grid is empty)
     hu, hv = np.abs(u[first:first + m]) * 0.9, np.abs(v[first:first + m]) * 0.9

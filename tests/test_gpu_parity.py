@@ -390,6 +390,91 @@ def test_tile_sharded_single_rank_and_device_frac_coord(orc):
     assert rel_err(g, orc.convgrid(gcf, np.zeros((n, n), complex), u, v, vis, wbin=wb)) < TOL
     vs = D.VisShardedGridder(n, n, _t(gcf))
     assert rel_err(vs.grid(_t(u), _t(v), _t(wb), _t(vis)).cpu().numpy(), g) < TOL
+    # the single-rank forms of the round-2 paths: routed records (packed plan update), degrid at the routed plan, active-row
+    # slabs + slab grid -> image + gather
+    model = _rand_c(rng, (n, n))
+    ts.grid(_t(u), _t(v), _t(wb), _t(vis), keep_route=True)
+    od = orc.convdegrid(gcf, model, u, v, wbin=wb)
+    assert rel_err(ts.degrid_routed(_t(model)).cpu().numpy(), od) < TOL
+    assert rel_err(ts.degrid(_t(model), _t(u), _t(v), _t(wb)).cpu().numpy(), od) < TOL
+    hv = np.abs(v) * 0.8                      # mirrored coverage: the lower half of the grid stays empty
+    hg = orc.convgrid(gcf, np.zeros((n, n), complex), u, hv, vis, wbin=wb)
+    lo, m = vs.set_active_rows(_t(hv))
+    assert lo >= n // 2 - s // 2 - 1 and lo + m <= n
+    work = torch.full((n, n), 3.0 - 1j, dtype=torch.complex128, device="cuda")
+    slab = torch.empty((m, n), dtype=torch.complex128, device="cuda")
+    vs.grid_slabs(_t(u), _t(hv), _t(wb), _t(vis), work, slab)
+    assert rel_err(slab.cpu().numpy(), hg[lo:lo + m]) < TOL
+    img, (c0, c1), mx = D.slab_grid_to_image(slab.clone(), n, spans=vs.spans())
+    oimg = np.real(orc.ifft(orc.make_grid_hermitian(hg)))
+    assert (c0, c1) == (0, n) and rel_err(img.cpu().numpy(), oimg) < TOL and abs(mx - oimg.max()) < TOL * abs(oimg.max())
+    vs.gather_slabs(slab, work)
+    assert rel_err(work.cpu().numpy(), hg) < TOL
+    assert rel_err(vs.degrid(work).cpu().numpy(), orc.convdegrid(gcf, hg, u, hv, wbin=wb)) < TOL
+
+
+def test_route_kernels_against_torch_reference(orc):
+    """skagrid_dev_route_count / _route_pack / _row_hist / _scatter_add against the integer torch restatement
+    (distributed.owners_of_rows) on slabs that split footprints, and Plan.update must raise on a bad w-plane index."""
+    import torch
+    from ska_sdp_accelerate_gridding_b200 import _lib
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    from ska_sdp_accelerate_gridding_b200 import distributed as D
+    rng = np.random.default_rng(43)
+    n, s, q, cnt = 512, 15, 8, 50000
+    u, v = rng.uniform(-0.55, 0.55, cnt), rng.uniform(-0.55, 0.55, cnt)
+    v[:5] = [np.nan, np.inf, -np.inf, 3e9, -0.5]
+    wb = rng.integers(0, 4, cnt)
+    vis = _rand_c(rng, cnt)
+    bounds = [0, 100, 107, 300, 512]            # a slab shorter than the kernel: footprints reach three owners
+    y, _ = orc.frac_coord(n, q, np.where(np.isfinite(v) & (np.abs(v) < 1e9), v, 10.0))
+    lo, hi, on = D.owners_of_rows(torch.from_numpy(y - s // 2), s, bounds)
+    want = [int((on & (lo <= g) & (hi >= g)).sum()) for g in range(4)]
+    counts = dv.route_count(n, q, s, bounds, _t(v)).tolist()
+    assert counts == want
+    send, sidx = dv.route_pack(n, q, s, bounds, _t(u), _t(v), _t(wb), _t(vis), counts, keep_index=True)
+    send, sidx = send.cpu().numpy(), sidx.cpu().numpy()
+    off = 0
+    for g in range(4):
+        sel = np.nonzero((on & (lo <= g) & (hi >= g)).numpy())[0]
+        seg_idx = sidx[off:off + counts[g]]
+        assert np.array_equal(np.sort(seg_idx), sel)              # the right visibilities, each once
+        seg = send[off:off + counts[g]]
+        assert np.array_equal(seg[:, 0], u[seg_idx]) and np.array_equal(seg[:, 1], v[seg_idx])
+        assert np.array_equal(seg[:, 2].view(np.int64), wb[seg_idx])
+        assert np.array_equal(seg[:, 3] + 1j * seg[:, 4], vis[seg_idx])
+        off += counts[g]
+    send3, _ = dv.route_pack(n, q, s, bounds, _t(u), _t(v), _t(wb), None, counts)
+    assert tuple(send3.shape) == (sum(counts), 3)
+    hist = torch.zeros(n, dtype=torch.int32, device="cuda")
+    dv.row_hist_(n, q, s, _t(v), hist)
+    oh = np.bincount(np.clip(y[(on).numpy()], 0, n - 1), minlength=n)
+    assert np.array_equal(hist.cpu().numpy(), oh)
+    out = torch.zeros(cnt, dtype=torch.complex128, device="cuda")
+    back = _rand_c(rng, sum(counts))
+    dv.scatter_add_(out, _t(sidx), _t(back))
+    ref = np.zeros(cnt, complex)
+    np.add.at(ref, sidx, back)
+    assert rel_err(out.cpu().numpy(), ref) < 1e-15
+    # a plan filled from the packed records grids what the SoA plan grids
+    gcf = _rand_c(rng, (4, q, q, s, s))
+    ok = np.isfinite(v) & (np.abs(v) < 1e9)
+    rec = np.stack([u[ok], v[ok], wb[ok].view(np.float64), vis[ok].real, vis[ok].imag], axis=1)
+    plan = dv.Plan.empty(n, n, gcf.shape, rec.shape[0] + 10)
+    plan.update_packed(_t(rec))
+    g = torch.zeros((n, n), dtype=torch.complex128, device="cuda")
+    plan.grid(_t(gcf), g)
+    assert rel_err(g.cpu().numpy(), orc.convgrid(gcf, np.zeros((n, n), complex), u[ok], v[ok], vis[ok], wbin=wb[ok])) < TOL
+    # ADVICE r1: update() with an out-of-range w-plane index must raise like the constructor does
+    bad = wb[ok].copy()
+    bad[7] = 4
+    p2 = dv.Plan(n, n, gcf.shape, _t(u[ok]), _t(v[ok]), _t(wb[ok]), _t(vis[ok]))
+    with pytest.raises(_lib.SkagridError):
+        p2.update(_t(u[ok]), _t(v[ok]), _t(bad), _t(vis[ok]))
+    p2.update(_t(u[ok]), _t(v[ok]), _t(bad), _t(vis[ok]), check=False)   # deferred: the word stays set until somebody looks
+    with pytest.raises(_lib.SkagridError):
+        p2.check()
+    p2.update(_t(u[ok]), _t(v[ok]), _t(wb[ok]), _t(vis[ok]))
 
 
 def test_two_gpu_torchrun_if_available():
