@@ -77,7 +77,9 @@ def parse():
     ap.add_argument("--c5-vis", type=float, default=1.25e8, help="config 5: visibilities per GPU per step (1e9 / 8)")
     ap.add_argument("--c5-grid", type=int, default=32768)
     ap.add_argument("--allreduce", action="store_true", help="N > 1: full-grid all-reduce + replicated grid -> image (the round-1 step) instead of reduce-scatter + slabs")
-    ap.add_argument("--one-group", action="store_true", help="N > 1: the image all-to-all shares the NCCL communicator of the all-gather (no overlap between them)")
+    ap.add_argument("--one-group", action="store_true", help="N > 1, --nccl: the image all-to-all shares the NCCL communicator of the all-gather (no overlap between them)")
+    ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL collectives (reduce-scatter, all-gather, all-to-all) for the exchange steps instead of the "
+                                                        "library's own peer-memory kernels and copy-engine pulls over NVLink (csrc/ipc.cu)")
     args = ap.parse_args()
     N_GRID, SUPPORT, NW = args.grid, args.support, args.nw
     args.skip = set(x for x in args.skip.split(",") if x)
@@ -197,11 +199,15 @@ class Env:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         self.img_group = None
+        self.pg = None
         if self.world > 1:
             dist.init_process_group("nccl", device_id=self.dev)
-            if not args.one_group:
+            if args.nccl and not args.one_group and not args.allreduce:
                 self.img_group = dist.new_group()   # second communicator: the image transpose overlaps the all-gather
         self.ctx = get_context(self.local)
+        if self.world > 1 and not args.nccl and not args.allreduce:
+            from ska_sdp_accelerate_gridding_b200.peer import PeerGroup
+            self.pg = PeerGroup()
 
     def ev(self):
         return self.torch.cuda.Event(enable_timing=True)
@@ -260,24 +266,41 @@ class Config4Step:
         self.env, self.table, self.V, self.variant, self.allreduce = env, table, V, variant, allreduce
         self.dv, self.D = dv, D
         self.u, self.v, self.wb, self.vis = dv.synth_vis(SEED, first, V, N_GRID, SUPPORT, NW, uniform=uniform)
-        self.grid = torch.zeros((N_GRID, N_GRID), dtype=torch.complex128, device=env.dev)
         self.vis_out = torch.empty(V, dtype=torch.complex128, device=env.dev)
         self.vs = D.VisShardedGridder(N_GRID, N_GRID, table, check=False)
-        self.vs.plan = dv.Plan(N_GRID, N_GRID, table.shape, self.u, self.v, self.wb, self.vis)
-        self.plan = self.vs.plan
         self.slabbed = env.world > 1 and not allreduce
-        if self.slabbed:
-            lo, m = self.vs.set_active_rows(self.v)
-            self.slab = torch.empty((m, N_GRID), dtype=torch.complex128, device=env.dev)
-            self.islab = torch.empty_like(self.slab)
-            self.spans = self.vs.spans()
+        self.peer = self.slabbed and env.pg is not None
+        self.pislab = None
+        # the rows any footprint of the data set can touch (collective, once per data set: mirrored coverage, v >= 0, leaves the
+        # lower half of the grid empty): the plan's bucket table covers only those, and only those are reduced / gathered
+        lo, m = self.vs.set_active_rows(self.v)
+        self.rows = (lo, lo + m * env.world)
+        self.spans = self.vs.spans()
+        self.vs.plan = dv.Plan(N_GRID, N_GRID, table.shape, self.u, self.v, self.wb, self.vis, rows=self.rows)
+        self.plan = self.vs.plan
+        if self.peer:
+            from ska_sdp_accelerate_gridding_b200.peer import PeerBuffer
+            self.grid = self.vs.enable_peer(env.pg)            # the local grid lives in peer-visible memory
+            self.pislab = PeerBuffer(env.pg, m * N_GRID * 16)   # this rank's reduced slab, transformed in place by the image stage
+            self.islab = self.pislab.tensor(torch.complex128, (m, N_GRID))
+            self.slab = self.grid[lo + env.rank * m:lo + (env.rank + 1) * m]
+        else:
+            self.grid = torch.zeros((N_GRID, N_GRID), dtype=torch.complex128, device=env.dev)
+            if self.slabbed:
+                self.slab = torch.empty((m, N_GRID), dtype=torch.complex128, device=env.dev)
+                self.islab = torch.empty_like(self.slab)
+        self.act = self.grid[self.rows[0]:self.rows[1]]        # what the plan's gridder / degridder see
         self.image_max = None
 
     def close(self):
         self.plan.close()
-        for k in ("u", "v", "wb", "vis", "grid", "vis_out", "slab", "islab"):
+        for k in ("u", "v", "wb", "vis", "grid", "act", "vis_out", "slab", "islab"):
             if hasattr(self, k):
                 delattr(self, k)
+        if self.peer:
+            self.vs.work = None
+            self.pislab.close()
+            self.vs.pgrid.close()
         self.env.torch.cuda.empty_cache()
 
     def step(self, e=None):
@@ -289,7 +312,7 @@ class Config4Step:
             self.plan.update(self.u, self.v, self.wb, self.vis, check=False)   # bit-exact binning + bucket sort (part of gridding)
             rec(1)
             self.grid.zero_()
-            self.plan.grid(self.table, self.grid, variant=self.variant)
+            self.plan.grid(self.table, self.act, variant=self.variant)
             rec(2)
             if env.world > 1:
                 env.dist.all_reduce(env.torch.view_as_real(self.grid))
@@ -297,7 +320,7 @@ class Config4Step:
             _, mx = dv.grid_to_image(self.grid, want_image=False)   # in place: the buffer now holds the transformed plane
             self.image_max = mx
             rec(4)
-            self.plan.degrid(self.table, self.grid, self.vis_out)    # adjoint pass over the same batch; the transformed plane stands in for the model grid
+            self.plan.degrid(self.table, self.act, self.vis_out)    # adjoint pass over the same batch; the transformed plane stands in for the model grid
             rec(5)
             return
         vs = self.vs
@@ -305,8 +328,27 @@ class Config4Step:
         act = self.grid[lo:lo + m * env.world]
         self.plan.update(self.u, self.v, self.wb, self.vis, check=False)
         rec(1)
+        if self.peer:
+            pg = env.pg
+            pg.barrier()                                   # every peer has pulled the previous step's slabs out of this grid
+            act.zero_()
+            self.plan.grid(self.table, self.act, variant=self.variant)
+            rec(2)
+            pg.barrier()                                   # all local grids complete
+            pg.peer_sum_(vs.pgrid, vs._slab_off(env.rank), m * N_GRID)   # reduce-scatter: ONE kernel reads this rank's slab of every peer's grid over NVLink
+            pg.barrier()                                   # all slabs reduced
+            rec(3)
+            self.islab.copy_(self.slab)
+            h = vs.gather_slabs_peer(join=False)           # all-gather by the copy engines, overlapping the image stage
+            _, _, mx = D.peer_slab_grid_to_image(pg, self.pislab, [a for a, _ in self.spans], self.spans, N_GRID, want_image=False, sync_max=False)
+            self.image_max = mx
+            h.wait()
+            rec(4)
+            self.plan.degrid(self.table, self.act, self.vis_out)
+            rec(5)
+            return
         act.zero_()                                        # the other rows are never written: they stay zero
-        self.plan.grid(self.table, self.grid, variant=self.variant)
+        self.plan.grid(self.table, self.act, variant=self.variant)
         rec(2)
         env.dist.reduce_scatter_tensor(env.torch.view_as_real(self.slab), env.torch.view_as_real(act))
         rec(3)
@@ -318,7 +360,7 @@ class Config4Step:
         self.image_max = mx
         h.wait()
         rec(4)
-        self.plan.degrid(self.table, self.grid, self.vis_out)
+        self.plan.degrid(self.table, self.act, self.vis_out)
         rec(5)
 
     def stage_times(self, reps=3):
@@ -352,13 +394,20 @@ def parity_config4(env, table, c4, cpu_sample):
     ksum = table.sum(dim=(-1, -2)).reshape(-1)
     expect = env.sum_over_ranks(complex((c4.vis * ksum[(c4.wb * q + yf) * q + xf]).sum().item()))[0].item()
     c4.plan.update(c4.u, c4.v, c4.wb, c4.vis, check=True)   # check=True: raises on any out-of-range index of the full batch
+    if c4.peer:
+        env.pg.barrier()
     c4.grid.zero_()
-    c4.plan.grid(table, c4.grid, variant=c4.variant)
+    c4.plan.grid(table, c4.act, variant=c4.variant)
     if world > 1:
         if c4.slabbed:
             lo, m = c4.vs.active
             act = c4.grid[lo:lo + m * world]
-            dist.reduce_scatter_tensor(torch.view_as_real(c4.slab), torch.view_as_real(act))
+            if c4.peer:
+                env.pg.barrier()
+                env.pg.peer_sum_(c4.vs.pgrid, c4.vs._slab_off(rank), m * N_GRID)
+                env.pg.barrier()
+            else:
+                dist.reduce_scatter_tensor(torch.view_as_real(c4.slab), torch.view_as_real(act))
             got = env.sum_over_ranks(complex(c4.slab.sum().item()))[0].item()
             peak = env.max_over_ranks(c4.slab.abs().max().item())
         else:
@@ -412,9 +461,15 @@ def run_config5(env, args):
     u, v, wb, vis = dv.synth_vis(SEED + 5, rank * V, V, N5, S5, NW5)
     ts = D.TileShardedGridder(N5, N5, table, check=False)
     bounds = ts.balance(v)   # once per data set: slabs with equal visibility counts (the uv coverage is known up front)
-    slab = torch.zeros((ts.rows[1] - ts.rows[0], N5), dtype=torch.complex128, device=env.dev)
-    ts.grid(u, v, wb, vis, out=slab, keep_route=True)
+    peer = env.pg is not None
+    if peer:
+        slab = ts.enable_peer(env.pg, send_capacity=int(V * 1.15) + 4096, recv_capacity=int(V * 1.3) + 4096)
+        ts.grid_peer(u, v, wb, vis)
+    else:
+        slab = torch.zeros((ts.rows[1] - ts.rows[0], N5), dtype=torch.complex128, device=env.dev)
+        ts.grid(u, v, wb, vis, out=slab, keep_route=True)
     nz = ts.nonzero_rows()   # rows of the slab the gridder can touch (v >= 0 after mirroring: the lower half stays empty); static
+    anz = ts.all_nonzero_rows()
     routed = int(env.sum_over_ranks(float(ts.last_routed))[0].item())
     ts._plan.check()
     # ---- parity: checksum of the slabs and the adjoint identity <grid(v), g> = <v, degrid(g)> with g = the gridded slabs
@@ -426,11 +481,11 @@ def run_config5(env, args):
     got = env.sum_over_ranks(complex(slab.sum().item()))[0].item()
     peak = env.max_over_ranks(slab.abs().max().item())
     lhs = env.sum_over_ranks(float((slab.real ** 2 + slab.imag ** 2).sum().item()))[0].item()
-    d = ts.degrid_routed(slab)
+    d = ts.degrid_routed_peer() if peer else ts.degrid_routed(slab)
     rhs = env.sum_over_ranks(complex((d.conj() * vis).sum().item()))[0].item()
     parity = {"checksum_rel_err": abs(got - expect) / max(abs(expect), peak), "adjoint_rel_err": abs(lhs - rhs) / abs(lhs), "grid_peak": peak,
               "note": "sum(slabs) vs sum_k vis_k * sum(table[slice_k]); <grid(v), g> vs <v, degrid(g)> with g = the gridded slabs "
-                      "(degrid through the routed plan and the return all-to-all)"}
+                      "(degrid through the routed plan and the return exchange)"}
     del d, xf, yf
     stage_names = ("route", "plan+grid", "image", "degrid", "return")
     marks = {}
@@ -438,21 +493,30 @@ def run_config5(env, args):
     def step(e=None):
         rec = (lambda i: e[i].record()) if e is not None else (lambda i: None)
         rec(0)
-        recs, route = ts.route(u, v, wb, vis, keep_index=True)   # owners -> counts -> pack -> all-to-all
+        if peer:   # counts -> count table (NCCL all-gather of P ints) -> pack -> barrier -> copy-engine pulls over NVLink
+            recs, route = ts.route_peer(u, v, wb, vis, keep_index=True)
+        else:      # counts -> pack -> one NCCL all-to-all
+            recs, route = ts.route(u, v, wb, vis, keep_index=True)
         rec(1)
         slab.zero_()
         ts.last_routed, ts._last_rec, ts._route, ts._count = int(recs.shape[0]), recs, route, int(u.numel())
         if recs.shape[0] > 0:
             ts._fill(recs).grid(table, slab)
         rec(2)
-        _, _, mx = D.slab_grid_to_image(slab, bounds, want_image=False, nonzero=nz, sync_max=False)   # in place: slab -> transformed rows
+        if peer:
+            _, _, mx = ts.image_peer(anz, want_image=False, sync_max=False)
+        else:
+            _, _, mx = D.slab_grid_to_image(slab, bounds, want_image=False, nonzero=nz, sync_max=False)   # in place: slab -> transformed rows
         marks["max"] = mx
         rec(3)
-        partial = torch.zeros(ts.last_routed, dtype=torch.complex128, device=env.dev)
+        partial = ts.partial_view(max(ts.last_routed, 1))[:ts.last_routed] if peer else torch.zeros(ts.last_routed, dtype=torch.complex128, device=env.dev)
         if ts.last_routed > 0:
             ts._plan.degrid(table, slab, partial)                 # the transformed plane stands in for the model grid
         rec(4)
-        marks["vis"] = partial if route is None else D.return_cuda(partial, route, int(u.numel()))
+        if peer:
+            marks["vis"] = ts.return_peer(int(u.numel()), route)
+        else:
+            marks["vis"] = partial if route is None else D.return_cuda(partial, route, int(u.numel()))
         rec(5)
 
     k = max(2, min(args.steps, 4))
@@ -465,10 +529,18 @@ def run_config5(env, args):
         for i, s in enumerate(stage_names):
             acc[s].append(e[i].elapsed_time(e[i + 1]))
     stages = {s: env.max_over_ranks(float(np.mean(x))) for s, x in acc.items()}
+    # where the exchange stages spend their time (one traced step: events at the sub-stage boundaries inside distributed.py)
+    D.TRACE = []
+    step()
+    torch.cuda.synchronize()
+    tr, D.TRACE = D.TRACE, None
+    sub = {}
+    for (la, ea), (lb, eb) in zip(tr, tr[1:]):
+        sub[f"{la} -> {lb}"] = env.max_over_ranks(ea.elapsed_time(eb))
     kern = stages["plan+grid"]
     out = {
         "metric": "visibilities/sec gridded+degridded (uv-tile-sharded)", "value": world * V / (ms * 1e-3), "unit": "vis/s", "n_gpus": world,
-        "steps": k, "ms_per_step": ms, "scaling": "weak", "stages_ms": stages,
+        "steps": k, "ms_per_step": ms, "scaling": "weak", "stages_ms": stages, "substages_ms": sub,
         "config": {"workload": f"config 5: {N5}^2 c128 grid, support {S5}, oversampling {QPX}, {NW5} w-planes, uv-tile-sharded (row slabs balanced by "
                                "the row histogram, routing by hand-written count/pack kernels + one all-to-all, no grid reduce)",
                    "vis_per_gpu_per_step": V, "vis_total_per_step": V * world, "routed_records": routed, "slab_bounds": bounds,
@@ -480,8 +552,14 @@ def run_config5(env, args):
                   "fp64_tflops_per_gpu_plan_plus_grid": flop_per_vis(S5) * (routed / world) / (kern * 1e-3) / 1e12},
         "gpu_launches": launches, "parity": parity,
     }
+    out["config"]["exchange"] = "none" if world == 1 else ("peer memory over NVLink (copy-engine pulls of routed records, partial sums and the image transpose)" if peer else "nccl all-to-all")
     ts._plan.close()
-    del slab, u, v, wb, vis, ts
+    if peer:
+        del slab
+        ts.slab = None
+        for b in (ts.psend, ts.ppart, ts.pslab):
+            b.close()
+    del u, v, wb, vis, ts
     torch.cuda.empty_cache()
     return out
 
@@ -637,7 +715,9 @@ def main():
     # isolate the gridder kernel from the memset that shares its bracket
     ez = [env.ev() for _ in range(3)]
     c4.plan.update(c4.u, c4.v, c4.wb, c4.vis, check=False)
-    ez[0].record(); c4.grid.zero_(); ez[1].record(); c4.plan.grid(table, c4.grid, variant=args.variant); ez[2].record()
+    if c4.peer:
+        env.pg.barrier()
+    ez[0].record(); c4.grid.zero_(); ez[1].record(); c4.plan.grid(table, c4.act, variant=args.variant); ez[2].record()
     torch.cuda.synchronize()
     kern_ms = ez[1].elapsed_time(ez[2])
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -675,7 +755,10 @@ def main():
             "vis_per_gpu_per_step": V, "uv": "uniform" if args.uniform else "core-dominated mixture (SURVEY 8d)", "seed": SEED,
             "step": ("bin+bucket -> tiled gridder -> hermitian+IFFT+real/max -> degridder" if world == 1 else
                      ("bin+bucket -> tiled gridder -> NCCL all-reduce -> hermitian+IFFT+real/max (replicated) -> degridder" if args.allreduce else
-                      "bin+bucket -> tiled gridder -> NCCL reduce-scatter of the active rows -> [slab-distributed grid->image || NCCL all-gather] -> degridder")),
+                      ("bin+bucket -> tiled gridder -> NCCL reduce-scatter of the active rows -> [slab-distributed grid->image || NCCL all-gather] -> degridder" if args.nccl else
+                       "bin+bucket -> tiled gridder -> peer-memory reduce-scatter of the active rows (one kernel summing this rank's slab of every peer's grid over NVLink) "
+                       "-> [slab-distributed grid->image with a copy-engine transpose || copy-engine all-gather] -> degridder"))),
+            "exchange": ("none" if world == 1 else ("nccl" if (args.nccl or args.allreduce) else "peer memory over NVLink (CUDA IPC; csrc/ipc.cu): device barrier, peer-sum kernel, copy-engine pulls")),
             "l2": f"inputs ({V * 40 / 1e9:.1f} GB) and grid ({N_GRID * N_GRID * 16 / 1e9:.2f} GB) exceed the 126 MB L2; no explicit flush",
             "gridder_variant": args.variant, "plan": stats,
             "active_rows": (None if not c4.slabbed else {"first": c4.vs.active[0], "per_rank": c4.vs.active[1]}),

@@ -1,0 +1,10 @@
+#!/bin/bash
+# round-2 run D (8 GPUs): multi-rank parity and the full N=8 bench line with the NCCL-only exchange steps
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1"
+timeout 600 $TR --master-port 29511 tests/mgpu_check.py > gpurun_out/r2d_mgpu_check.log 2>&1
+echo "mgpu_check rc=$?" >> gpurun_out/r2d_mgpu_check.log
+timeout 900 $TR --master-port 29512 bench.py --gpus 8 --steps 5 --warmup 3 > gpurun_out/r2d_n8.json 2> gpurun_out/r2d_n8.err
+echo "bench rc=$?" >> gpurun_out/r2d_mgpu_check.log
+nvidia-smi topo -m > gpurun_out/r2d_topo.txt 2>&1
+tail -4 gpurun_out/r2d_mgpu_check.log; tail -3 gpurun_out/r2d_n8.err

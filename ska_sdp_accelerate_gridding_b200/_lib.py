@@ -71,6 +71,14 @@ _SIGS = {
     "skagrid_dev_route_count": [vp, i64, i64, i64, ip, vp, i64, vp, vp, vp],
     "skagrid_dev_route_pack": [vp, i64, i64, i64, ip, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp],
     "skagrid_dev_scatter_add": [vp, i64, vp, vp, vp, vp],
+    "skagrid_ipc_alloc": [vp, i64, C.POINTER(vp), vp],
+    "skagrid_ipc_free": [vp, vp],
+    "skagrid_ipc_open": [vp, vp, C.POINTER(vp)],
+    "skagrid_ipc_close": [vp, vp],
+    "skagrid_dev_peer_sum": [vp, ip, vp, vp, i64, vp],
+    "skagrid_dev_peer_barrier": [vp, ip, ip, vp, C.c_uint32, vp],
+    "skagrid_dev_peer_copy": [vp, vp, vp, i64, vp],
+    "skagrid_dev_peer_copy2d": [vp, vp, i64, vp, i64, i64, i64, vp],
     "skagrid_dev_plan_stats": [vp, vp, vp, C.POINTER(i64 * 5)],
     "skagrid_dev_grid": [vp, vp, vp, vp, ip, vp],
     "skagrid_dev_degrid": [vp, vp, vp, vp, vp, vp],

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libskagrid.so")
-SOURCES = ["ctx.cu", "plan.cu", "gridder.cu", "prep.cu", "awkern.cu", "image.cu", "synth.cu", "api.cu", "mgpu.cu", "route.cu"]
+SOURCES = ["ctx.cu", "plan.cu", "gridder.cu", "prep.cu", "awkern.cu", "image.cu", "synth.cu", "api.cu", "mgpu.cu", "route.cu", "ipc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", CSRC,

@@ -807,13 +807,14 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
     }
     SK_CUDA(ctx, cudaMemsetAsync(plan->d_counters + 1, 0, sizeof(uint32_t), st));
     const int MT = plan->g.MT;
-    if (plan->g.dense && variant != 2 && variant != 3 && variant != 4) {
+    if (plan->g.dense && variant != 2 && variant != 3 && variant != 4) {  // (6 is a dense variant)
         // dense layout (S = 14, 15, 29..31).  B200, r02 (profiles/r02_gridder_ab.md): R=16, 1e8 visibilities: 8x16 threads with two
         // residues each 21.3 ms (default), 4x16 threads with four residues 22.5 ms (variant 5), r01 predicated kernel 21.65 ms;
         // R=32 (S=31), 5e7 visibilities: 16x16 threads with four residues 42.8 ms (default), 32x16 threads with two 44.2 ms
         // (variant 5), r01 kernel 44.6 ms
         if (R == 16) {
             if (variant == 5) return MT == 2 ? launch_dense<16, 2, 4>(ctx, A, st) : launch_dense<16, 4, 4>(ctx, A, st);
+            if (variant == 6) return MT == 2 ? launch_dense<16, 2, 16>(ctx, A, st) : launch_dense<16, 4, 16>(ctx, A, st);  // 16x16 threads, one residue each
             return MT == 2 ? launch_dense<16, 2, 8>(ctx, A, st) : launch_dense<16, 4, 8>(ctx, A, st);
         }
         if (variant == 5) return MT == 2 ? launch_dense<32, 2, 32>(ctx, A, st) : launch_dense<32, 4, 32>(ctx, A, st);

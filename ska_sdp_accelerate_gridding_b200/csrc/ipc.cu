@@ -1,0 +1,160 @@
+// ipc.cu -- peer-memory exchange for the one-process-per-GPU multi-GPU modes: the data path over NVLink 5 / NVSwitch without
+// a collective library.  Every rank allocates its exchange buffers here (cudaMalloc), exports a CUDA IPC handle, the ranks
+// swap the 64-byte handles once (any transport: torch.distributed in the Python layer) and open each other's buffers; from
+// then on the kernels below dereference peer memory directly and the copy engines move slabs between devices.
+//
+//   peer_sum       own[i] += sum over peers of peer[i]   -- the reduce-scatter of the visibility-sharded mode (gridding is
+//                  linear in the visibilities, permute (+), src/Gridding.hs:377): rank r sums row slab r of every peer's grid
+//   peer_barrier   stream-ordered barrier between the ranks: a flag per (rank, peer) in peer memory, written with
+//                  st.release.sys, polled with ld.acquire.sys (bounded), so no host thread and no collective is involved
+//   peer_copy(2d)  cudaMemcpyAsync / cudaMemcpy2DAsync between an opened peer buffer and a local one (copy engines over
+//                  NVLink): all-gather of reduced slabs, routed records, returned partial sums, the image transpose
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+constexpr int IPC_MAX = 64;
+
+struct IpcPeers {
+    const double2 *p[IPC_MAX];
+    int n;
+};
+struct IpcFlags {
+    uint32_t *p[IPC_MAX];  // p[k]: rank k's flag array (IPC_MAX words), p[me] the local one
+    int n, me;
+};
+
+__global__ void __launch_bounds__(256) ipc_sum_kernel(double2 *own, IpcPeers peers, i64 n) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double2 v[IPC_MAX / 8];
+        double2 a = own[i];
+        // peer loads first (independent, all in flight over NVLink), then the sum
+        for (int k0 = 0; k0 < peers.n; k0 += IPC_MAX / 8) {
+#pragma unroll
+            for (int k = 0; k < IPC_MAX / 8; ++k)
+                if (k0 + k < peers.n) v[k] = __ldcv(peers.p[k0 + k] + i);
+#pragma unroll
+            for (int k = 0; k < IPC_MAX / 8; ++k)
+                if (k0 + k < peers.n) { a.x += v[k].x; a.y += v[k].y; }
+        }
+        own[i] = a;
+    }
+}
+
+// One block, one thread per peer.  Thread k tells rank k "rank `me` has reached epoch e" (release: everything this rank's
+// stream did before is visible system-wide first) and waits until rank k has said the same to us (acquire).
+__global__ void ipc_barrier_kernel(IpcFlags F, uint32_t epoch, uint32_t *err_flag) {
+    const int k = threadIdx.x;
+    if (k >= F.n || k == F.me) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(F.p[k] + F.me), "r"(epoch) : "memory");
+    const uint32_t *mine = F.p[F.me] + k;
+    uint32_t seen = 0;
+    for (long long spin = 0; spin < (1ll << 26); ++spin) {  // ~30 s
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(mine) : "memory");
+        if ((int32_t)(seen - epoch) >= 0) return;
+        __nanosleep(64);
+    }
+    atomicOr(err_flag, 4u);  // a peer never arrived (bit 2 of the context's error word): do not hang the device forever
+}
+
+extern "C" int skagrid_ipc_alloc(skagrid_ctx *ctx, int64_t bytes, void **d_ptr, unsigned char handle[64]) {
+    SK_TRY(sk_api_enter(ctx));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (!d_ptr || !handle || bytes <= 0) return sk_fail(ctx, SKAGRID_EINVAL, "ipc_alloc: bad argument");
+    *d_ptr = nullptr;
+    void *p = nullptr;
+    if (cudaMalloc(&p, (size_t)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return sk_fail(ctx, SKAGRID_ENOMEM, "ipc_alloc: %lld bytes", (long long)bytes);
+    }
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return sk_fail(ctx, SKAGRID_ECUDA, "ipc_alloc: cudaIpcGetMemHandle: %s", cudaGetErrorString(e));
+    }
+    SK_CUDA(ctx, cudaMemset(p, 0, (size_t)bytes));
+    memcpy(handle, &h, 64);
+    *d_ptr = p;
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_ipc_free(skagrid_ctx *ctx, void *d_ptr) {
+    SK_TRY(sk_api_enter(ctx));
+    if (d_ptr) SK_CUDA(ctx, cudaFree(d_ptr));
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_ipc_open(skagrid_ctx *ctx, const unsigned char handle[64], void **d_ptr) {
+    SK_TRY(sk_api_enter(ctx));
+    if (!d_ptr || !handle) return sk_fail(ctx, SKAGRID_EINVAL, "ipc_open: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    *d_ptr = nullptr;
+    const cudaError_t e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return sk_fail(ctx, SKAGRID_ECUDA, "ipc_open: cudaIpcOpenMemHandle: %s (peer access between the two devices is required)", cudaGetErrorString(e));
+    }
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_ipc_close(skagrid_ctx *ctx, void *d_ptr) {
+    SK_TRY(sk_api_enter(ctx));
+    if (d_ptr) SK_CUDA(ctx, cudaIpcCloseMemHandle(d_ptr));
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_dev_peer_sum(skagrid_ctx *ctx, int npeers, const double *const *d_peers, double *d_own, int64_t ncomplex, void *stream) {
+    SK_TRY(sk_api_enter(ctx));
+    if (npeers < 0 || npeers > IPC_MAX) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_sum: 0..%d peers", IPC_MAX);
+    if (ncomplex <= 0 || npeers == 0) return SKAGRID_OK;
+    if (!d_peers || !d_own) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_sum: NULL pointer");
+    IpcPeers P;
+    P.n = npeers;
+    for (int k = 0; k < npeers; ++k) {
+        if (!d_peers[k]) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_sum: peer %d is NULL", k);
+        P.p[k] = reinterpret_cast<const double2 *>(d_peers[k]);
+    }
+    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((ncomplex + 255) / 256, (i64)ctx->sm_count * 8));
+    ipc_sum_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(reinterpret_cast<double2 *>(d_own), P, ncomplex);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_dev_peer_barrier(skagrid_ctx *ctx, int nranks, int rank, uint32_t *const *d_flags, uint32_t epoch, void *stream) {
+    SK_TRY(sk_api_enter(ctx));
+    if (nranks < 1 || nranks > IPC_MAX || rank < 0 || rank >= nranks) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_barrier: bad rank / world");
+    if (nranks == 1) return SKAGRID_OK;
+    if (!d_flags) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_barrier: NULL flags");
+    IpcFlags F;
+    F.n = nranks; F.me = rank;
+    for (int k = 0; k < nranks; ++k) {
+        if (!d_flags[k]) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_barrier: flags of rank %d are NULL", k);
+        F.p[k] = d_flags[k];
+    }
+    ipc_barrier_kernel<<<1, IPC_MAX, 0, sk_stream(ctx, stream)>>>(F, epoch, ctx->d_flags);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_dev_peer_copy(skagrid_ctx *ctx, void *d_dst, const void *d_src, int64_t bytes, void *stream) {
+    SK_TRY(sk_api_enter(ctx));
+    if (bytes <= 0) return SKAGRID_OK;
+    if (!d_dst || !d_src) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_copy: NULL pointer");
+    SK_CUDA(ctx, cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDefault, sk_stream(ctx, stream)));
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_dev_peer_copy2d(skagrid_ctx *ctx, void *d_dst, int64_t dpitch, const void *d_src, int64_t spitch, int64_t width_bytes,
+                                       int64_t rows, void *stream) {
+    SK_TRY(sk_api_enter(ctx));
+    if (width_bytes <= 0 || rows <= 0) return SKAGRID_OK;
+    if (!d_dst || !d_src) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_copy2d: NULL pointer");
+    SK_CUDA(ctx, cudaMemcpy2DAsync(d_dst, (size_t)dpitch, d_src, (size_t)spitch, (size_t)width_bytes, (size_t)rows, cudaMemcpyDefault,
+                                   sk_stream(ctx, stream)));
+    return SKAGRID_OK;
+}

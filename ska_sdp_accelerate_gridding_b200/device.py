@@ -42,6 +42,8 @@ def check_errors(ctx=None):
         raise _lib.SkagridError(-5, "plan: a w-plane / oversampling / antenna index is out of range (the visibility was dropped)")
     if flags.value & 2:
         raise _lib.SkagridError(-5, "doweight: a visibility falls outside the weight grid")
+    if flags.value & 4:
+        raise _lib.SkagridError(-2, "peer barrier: a rank did not arrive (timed out)")
     if flags.value:
         raise _lib.SkagridError(-5, f"device error word {flags.value:#x}")
 
@@ -308,9 +310,10 @@ def route_count(height, qpx, gh, bounds, v, ctx=None):
     return counts
 
 
-def route_pack(height, qpx, gh, bounds, u, v, wbin, vis, send_counts, keep_index=False, ctx=None):
+def route_pack(height, qpx, gh, bounds, u, v, wbin, vis, send_counts, keep_index=False, ctx=None, out=None):
     """Destination-major send buffer [sum(send_counts), W] float64 (W = 5 with vis, 3 without) and, with keep_index, the
-    source index of every record (int32).  send_counts: host list from route_count."""
+    source index of every record (int32).  send_counts: host list from route_count.  out: a float64 CUDA tensor with room
+    for the records (e.g. a view of peer-visible memory) to pack into instead of a fresh tensor."""
     ctx = ctx or context_for_current_device()
     _chk(u, torch.float64, "u"); _chk(v, torch.float64, "v"); _chk(wbin, torch.int64, "wbin"); _chk(vis, torch.complex128, "vis")
     b, bp = _bounds_arg(bounds)
@@ -318,7 +321,13 @@ def route_pack(height, qpx, gh, bounds, u, v, wbin, vis, send_counts, keep_index
     seg[1:] = np.cumsum(np.asarray(send_counts, dtype=np.int64))[:-1]
     total = int(np.sum(send_counts))
     w = 3 if vis is None else 5
-    send = torch.empty((total, w), dtype=torch.float64, device=u.device)
+    if out is None:
+        send = torch.empty((total, w), dtype=torch.float64, device=u.device)
+    else:
+        _chk(out, torch.float64, "out")
+        if out.numel() < total * w:
+            raise ValueError(f"send buffer too small: {out.numel()} doubles for {total} records of {w}")
+        send = out.reshape(-1)[:total * w].view(total, w)
     sidx = torch.empty(total, dtype=torch.int32, device=u.device) if keep_index else None
     ctx.check(ctx.lib.skagrid_dev_route_pack(ctx.h, int(height), int(qpx), int(gh), len(b) - 1, bp, u.numel(), _p(u), _p(v), _p(wbin), _p(vis),
                                              C.c_void_p(seg.ctypes.data), _p(send), _p(sidx), _stream()))

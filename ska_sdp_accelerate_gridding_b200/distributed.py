@@ -22,6 +22,16 @@ import torch
 import torch.distributed as dist
 
 
+TRACE = None   # a list: the exchange functions below append (label, CUDA event) at their sub-stage boundaries (bench.py)
+
+
+def _mark(label):
+    if TRACE is not None:
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        TRACE.append((label, ev))
+
+
 def shard_range(count: int, rank: int, world: int):
     """Contiguous, balanced slice [first, first+n) of `count` items for `rank` (first ranks get the remainder)."""
     base, rem = divmod(int(count), int(world))
@@ -240,6 +250,44 @@ def return_cuda(partial: torch.Tensor, route, count: int, group=None):
     return dv.scatter_add_(out, route["sidx"], back)
 
 
+def peer_slab_grid_to_image(pg, pbuf, row_base, spans, n, group=None, want_image=True, sync_max=True):
+    """slab_grid_to_image with the transpose pulled over NVLink peer memory instead of an all-to-all: rank s holds grid rows
+    [row_base[s], ...) as [rows, n] complex128 at the start of its peer-visible buffer `pbuf`; spans[s] = (a, b) are the rows
+    of rank s that can be non-zero (host list, all ranks).  Row transforms in place, device barrier, then every rank pulls its
+    column block of every peer's rows with ONE strided copy-engine copy per peer straight into place (no pack, no unpack),
+    column transforms.  Returns (image columns or None, (c0, c1), max)."""
+    from . import device as dv
+    P, me = pg.world, pg.rank
+    a, b = spans[me]
+    b = max(b, a)
+    _mark("image: start")
+    if b > a:
+        rows = pbuf.tensor(torch.complex128, (b - a, n), offset_bytes=(a - row_base[me]) * n * 16)
+        dv.slab_fft_rows_(n, a, rows)
+    _mark("image: row transforms")
+    cb = [n * h // P for h in range(P + 1)]
+    c0, c1 = cb[me], cb[me + 1]
+    cw = c1 - c0
+    pg.barrier()                                                  # all row transforms are done
+    dev = torch.device("cuda", pg.ctx.device)
+    cols = torch.zeros((n, cw), dtype=torch.complex128, device=dev)
+    copies = []
+    for s_ in range(P):
+        sa, sb = spans[s_]
+        if sb <= sa:
+            continue
+        src = pbuf.ptrs[s_] + ((sa - row_base[s_]) * n + c0) * 16
+        copies.append((cols.data_ptr() + sa * cw * 16, cw * 16, src, n * 16, cw * 16, sb - sa))
+    _mark("image: barrier + zeroed columns")
+    pg.pull(copies)
+    _mark("image: transpose pulled")
+    img, mx = dv.slab_fft_cols_(n, c0, cols, want_image=want_image)
+    if P > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    _mark("image: column transforms + max")
+    return img, (c0, c1), (float(mx.item()) if sync_max else mx)
+
+
 class VisShardedGridder:
     """Visibility-sharded gridding / degridding on CUDA tensors (config 4).
 
@@ -322,6 +370,41 @@ class VisShardedGridder:
             return dist.all_gather_into_tensor(torch.view_as_real(act), torch.view_as_real(slab), group=self.group, async_op=async_op)
         act.copy_(slab)
         return None
+
+    # ---- the same over peer memory (csrc/ipc.cu): no collective library in the data path
+    def enable_peer(self, pg):
+        """Collective.  The local grid moves into a peer-visible buffer (`self.work`, [h, w] complex128)."""
+        from .peer import PeerBuffer
+        self.pg = pg
+        self.pgrid = PeerBuffer(pg, self.h * self.w * 16)
+        self.work = self.pgrid.tensor(torch.complex128, (self.h, self.w))
+        return self.work
+
+    def _slab_off(self, r):
+        lo, m = self.active
+        return (lo + r * m) * self.w * 16
+
+    def grid_slabs_peer(self, u=None, v=None, wbin=None, vis=None, variant=0):
+        """Reduce-scatter over NVLink peer memory: grid into the local peer-visible grid, barrier, then ONE kernel on every
+        rank sums its row slab of all peers' grids in place (all peers in flight), barrier.  Returns this rank's reduced
+        slab (a view of rows spans()[rank] of `self.work`).  u = None: the plan was already updated by the caller."""
+        lo, m = self.active
+        plan = self.plan if u is None else self._plan(u, v, wbin, vis)
+        self.pg.barrier()                      # every peer has finished pulling the previous pass's slabs from this grid
+        self.work[lo:lo + m * self.world].zero_()
+        plan.grid(self.table, self.work, variant=variant)
+        self.pg.barrier()                      # all local grids are complete
+        self.pg.peer_sum_(self.pgrid, self._slab_off(self.rank), m * self.w)
+        self.pg.barrier()                      # all slabs are reduced
+        return self.work[lo + self.rank * m:lo + (self.rank + 1) * m]
+
+    def gather_slabs_peer(self, join=True):
+        """All-gather of the reduced slabs by the copy engines: every rank pulls the other ranks' slabs out of their grids
+        into the same rows of its own.  join=False returns a handle; wait() before reading `self.work`."""
+        lo, m = self.active
+        nbytes = m * self.w * 16
+        copies = [(self.pgrid.local + self._slab_off(p), self.pgrid.ptrs[p] + self._slab_off(p), nbytes) for p in range(self.world) if p != self.rank]
+        return self.pg.pull(copies, join=join)
 
     def degrid(self, grid, u=None, v=None, wbin=None, out=None):
         """Every rank holds the full (model) grid; each degrids its own visibilities.  u = None: at the coordinates of the
@@ -435,3 +518,115 @@ class TileShardedGridder:
         if route is None:
             return partial
         return return_cuda(partial, route, u.numel(), self.group)
+
+    # ---- the same over peer memory (csrc/ipc.cu): NCCL only carries the P x P table of record counts
+    def enable_peer(self, pg, send_capacity, recv_capacity=None):
+        """Collective, after the bounds are final (`balance`).  send_capacity / recv_capacity: most records this rank packs /
+        receives per batch.  Allocates the peer-visible send buffer, partial-sum buffer and slab; returns the slab
+        ([rows, w] complex128 view)."""
+        from .peer import PeerBuffer
+        self.pg = pg
+        self.send_cap = int(send_capacity)
+        self.recv_cap = int(recv_capacity if recv_capacity is not None else send_capacity)
+        self.psend = PeerBuffer(pg, self.send_cap * 40)
+        self.ppart = PeerBuffer(pg, self.recv_cap * 16)
+        rows = self.rows[1] - self.rows[0]
+        self.pslab = PeerBuffer(pg, rows * self.w * 16)
+        self.slab = self.pslab.tensor(torch.complex128, (rows, self.w))
+        return self.slab
+
+    def route_peer(self, u, v, wbin, vis=None, keep_index=False):
+        """route() with the records pulled over NVLink by the destination's copy engines: counts -> all-gather of the count
+        table (the one host synchronisation) -> pack into the peer-visible send buffer -> barrier -> every rank pulls its
+        segment out of every peer's send buffer."""
+        from . import device as dv
+        gh, qpx = self.table.shape[-2], self.table.shape[-3]
+        P, me = self.world, self.rank
+        _mark("route: start")
+        counts = dv.route_count(self.h, qpx, gh, self.bounds, v)
+        table = torch.empty((P, P), dtype=torch.int32, device=v.device)
+        dist.all_gather_into_tensor(table.view(-1), counts, group=self.group)
+        cnt = table.tolist()                                      # cnt[s][g]: records rank s sends to rank g
+        W = 3 if vis is None else 5
+        sent = sum(cnt[me])
+        recv = sum(cnt[s][me] for s in range(P))
+        if sent > self.send_cap or recv > self.recv_cap:
+            raise RuntimeError(f"route_peer: {sent} records to send / {recv} to receive exceed the capacities {self.send_cap} / {self.recv_cap}")
+        _mark("route: counts on host")
+        self.pg.barrier()                                         # every peer has finished pulling the previous batch
+        send_view = self.psend.tensor(torch.float64, (self.send_cap * 5,))
+        _, sidx = dv.route_pack(self.h, qpx, gh, self.bounds, u, v, wbin, vis, cnt[me], keep_index=keep_index, out=send_view)
+        _mark("route: packed")
+        self.pg.barrier()                                         # all send buffers are packed
+        rec = torch.empty((recv, W), dtype=torch.float64, device=v.device)
+        copies, off = [], 0
+        offs = []
+        for s in range(P):
+            seg = sum(cnt[s][:me])                                # start of my segment in rank s's send buffer
+            n = cnt[s][me]
+            offs.append(off)
+            if n:
+                copies.append((rec.data_ptr() + off * W * 8, self.psend.ptrs[s] + seg * W * 8, n * W * 8))
+            off += n
+        self.pg.pull(copies)
+        _mark("route: pulled")
+        return rec, {"sidx": sidx, "cnt": cnt, "offs_in_owner": None}
+
+    def return_peer(self, count, route):
+        """The owners' partial sums (in the peer-visible `ppart`, one per received record) travel back: every source pulls the
+        values of its records from every owner and adds them per visibility."""
+        from . import device as dv
+        P, me = self.world, self.rank
+        cnt = route["cnt"]
+        sent = sum(cnt[me])
+        back = torch.empty(sent, dtype=torch.complex128, device=self.slab.device)
+        _mark("return: start")
+        self.pg.barrier()                                         # all owners have written their partial sums
+        copies, seg = [], 0
+        for g in range(P):
+            n = cnt[me][g]
+            off = sum(cnt[s][g] for s in range(me))               # where my records start in owner g's receive order
+            if n:
+                copies.append((back.data_ptr() + seg * 16, self.ppart.ptrs[g] + off * 16, n * 16))
+            seg += n
+        self.pg.pull(copies)
+        _mark("return: pulled")
+        out = torch.zeros(count, dtype=torch.complex128, device=self.slab.device)
+        dv.scatter_add_(out, route["sidx"], back)
+        _mark("return: added")
+        return out
+
+    def partial_view(self, n):
+        return self.ppart.tensor(torch.complex128, (n,))
+
+    def all_nonzero_rows(self):
+        """nonzero_rows() of every rank (collective; host list of (lo, hi))."""
+        nz = torch.tensor(self.nonzero_rows(), dtype=torch.int64, device=self.table.device)
+        if self.world == 1:
+            return [tuple(int(x) for x in nz.tolist())]
+        out = torch.empty((self.world, 2), dtype=torch.int64, device=self.table.device)
+        dist.all_gather_into_tensor(out.view(-1), nz, group=self.group)
+        return [(int(a), int(b)) for a, b in out.tolist()]
+
+    def grid_peer(self, u, v, wbin, vis):
+        """grid(..., keep_route=True) over peer memory, into the peer-visible slab of enable_peer (zeroed here)."""
+        rec, route = self.route_peer(u, v, wbin, vis, keep_index=True)
+        self.last_routed, self._last_rec, self._route, self._count = int(rec.shape[0]), rec, route, int(u.numel())
+        self.slab.zero_()
+        if rec.shape[0] > 0:
+            self._fill(rec).grid(self.table, self.slab)
+        return self.slab
+
+    def degrid_routed_peer(self):
+        """Adjoint of the last grid_peer at the same coordinates, on whatever the slab holds now: the routed plan is reused,
+        the partial sums return through peer memory."""
+        partial = self.partial_view(max(self.last_routed, 1))[:self.last_routed]
+        if self.last_routed > 0:
+            self._plan.degrid(self.table, self.slab, partial)
+        return self.return_peer(self._count, self._route)
+
+    def image_peer(self, all_nonzero, want_image=False, sync_max=True):
+        """slab_grid_to_image on the peer-visible slab with the transpose pulled over NVLink (peer_slab_grid_to_image).
+        all_nonzero: the (lo, hi) non-zero row interval of EVERY rank (host list; static per data set)."""
+        return peer_slab_grid_to_image(self.pg, self.pslab, self.bounds[:-1], all_nonzero, self.h, group=self.group, want_image=want_image,
+                                       sync_max=sync_max)

@@ -1,0 +1,141 @@
+"""Peer-memory plumbing of the one-process-per-GPU modes (csrc/ipc.cu): exchange buffers every rank can dereference over
+NVLink, a stream-ordered device barrier, copy-engine pulls.  torch.distributed is used ONCE per buffer, to swap the 64-byte
+CUDA IPC handles; the data path afterwards is the library's own kernels and cudaMemcpyAsync."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.distributed as dist
+
+from .context import Context
+from .device import _DevArray, _stream, context_for_current_device
+
+_TYPESTR = {torch.float64: "<f8", torch.int32: "<i4", torch.int64: "<i8", torch.uint8: "|u1"}
+
+
+class PeerBuffer:
+    """`nbytes` of device memory on every rank of `pg` (sizes may differ per rank), opened on all the others.
+    ptrs[k] = device address of rank k's buffer as seen from this process."""
+
+    def __init__(self, pg: "PeerGroup", nbytes: int):
+        self.pg, self.ctx, self.nbytes = pg, pg.ctx, max(int(nbytes), 256)
+        lib, h = self.ctx.lib, self.ctx.h
+        handle = (C.c_ubyte * 64)()
+        p = C.c_void_p()
+        self.ctx.check(lib.skagrid_ipc_alloc(h, self.nbytes, C.byref(p), handle))
+        self.local = int(p.value)
+        dev = torch.device("cuda", self.ctx.device)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        every = torch.empty(64 * pg.world, dtype=torch.uint8, device=dev)
+        if pg.world > 1:
+            dist.all_gather_into_tensor(every, mine, group=pg.group)
+        else:
+            every.copy_(mine)
+        host = every.cpu().numpy()
+        self.ptrs = []
+        for k in range(pg.world):
+            if k == pg.rank:
+                self.ptrs.append(self.local)
+                continue
+            hk = (C.c_ubyte * 64)(*host[64 * k:64 * (k + 1)].tolist())
+            q = C.c_void_p()
+            self.ctx.check(lib.skagrid_ipc_open(h, hk, C.byref(q)))
+            self.ptrs.append(int(q.value))
+        if pg.world > 1:
+            dist.barrier(group=pg.group)   # nobody frees before everybody has opened
+
+    def tensor(self, dtype, shape, offset_bytes=0):
+        """A torch view (no copy) of the LOCAL buffer."""
+        itemsize = torch.empty(0, dtype=torch.float64 if dtype == torch.complex128 else dtype).element_size()
+        if dtype == torch.complex128:
+            t = torch.as_tensor(_DevArray(self.local + offset_bytes, tuple(shape) + (2,), "<f8"), device=torch.device("cuda", self.ctx.device))
+            return torch.view_as_complex(t)
+        n = 1
+        for s in shape:
+            n *= int(s)
+        if offset_bytes + n * itemsize > self.nbytes:
+            raise ValueError("view exceeds the peer buffer")
+        return torch.as_tensor(_DevArray(self.local + offset_bytes, shape, _TYPESTR[dtype]), device=torch.device("cuda", self.ctx.device))
+
+    def close(self):
+        if getattr(self, "ptrs", None) is None:
+            return
+        torch.cuda.synchronize()
+        if self.pg.world > 1:
+            dist.barrier(group=self.pg.group)   # nobody is still reading
+        for k, q in enumerate(self.ptrs):
+            if k != self.pg.rank:
+                self.ctx.lib.skagrid_ipc_close(self.ctx.h, C.c_void_p(q))
+        if self.pg.world > 1:
+            dist.barrier(group=self.pg.group)   # everybody has unmapped before the owner frees
+        self.ctx.lib.skagrid_ipc_free(self.ctx.h, C.c_void_p(self.local))
+        self.ptrs = None
+
+
+class _Pending:
+    def __init__(self, streams):
+        self.streams = streams
+
+    def wait(self):
+        main = torch.cuda.current_stream()
+        for s in self.streams:
+            main.wait_stream(s)
+        self.streams = []
+
+
+class PeerGroup:
+    """The ranks of a torch.distributed group as NVLink peers: flag buffer for the device barrier, side streams for pulls."""
+
+    def __init__(self, group=None, ctx: Context | None = None):
+        self.group = group
+        self.ctx = ctx or context_for_current_device()
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.flags = PeerBuffer(self, 4096)
+        self._flag_ptrs = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.flags.ptrs])
+        self.epoch = 0
+        self.streams = [torch.cuda.Stream() for _ in range(max(1, min(self.world - 1, 8)))]
+        self._fork = torch.cuda.Event()
+
+    def barrier(self):
+        """Stream-ordered barrier on the current stream: the kernels enqueued after it on ANY rank start only when every
+        rank's stream has reached it.  No host synchronisation."""
+        if self.world == 1:
+            return
+        self.epoch += 1
+        self.ctx.check(self.ctx.lib.skagrid_dev_peer_barrier(self.ctx.h, self.world, self.rank, self._flag_ptrs, self.epoch & 0xFFFFFFFF, _stream()))
+
+    def peer_sum_(self, buf: PeerBuffer, offset_bytes: int, ncomplex: int):
+        """local[offset ...] += sum over the other ranks of theirs[offset ...] (complex128 values), one kernel, all peers in flight."""
+        others = [buf.ptrs[k] + offset_bytes for k in range(self.world) if k != self.rank]
+        arr = (C.c_void_p * max(len(others), 1))(*[C.c_void_p(p) for p in others])
+        self.ctx.check(self.ctx.lib.skagrid_dev_peer_sum(self.ctx.h, len(others), arr, C.c_void_p(buf.local + offset_bytes), int(ncomplex), _stream()))
+
+    def pull(self, copies, join=True):
+        """copies: iterable of (dst address, src address, bytes) or (dst, dpitch, src, spitch, width_bytes, rows): enqueued
+        round-robin on the side streams after everything already on the current stream.  join=True: the current stream
+        waits for them; join=False: returns an object whose wait() does that later (the pulls overlap what is enqueued on
+        the current stream in between)."""
+        main = torch.cuda.current_stream()
+        self._fork.record(main)
+        lib, h = self.ctx.lib, self.ctx.h
+        used = set()
+        for i, c in enumerate(copies):
+            s = self.streams[i % len(self.streams)]
+            if i < len(self.streams):
+                s.wait_event(self._fork)
+            used.add(i % len(self.streams))
+            sp = C.c_void_p(s.cuda_stream)
+            if len(c) == 3:
+                self.ctx.check(lib.skagrid_dev_peer_copy(h, C.c_void_p(c[0]), C.c_void_p(c[1]), int(c[2]), sp))
+            else:
+                self.ctx.check(lib.skagrid_dev_peer_copy2d(h, C.c_void_p(c[0]), int(c[1]), C.c_void_p(c[2]), int(c[3]), int(c[4]), int(c[5]), sp))
+        pending = _Pending([self.streams[i] for i in sorted(used)])
+        if join:
+            pending.wait()
+            return None
+        return pending
+
+    def close(self):
+        self.flags.close()

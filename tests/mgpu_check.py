@@ -56,6 +56,28 @@ def main():
     d2 = vs.degrid(work).cpu().numpy()   # at the coordinates of the plan grid_slabs filled
     err_d = max(err_d, np.abs(d2 - od).max() / np.abs(od).max())
 
+    # the same reduce-scatter / gather / transpose over NVLink peer memory (csrc/ipc.cu), no NCCL in the data path
+    from ska_sdp_accelerate_gridding_b200.peer import PeerBuffer, PeerGroup
+    pg = PeerGroup()
+    vp = D.VisShardedGridder(n, n, table)
+    vp.set_active_rows(lv)
+    vp.enable_peer(pg)
+    vp.work.fill_(5.0 - 2j)   # garbage in the active rows must not survive
+    vp.work[:vp.active[0]].zero_(); vp.work[vp.active[0] + vp.active[1] * world:].zero_()
+    for _ in range(2):        # twice: the second pass exercises the barrier that protects the gathered grid
+        ps = vp.grid_slabs_peer(lu, lv, lwb, lvis)
+        err_p = np.abs(ps.cpu().numpy() - full[a:b]).max() / peak
+        pis = PeerBuffer(pg, ps.numel() * 16)
+        pis.tensor(torch.complex128, tuple(ps.shape)).copy_(ps)
+        hnd = vp.gather_slabs_peer(join=False)
+        pimg, (pc0, pc1), pmx = D.peer_slab_grid_to_image(pg, pis, [x[0] for x in vp.spans()], vp.spans(), n)
+        hnd.wait()
+        err_p = max(err_p, np.abs(pimg.cpu().numpy() - oimg[:, pc0:pc1]).max() / np.abs(oimg).max(), abs(pmx - oimg.max()) / abs(oimg.max()))
+        err_p = max(err_p, np.abs(vp.work.cpu().numpy() - full).max() / peak)
+        dp = vp.degrid(vp.work).cpu().numpy()
+        err_p = max(err_p, np.abs(dp - od).max() / np.abs(od).max())
+        pis.close()
+
     ts = D.TileShardedGridder(n, n, table)
     slab_t = ts.grid(lu, lv, lwb, lvis, keep_route=True)
     slab = slab_t.cpu().numpy()
@@ -81,8 +103,8 @@ def main():
     img2, (c0, c1), mx2 = D.slab_grid_to_image(hslab, ts.bounds, nonzero=nz)
     himg = np.real(orc.ifft(orc.make_grid_hermitian(hfull)))
     err_t = max(err_t, np.abs(img2.cpu().numpy() - himg[:, c0:c1]).max() / np.abs(himg).max(), abs(mx2 - himg.max()) / abs(himg.max()))
-    if rank == 0 and not (nz[0] > r0 + 100):
-        err_t = 1.0  # rank 0 owns the empty lower half: its non-zero interval must start far above its first row
+    if nz[0] < min(r1, n // 2 - s // 2 - 1):
+        err_t = 1.0  # v >= 0: no row below the centre minus half a kernel can be non-zero
     # doweight over sharded visibilities: counts all-reduced between the two phases (bit-exact: integer counts, one division)
     theta, lam = 0.01, n * 100
     uw, vw = u * lam * 0.9, v * lam * 0.9
@@ -90,10 +112,29 @@ def main():
     D.doweight_sharded_(theta, lam, t(uw[first:first + m]), t(vw[first:first + m]), wvis)
     ow = orc.doweight(theta, lam, uw, vw, vis)[first:first + m]
     err_t = max(err_t, 0.0 if np.array_equal(wvis.cpu().numpy(), ow) else 1.0)
-    res = torch.tensor([err_v, err_d, err_t], dtype=torch.float64, device="cuda")
+    # uv-tile-sharded over peer memory: routed records pulled by the owners, partial sums pulled back, transpose pulled
+    tp = D.TileShardedGridder(n, n, table)
+    tp.balance(t(hv))
+    tp.enable_peer(pg, send_capacity=2 * m + 64, recv_capacity=cnt + 64)
+    r0, r1 = tp.rows
+    err_tp = 0.0
+    for _ in range(2):
+        pslab = tp.grid_peer(t(hu), t(hv), lwb, lvis)
+        err_tp = max(err_tp, np.abs(pslab.cpu().numpy() - hfull[r0:r1]).max() / np.abs(hfull).max())
+        hod = orc.convdegrid(gcf, hfull, hu, hv, wbin=wb[first:first + m])
+        pslab.copy_(t(hfull[r0:r1].copy()))
+        dpp = tp.degrid_routed_peer().cpu().numpy()
+        err_tp = max(err_tp, np.abs(dpp - hod).max() / np.abs(hod).max())
+        anz = tp.all_nonzero_rows()
+        img3, (c0, c1), mx3 = tp.image_peer(anz, want_image=True)
+        err_tp = max(err_tp, np.abs(img3.cpu().numpy() - himg[:, c0:c1]).max() / np.abs(himg).max(), abs(mx3 - himg.max()) / abs(himg.max()))
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    dv.check_errors()
+    res = torch.tensor([err_v, err_d, err_t, err_p, err_tp], dtype=torch.float64, device="cuda")
     dist.all_reduce(res, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print(f"world={world} vis-sharded grid err {res[0]:.2e}, degrid err {res[1]:.2e}, tile-sharded (grid, balanced grid, degrid) + slab grid->image + sharded doweight err {res[2]:.2e}")
+        print(f"world={world} vis-sharded grid err {res[0]:.2e}, degrid err {res[1]:.2e}, tile-sharded (grid, balanced grid, degrid) + slab grid->image + "
+              f"sharded doweight err {res[2]:.2e}, vis-sharded over peer memory {res[3]:.2e}, tile-sharded over peer memory {res[4]:.2e}")
     dist.destroy_process_group()
     sys.exit(0 if float(res.max()) < 1e-10 else 1)
 
