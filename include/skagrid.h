@@ -329,7 +329,8 @@ int skagrid_dev_take_error(skagrid_ctx *ctx, void *stream, int *flags_out);
  *   route_count  d_counts[g] (uint32, nranks entries, zeroed by the call) = records this device sends to rank g
  *   route_pack   appends the records, destination-major, to d_send: rank g's segment starts at record seg[g] (host array);
  *                a record is 5 doubles {u, v, wbin, re, im}, or 3 when d_vis == NULL; d_sidx (may be NULL) receives
- *                the source index of every record
+ *                the source index of every record.  Must follow route_count of the same (count, d_v, bounds) on this
+ *                context: it places the records with the per-block offsets that call left behind (no global atomics)
  *   scatter_add  d_out[d_sidx[i]] += d_back[i] (complex): returned degridding partial sums, one per routed record */
 int skagrid_dev_row_hist(skagrid_ctx *ctx, int64_t height, int64_t qpx, int64_t gh, int64_t count, const double *d_v,
                          uint32_t *d_hist, void *stream);

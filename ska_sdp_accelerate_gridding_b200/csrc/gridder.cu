@@ -568,37 +568,53 @@ __global__ void __launch_bounds__(NT, 1024 / NT) degrid_tile_kernel(const GridAr
         }
         __syncthreads();
         const uint32_t nrec = it.end - it.begin;
-        const uint32_t rounds = (nrec + (uint32_t)NHW - 1u) / (uint32_t)NHW;
-        for (uint32_t q = 0; q < rounds; ++q) {
-            const uint32_t r = q * (uint32_t)NHW + (uint32_t)hw;  // both halves of a warp stay in the loop (shuffles below)
-            const bool live = r < nrec;
-            double ar = 0.0, ai = 0.0;
-            uint32_t out_index = 0;
-            if (live) {
-                const uint4 meta = __ldg(reinterpret_cast<const uint4 *>(A.rec + it.begin + r) + 1);
-                out_index = meta.z;
-                const int lx = (int)(meta.y & 255u), ly = (int)((meta.y >> 8) & 255u);
-                const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
-                const uint32_t kslice = meta.x + dy * (uint32_t)A.kpitch + dx;
-                for (int j = hl; j < A.gw; j += 16) {
-                    const double2 *kp = A.table + (uint32_t)(kslice + (uint32_t)j);
-                    const double2 *gp = sg + ly * SGW + lx + j;
+        // contiguous run of records per half-warp, walked in blocks of 16 whose second halves (table offset, loc, output index)
+        // arrive with one request per block, prefetched one block ahead, and are broadcast by shuffle (as degrid_reg_kernel)
+        const uint32_t chunk = (nrec + (uint32_t)NHW - 1u) / (uint32_t)NHW;
+        const uint32_t r0 = (uint32_t)hw * chunk;
+        const uint32_t r1 = min(nrec, r0 + chunk);
+        const uint4 *recm = reinterpret_cast<const uint4 *>(A.rec + it.begin) + 1;
+        auto load_meta = [&](uint32_t q0) {
+            const uint32_t r = r0 + q0 + (uint32_t)hl;
+            return r < r1 ? __ldg(recm + 2 * (size_t)r) : make_uint4(0u, 0u, 0u, 0u);
+        };
+        uint4 meta_next = load_meta(0);
+        for (uint32_t q0 = 0; q0 < chunk; q0 += 16) {  // both halves of a warp run the same trip count (shuffles below)
+            const uint4 meta = meta_next;
+            if (q0 + 16 < chunk) meta_next = load_meta(q0 + 16);
+            double2 res = make_double2(0.0, 0.0);
+#pragma unroll 1
+            for (int qq = 0; qq < 16; ++qq) {
+                const uint32_t kb = __shfl_sync(0xffffffffu, meta.x, qq, 16);
+                const uint32_t loc = __shfl_sync(0xffffffffu, meta.y, qq, 16);
+                const bool live = r0 + q0 + (uint32_t)qq < r1;
+                double ar = 0.0, ai = 0.0;
+                if (live) {
+                    const int lx = (int)(loc & 255u), ly = (int)((loc >> 8) & 255u);
+                    const uint32_t dx = (uint32_t)(lx & ~A.mt_mask), dy = (uint32_t)(ly & ~A.mt_mask);
+                    const uint32_t kslice = kb + dy * (uint32_t)A.kpitch + dx;
+                    for (int j = hl; j < A.gw; j += 16) {
+                        const double2 *kp = A.table + (uint32_t)(kslice + (uint32_t)j);
+                        const double2 *gp = sg + ly * SGW + lx + j;
 #pragma unroll UNROLL
-                    for (int i = 0; i < A.gh; ++i) {
-                        const double2 k = ldg2(kp);
-                        const double2 g = *gp;
-                        ar = fma(k.x, g.x, ar); ar = fma(k.y, g.y, ar);   // conj(k) * g
-                        ai = fma(k.x, g.y, ai); ai = fma(-k.y, g.x, ai);
-                        kp += A.kpitch; gp += SGW;
+                        for (int i = 0; i < A.gh; ++i) {
+                            const double2 k = ldg2(kp);
+                            const double2 g = *gp;
+                            ar = fma(k.x, g.x, ar); ar = fma(k.y, g.y, ar);   // conj(k) * g
+                            ai = fma(k.x, g.y, ai); ai = fma(-k.y, g.x, ai);
+                            kp += A.kpitch; gp += SGW;
+                        }
                     }
                 }
-            }
+                const bool hi = (hl & 8) != 0;
+                const double send = hi ? ar : ai, keep = hi ? ai : ar;
+                double sum = keep + __shfl_xor_sync(0xffffffffu, send, 8);
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                ar += __shfl_xor_sync(0xffffffffu, ar, o);
-                ai += __shfl_xor_sync(0xffffffffu, ai, o);
+                for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const double other = __shfl_xor_sync(0xffffffffu, sum, 8);
+                if (hl == qq) res = hi ? make_double2(other, sum) : make_double2(sum, other);
             }
-            if (live && hl == 0) A.vis_out[out_index] = make_double2(ar, ai);
+            if (r0 + q0 + (uint32_t)hl < r1) A.vis_out[meta.z] = res;
         }
     }
 }

@@ -48,16 +48,25 @@ __global__ void __launch_bounds__(256) rt_row_hist_kernel(i64 count, const doubl
     }
 }
 
-// Pass 1 (send == NULL): counts[g] += records for rank g.  Pass 2: the records are appended at cursor[g]++ (one atomic per warp
-// and destination) as `W` doubles {u, v, wbin, [re, im]}; sidx (optional) keeps the source index of every record.
-template <int W>
+// Both passes walk the visibilities with the SAME block / iteration mapping, so the records a block sends to every rank are
+// known after pass 1 and pass 2 needs no global atomics at all (a same-address atomic per warp and destination serialises:
+// 5.8 + 8.3 ms per 1.25e8 visibilities in the first version, profiles/r02_config5_substages.md):
+//   pass 1  every block counts its records per destination in shared memory -> blockcounts[block][g]
+//   scan    bases[block][g] = records of the blocks before it for destination g; totals[g]
+//   pass 2  the block's shared-memory cursors start at seg[g] + bases[block][g]; a warp reserves its run with one
+//           shared-memory atomic per destination and appends `W` doubles {u, v, wbin, [re, im]} per record; sidx (optional)
+//           keeps the source index of every record.
+template <int W, bool PACK>
 __global__ void __launch_bounds__(256) rt_route_kernel(i64 count, const double *__restrict__ u, const double *__restrict__ v,
                                                        const i64 *__restrict__ wbin, const double2 *__restrict__ vis, i64 height, i64 qpx, i64 gh,
-                                                       RtBounds B, uint32_t *__restrict__ counts, uint32_t *__restrict__ cursor,
+                                                       RtBounds B, uint32_t *__restrict__ blockcounts, const uint32_t *__restrict__ bases, RtSeg seg,
                                                        double *__restrict__ send, uint32_t *__restrict__ sidx) {
+    __shared__ uint32_t s_cur[RT_MAX];
     const double halfhf = (double)(height / 2), hf = (double)height, qpxf = (double)qpx, qpxfrac = 0.5 / (double)qpx;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     const int lane = threadIdx.x & 31;
+    if ((int)threadIdx.x < B.n) s_cur[threadIdx.x] = PACK ? seg.s[threadIdx.x] + bases[(size_t)blockIdx.x * B.n + threadIdx.x] : 0u;
+    __syncthreads();
     for (i64 base = (i64)blockIdx.x * blockDim.x; base < count; base += stride) {  // warp-uniform trip count
         const i64 k = base + threadIdx.x;
         int lo = 1, hi = 0;
@@ -81,8 +90,8 @@ __global__ void __launch_bounds__(256) rt_route_kernel(i64 count, const double *
             if (!m) continue;
             const int leader = __ffs(m) - 1;
             uint32_t pos = 0;
-            if (lane == leader) pos = atomicAdd(send ? &cursor[g] : &counts[g], (uint32_t)__popc(m));
-            if (!send) continue;
+            if (lane == leader) pos = atomicAdd(&s_cur[g], (uint32_t)__popc(m));
+            if (!PACK) continue;
             pos = __shfl_sync(0xffffffffu, pos, leader) + (uint32_t)__popc(m & ((1u << lane) - 1u));
             if (mine) {
                 double *r = send + (size_t)pos * W;
@@ -98,10 +107,23 @@ __global__ void __launch_bounds__(256) rt_route_kernel(i64 count, const double *
             }
         }
     }
+    if (!PACK) {
+        __syncthreads();
+        if ((int)threadIdx.x < B.n) blockcounts[(size_t)blockIdx.x * B.n + threadIdx.x] = s_cur[threadIdx.x];
+    }
 }
 
-__global__ void rt_set_cursor_kernel(uint32_t *cursor, RtSeg seg, int n) {
-    if ((int)threadIdx.x < n) cursor[threadIdx.x] = seg.s[threadIdx.x];
+// bases[b][g] = sum of blockcounts[b'][g] over b' < b; totals[g] = the column sum.  One thread per destination.
+__global__ void rt_scan_kernel(const uint32_t *__restrict__ blockcounts, uint32_t *__restrict__ bases, uint32_t *__restrict__ totals, int nblocks, int n) {
+    const int g = threadIdx.x;
+    if (g >= n) return;
+    uint32_t run = 0;
+    for (int b = 0; b < nblocks; ++b) {
+        const uint32_t c = blockcounts[(size_t)b * n + g];
+        bases[(size_t)b * n + g] = run;
+        run += c;
+    }
+    totals[g] = run;
 }
 
 // out[sidx[i]] += back[i]
@@ -140,6 +162,14 @@ extern "C" int skagrid_dev_row_hist(skagrid_ctx *ctx, int64_t height, int64_t qp
     return SKAGRID_OK;
 }
 
+// per-block counts and bases of the last route_count on this context (consumed by route_pack)
+static int rt_state(skagrid_ctx *ctx, unsigned blocks, int nranks, uint32_t **blockcounts, uint32_t **bases) {
+    const size_t bytes = (size_t)blocks * nranks * sizeof(uint32_t);
+    SK_TRY(sk_scratch(ctx, "rt_blockcounts", bytes, (void **)blockcounts));
+    SK_TRY(sk_scratch(ctx, "rt_bases", bytes, (void **)bases));
+    return SKAGRID_OK;
+}
+
 extern "C" int skagrid_dev_route_count(skagrid_ctx *ctx, int64_t height, int64_t qpx, int64_t gh, int nranks, const int64_t *bounds,
                                        int64_t count, const double *d_v, uint32_t *d_counts, void *stream) {
     SK_TRY(sk_api_enter(ctx));
@@ -151,12 +181,20 @@ extern "C" int skagrid_dev_route_count(skagrid_ctx *ctx, int64_t height, int64_t
     SK_CUDA(ctx, cudaMemsetAsync(d_counts, 0, (size_t)nranks * sizeof(uint32_t), st));
     if (count <= 0) return SKAGRID_OK;
     if (!d_v) return sk_fail(ctx, SKAGRID_EINVAL, "dev_route_count: NULL v");
-    rt_route_kernel<3><<<rt_blocks(ctx, count), 256, 0, st>>>(count, nullptr, d_v, nullptr, nullptr, height, qpx, gh, B, d_counts, nullptr, nullptr,
-                                                              nullptr);
+    const unsigned blocks = rt_blocks(ctx, count);
+    uint32_t *blockcounts, *bases;
+    SK_TRY(rt_state(ctx, blocks, nranks, &blockcounts, &bases));
+    RtSeg S;
+    for (int g = 0; g < RT_MAX; ++g) S.s[g] = 0;
+    rt_route_kernel<3, false><<<blocks, 256, 0, st>>>(count, nullptr, d_v, nullptr, nullptr, height, qpx, gh, B, blockcounts, nullptr, S, nullptr, nullptr);
+    SK_LAUNCH_CHECK(ctx);
+    rt_scan_kernel<<<1, RT_MAX, 0, st>>>(blockcounts, bases, d_counts, (int)blocks, nranks);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
 
+// Must follow skagrid_dev_route_count of the same (count, d_v, bounds) on this context: it consumes the per-block bases that
+// call left in the context (no global atomics in the packing pass).
 extern "C" int skagrid_dev_route_pack(skagrid_ctx *ctx, int64_t height, int64_t qpx, int64_t gh, int nranks, const int64_t *bounds,
                                       int64_t count, const double *d_u, const double *d_v, const int64_t *d_wbin, const double *d_vis,
                                       const int64_t *seg, double *d_send, uint32_t *d_sidx, void *stream) {
@@ -174,16 +212,14 @@ extern "C" int skagrid_dev_route_pack(skagrid_ctx *ctx, int64_t height, int64_t 
         S.s[g] = (uint32_t)seg[g];
     }
     cudaStream_t st = sk_stream(ctx, stream);
-    uint32_t *cursor;
-    SK_TRY(sk_scratch(ctx, "rt_cursor", RT_MAX * sizeof(uint32_t), (void **)&cursor));
-    rt_set_cursor_kernel<<<1, RT_MAX, 0, st>>>(cursor, S, nranks);
-    SK_LAUNCH_CHECK(ctx);
+    const unsigned blocks = rt_blocks(ctx, count);
+    uint32_t *blockcounts, *bases;
+    SK_TRY(rt_state(ctx, blocks, nranks, &blockcounts, &bases));
     if (d_vis)
-        rt_route_kernel<5><<<rt_blocks(ctx, count), 256, 0, st>>>(count, d_u, d_v, (const i64 *)d_wbin, (const double2 *)d_vis, height, qpx, gh, B,
-                                                                  nullptr, cursor, d_send, d_sidx);
+        rt_route_kernel<5, true><<<blocks, 256, 0, st>>>(count, d_u, d_v, (const i64 *)d_wbin, (const double2 *)d_vis, height, qpx, gh, B, nullptr, bases, S,
+                                                         d_send, d_sidx);
     else
-        rt_route_kernel<3><<<rt_blocks(ctx, count), 256, 0, st>>>(count, d_u, d_v, (const i64 *)d_wbin, nullptr, height, qpx, gh, B, nullptr, cursor,
-                                                                  d_send, d_sidx);
+        rt_route_kernel<3, true><<<blocks, 256, 0, st>>>(count, d_u, d_v, (const i64 *)d_wbin, nullptr, height, qpx, gh, B, nullptr, bases, S, d_send, d_sidx);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }

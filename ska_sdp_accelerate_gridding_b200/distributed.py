@@ -67,6 +67,22 @@ def balanced_slab_bounds(row_hist: torch.Tensor, world: int):
     return bounds
 
 
+def weighted_slab_bounds(row_cost: torch.Tensor, world: int):
+    """Row slabs of (nearly) equal total cost: bounds at the k/world quantiles of the cumulative per-row cost (any
+    non-negative float tensor, e.g. visibility counts scaled by a measured cost per visibility).  Every slab keeps at least
+    one row."""
+    height = int(row_cost.numel())
+    cum = torch.cumsum(row_cost.to(torch.float64).cpu(), 0)
+    total = float(cum[-1].item())
+    bounds = [0]
+    for g in range(1, world):
+        b = int(torch.searchsorted(cum, torch.tensor([total * g / world], dtype=torch.float64), right=True).item())
+        b = min(max(b, bounds[-1] + 1), height - (world - g))
+        bounds.append(b)
+    bounds.append(height)
+    return bounds
+
+
 def owners_of_rows(y0: torch.Tensor, gh: int, bounds: Sequence[int]):
     """For footprints covering rows [y0, y0+gh): first and last owning rank (clamped to the grid).  Integer only.
     Returns (lo, hi, on_grid)."""
@@ -449,7 +465,48 @@ class TileShardedGridder:
         dv.row_hist_(self.h, self.table.shape[-3], self.table.shape[-2], v, hist)
         if self.world > 1:
             dist.all_reduce(hist, group=self.group)
+        self._row_hist = hist
         self.set_bounds(balanced_slab_bounds(hist, self.world))
+        return self.bounds
+
+    def rebalance(self, seconds):
+        """Collective, after `balance` and a measured pass: `seconds` is what this rank's work on its current slab took
+        (binning, gridding, the row transforms of the image stage, degridding).  Equal visibility counts do not mean equal
+        time: a slab costs  alpha * visibilities + beta * non-empty rows  (the dense core rows are cheap per visibility, the
+        sparse outer ones pay per row: tiles to zero and flush, rows to transform).  alpha and beta are fitted (least squares)
+        to every measurement so far -- one equation per rank and round -- and the bounds move to the equal-cost quantiles of
+        alpha * hist[row] + beta * [hist[row] > 0].  Falls back to scaling each slab's rows by its own measured cost per
+        visibility when the fit is degenerate.  Returns the new bounds."""
+        import numpy as np
+        t = torch.tensor([float(seconds)], dtype=torch.float64, device=self._row_hist.device)
+        every = torch.empty(self.world, dtype=torch.float64, device=t.device)
+        if self.world > 1:
+            dist.all_gather_into_tensor(every, t, group=self.group)
+        else:
+            every.copy_(t)
+        hist = self._row_hist.to(torch.float64).cpu()
+        nonempty = (hist > 0).to(torch.float64)
+        if not hasattr(self, "_fit_rows"):
+            self._fit_rows = []
+        times = every.tolist()
+        for g, tg in enumerate(times):
+            a, b = self.bounds[g], self.bounds[g + 1]
+            self._fit_rows.append((float(hist[a:b].sum()), float(nonempty[a:b].sum()), tg))
+        A = np.array([[n, r] for n, r, _ in self._fit_rows])
+        y = np.array([tg for _, _, tg in self._fit_rows])
+        cost = None
+        if len(self._fit_rows) >= 2:
+            (alpha, beta), *_ = np.linalg.lstsq(A, y, rcond=None)
+            if alpha > 0 and beta >= 0:
+                cost = alpha * hist + beta * nonempty
+        if cost is None:
+            cost = torch.zeros_like(hist)
+            for g, tg in enumerate(times):
+                a, b = self.bounds[g], self.bounds[g + 1]
+                n = float(hist[a:b].sum())
+                if n > 0:
+                    cost[a:b] = hist[a:b] * (tg / n)
+        self.set_bounds(weighted_slab_bounds(cost, self.world))
         return self.bounds
 
     def route(self, u, v, wbin, vis=None, keep_index=False):

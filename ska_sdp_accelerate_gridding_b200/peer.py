@@ -95,7 +95,7 @@ class PeerGroup:
         self.flags = PeerBuffer(self, 4096)
         self._flag_ptrs = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.flags.ptrs])
         self.epoch = 0
-        self.streams = [torch.cuda.Stream() for _ in range(max(1, min(self.world - 1, 8)))]
+        self.streams = [torch.cuda.Stream() for _ in range(max(4, min(self.world - 1, 8)))]
         self._fork = torch.cuda.Event()
 
     def barrier(self):
@@ -121,7 +121,17 @@ class PeerGroup:
         self._fork.record(main)
         lib, h = self.ctx.lib, self.ctx.h
         used = set()
-        for i, c in enumerate(copies):
+        # large contiguous copies are cut into pieces so that several copy engines work on them when there are few peers
+        pieces = []
+        for c in copies:
+            if len(c) == 3 and c[2] > (256 << 20) and len(copies) < len(self.streams):
+                k = min(4, len(self.streams))
+                step = (-(-c[2] // k) + 255) // 256 * 256
+                for off in range(0, c[2], step):
+                    pieces.append((c[0] + off, c[1] + off, min(step, c[2] - off)))
+            else:
+                pieces.append(c)
+        for i, c in enumerate(pieces):
             s = self.streams[i % len(self.streams)]
             if i < len(self.streams):
                 s.wait_event(self._fork)

@@ -134,6 +134,24 @@ def test_balanced_slab_bounds():
     assert b2[0] == 0 and b2[-1] == 64 and all(b2[i] < b2[i + 1] for i in range(8))
 
 
+def test_weighted_slab_bounds_and_active_rows():
+    cost = torch.zeros(1000, dtype=torch.float64)
+    cost[500:520] = 50.0         # cheap dense core rows ...
+    cost[520:1000] = 4.0         # ... expensive sparse ones
+    b = D.weighted_slab_bounds(cost, 4)
+    assert b[0] == 0 and b[-1] == 1000 and all(b[i] < b[i + 1] for i in range(4))
+    parts = [float(cost[b[i]:b[i + 1]].sum()) for i in range(4)]
+    assert max(parts) - min(parts) <= 2 * 50.0
+    assert D.weighted_slab_bounds(torch.zeros(16, dtype=torch.float64), 4)[-1] == 16   # degenerate: still valid bounds
+    # active rows: clamped to the grid and widened to equal slabs inside it
+    assert D.active_row_slabs(8192, 4088, 8192, 8) == (4088, 513)
+    lo, m = D.active_row_slabs(100, 90, 100, 4)
+    assert lo + 4 * m <= 100 and lo <= 90 and lo + 4 * m >= 100
+    assert D.active_row_slabs(64, 10, 5, 2) == (0, 1)                  # empty interval
+    with pytest.raises(ValueError):
+        D.active_row_slabs(4, 0, 4, 8)
+
+
 def _transpose_worker(rank, world, port, ret):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

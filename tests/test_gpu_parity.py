@@ -291,6 +291,30 @@ def test_aw_gridding_end_to_end(G, orc):
     assert abs(lhs - rhs) < 1e-10 * abs(lhs)
 
 
+def test_aw_gridding_config1_shape(G, orc):
+    """BASELINE.json configs 1-3 at THEIR shape (src/ImageDataset.hs:32-33: theta 0.008 x lam 300000 = a 2400^2 grid; S = 15, Q = 8,
+    64 w-planes, 64 antennas: the R' stand-in of SURVEY 8d, generated by scripts/bench_aw.py) against the oracle, image and grid;
+    2400 = 2^5 * 3 * 5^2 exercises the non-power-of-two transform and the 16-cell tile edge that does not divide the grid."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts"))
+    import bench_aw
+    from ska_sdp_accelerate_gridding_b200 import image_dataset as D
+    cnt = 2500
+    wk, wbins, ak, uvw_m, a1, a2, freq, vis = bench_aw.standin(cnt)
+    mx, img, grd = D.aw_gridding_arrays(bench_aw.THETA, bench_aw.LAM, wk, wbins, ak, uvw_m, a1, a2, freq, vis, want_grid=True)
+    assert img.shape == (2400, 2400)
+    oimg, omx, ogrid = orc.aw_gridding(bench_aw.THETA, bench_aw.LAM, wk, wbins, ak, uvw_m[:, 0], uvw_m[:, 1], uvw_m[:, 2], a1, a2, freq, vis)
+    assert rel_err(grd, ogrid) < TOL
+    assert rel_err(img, oimg) < TOL
+    assert abs(mx - omx) <= TOL * abs(omx)
+    # config 3: degridding of the model grid at the same coordinates (exact adjoint of the AW gridder, SURVEY 8c)
+    u, v, w = orc.uvw_lambda(freq, uvw_m[:, 0], uvw_m[:, 1], uvw_m[:, 2])
+    wb = orc.find_closest(wbins, w)
+    lam = float(bench_aw.LAM)
+    d = G.convdegrid3(wk, ak, ogrid, (u / lam, v / lam), (wb, a1, a2))
+    assert rel_err(d, orc.convdegrid_aw(wk, ak, ogrid, u / lam, v / lam, wb, a1, a2)) < TOL
+
+
 # ------------------------------------------------------------------------------------------------ grid -> image
 @pytest.mark.parametrize("n", [8, 9, 240, 255, 2400])
 def test_hermitian_fft_image(G, orc, n):
