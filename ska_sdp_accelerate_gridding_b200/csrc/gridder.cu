@@ -49,6 +49,28 @@ struct GridArgs {
 
 __device__ __forceinline__ double2 ldg2(const double2 *p) { return __ldg(p); }
 
+// Kernel-tap load.  The taps stream out of the L2-resident table with ~1-3 % L1 hits, and ncu shows the dense gridder at 96 %
+// of the L1TEX pipe (profiles/r02_ncu_summary.txt): LD selects how the miss is handled --
+//   0  ld.global.nc (LDG.CONSTANT): allocates the line in L1 (r01 behaviour)
+//   1  ld.global.cg: cached in L2 only
+//   2  ld.global.nc.L1::no_allocate: read-only path, no L1 allocation
+template <int LD>
+__device__ __forceinline__ double2 ld_tap(const double2 *p) {
+    if constexpr (LD == 1) {
+        return __ldcg(p);
+    } else if constexpr (LD == 2) {
+        double2 v;
+        asm("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+        return v;
+    } else {
+        return __ldg(p);
+    }
+}
+static int tap_load_mode() {
+    static const int m = getenv("SKAGRID_TAP_LOAD") ? atoi(getenv("SKAGRID_TAP_LOAD")) : 0;
+    return (m == 1 || m == 2) ? m : 0;
+}
+
 __device__ __forceinline__ void red_add(double *addr, double v) {
     asm volatile("red.global.add.f64 [%0], %1;" ::"l"(addr), "d"(v) : "memory");
 }
@@ -306,7 +328,7 @@ template <int R, int TY> struct DenseCfg {
     static constexpr int min_blocks = R == 16 ? (TY == 8 ? 8 : (TY == 4 ? 10 : 4)) : 2;
 };
 
-template <int R, int MT, int TY>
+template <int R, int MT, int TY, int LD = 0>
 __global__ void __launch_bounds__(16 * TY, DenseCfg<R, TY>::min_blocks) grid_dense_kernel(const GridArgs A) {
     constexpr int CY = R / TY, CX = R / 16;  // residues per thread
     constexpr int NT = 16 * TY;
@@ -379,7 +401,7 @@ __global__ void __launch_bounds__(16 * TY, DenseCfg<R, TY>::min_blocks) grid_den
 #pragma unroll
             for (int a = 0; a < CY; ++a)
 #pragma unroll
-                for (int b = 0; b < CX; ++b) s.k[a][b] = ldg2(tp[a][b] + m.x);
+                for (int b = 0; b < CX; ++b) s.k[a][b] = ld_tap<LD>(tp[a][b] + m.x);
         };
         auto consume = [&](const uint4 *buf, uint32_t j, const Slot &s) {
             const double2 vis = *reinterpret_cast<const double2 *>(&buf[2 * j]);
@@ -625,7 +647,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) degrid_tile_kernel(const GridAr
 // does not change.  In dense uv regions hundreds of consecutive visibilities share the origin, so the per-visibility
 // work is just the tap stream: gh 128-bit loads and 4*gh FMAs per lane -- half of the L1/shared-memory wavefronts of
 // the tiled kernel, which is bound by exactly that pipe.
-template <int GH, int NT, int MINB, bool EXACT>
+template <int GH, int NT, int MINB, bool EXACT, int LD = 0>
 __global__ void __launch_bounds__(NT, MINB) degrid_reg_kernel(const GridArgs A) {
     // EXACT: gh == GH, so the row loops carry no predicate; the padded table (pitch 16 >= gw, zero pad columns) lets every
     // lane load its tap unconditionally, lanes >= gw just read the pad
@@ -695,7 +717,7 @@ __global__ void __launch_bounds__(NT, MINB) degrid_reg_kernel(const GridArgs A) 
                     const double2 *kp = A.table + (uint32_t)(kb + dy * (uint32_t)A.kpitch + dx + (uint32_t)hl);
                     double2 k[GH];
 #pragma unroll
-                    for (int i = 0; i < GH; ++i) k[i] = (EXACT || i < A.gh) ? ldg2(kp + i * 16) : make_double2(0.0, 0.0);  // kpitch == 16 here: immediate offsets
+                    for (int i = 0; i < GH; ++i) k[i] = (EXACT || i < A.gh) ? ld_tap<LD>(kp + i * 16) : make_double2(0.0, 0.0);  // kpitch == 16 here: immediate offsets
 #pragma unroll
                     for (int i = 0; i < GH; ++i) {  // conj(k) * g
                         ar = fma(k[i].x, g[i].x, ar); ar = fma(k[i].y, g[i].y, ar);
@@ -792,16 +814,16 @@ static int launch_tiled(skagrid_ctx *ctx, const GridArgs &A, cudaStream_t st) {
     return SKAGRID_OK;
 }
 
-template <int R, int MT, int TY>
+template <int R, int MT, int TY, int LD = 0>
 static int launch_dense(skagrid_ctx *ctx, const GridArgs &A, cudaStream_t st) {
     constexpr int NT = 16 * TY;
     const size_t smem = (size_t)A.SG * A.SG * sizeof(double2);
-    if (ctx->smem_configured.insert((const void *)grid_dense_kernel<R, MT, TY>).second)
-        SK_CUDA(ctx, cudaFuncSetAttribute(grid_dense_kernel<R, MT, TY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (ctx->smem_configured.insert((const void *)grid_dense_kernel<R, MT, TY, LD>).second)
+        SK_CUDA(ctx, cudaFuncSetAttribute(grid_dense_kernel<R, MT, TY, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int per_sm = 0;
-    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_dense_kernel<R, MT, TY>, NT, smem));
+    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_dense_kernel<R, MT, TY, LD>, NT, smem));
     if (per_sm < 1) return sk_fail(ctx, SKAGRID_ECUDA, "dense gridder does not fit on an SM (smem %zu)", smem);
-    grid_dense_kernel<R, MT, TY><<<ctx->sm_count * per_sm, NT, smem, st>>>(A);
+    grid_dense_kernel<R, MT, TY, LD><<<ctx->sm_count * per_sm, NT, smem, st>>>(A);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
@@ -831,9 +853,13 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
         if (R == 16) {
             if (variant == 5) return MT == 2 ? launch_dense<16, 2, 4>(ctx, A, st) : launch_dense<16, 4, 4>(ctx, A, st);
             if (variant == 6) return MT == 2 ? launch_dense<16, 2, 16>(ctx, A, st) : launch_dense<16, 4, 16>(ctx, A, st);  // 16x16 threads, one residue each
+            if (MT == 2 && tap_load_mode() == 1) return launch_dense<16, 2, 8, 1>(ctx, A, st);
+            if (MT == 2 && tap_load_mode() == 2) return launch_dense<16, 2, 8, 2>(ctx, A, st);
             return MT == 2 ? launch_dense<16, 2, 8>(ctx, A, st) : launch_dense<16, 4, 8>(ctx, A, st);
         }
         if (variant == 5) return MT == 2 ? launch_dense<32, 2, 32>(ctx, A, st) : launch_dense<32, 4, 32>(ctx, A, st);
+        if (MT == 2 && tap_load_mode() == 1) return launch_dense<32, 2, 16, 1>(ctx, A, st);
+        if (MT == 2 && tap_load_mode() == 2) return launch_dense<32, 2, 16, 2>(ctx, A, st);
         return MT == 2 ? launch_dense<32, 2, 16>(ctx, A, st) : launch_dense<32, 4, 16>(ctx, A, st);
     }
     // variants (A/B measurements on B200; 1e8 visibilities, config 4, per launch):
@@ -880,6 +906,12 @@ extern "C" int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const do
         if (A.gh == 15 && variant == 4) {
             SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_reg_kernel<15, 128, 5, true>, 128, tile_smem));
             degrid_reg_kernel<15, 128, 5, true><<<ctx->sm_count * (per_sm < 1 ? 1 : per_sm), 128, tile_smem, st>>>(A);
+        } else if (A.gh == 15 && tap_load_mode() == 1) {
+            SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_reg_kernel<15, 128, 4, true, 1>, 128, tile_smem));
+            degrid_reg_kernel<15, 128, 4, true, 1><<<ctx->sm_count * (per_sm < 1 ? 1 : per_sm), 128, tile_smem, st>>>(A);
+        } else if (A.gh == 15 && tap_load_mode() == 2) {
+            SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_reg_kernel<15, 128, 4, true, 2>, 128, tile_smem));
+            degrid_reg_kernel<15, 128, 4, true, 2><<<ctx->sm_count * (per_sm < 1 ? 1 : per_sm), 128, tile_smem, st>>>(A);
         } else if (A.gh == 15) {
             SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, degrid_reg_kernel<15, 128, 4, true>, 128, tile_smem));
             degrid_reg_kernel<15, 128, 4, true><<<ctx->sm_count * (per_sm < 1 ? 1 : per_sm), 128, tile_smem, st>>>(A);

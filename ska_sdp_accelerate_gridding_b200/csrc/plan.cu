@@ -146,8 +146,10 @@ __global__ void __launch_bounds__(256) bin_hist_kernel(BinParams P, i64 count, c
 // stores): the kernel is bound by the latency of random DRAM / L2 accesses at full occupancy (ncu: every warp on the
 // long scoreboard, DRAM at 28 %), so the only lever is more independent accesses in flight per thread.
 constexpr int SCATTER_U = 4;
-template <int ES>
-__global__ void __launch_bounds__(256) bin_scatter_kernel(BinParams P, i64 count, const double *__restrict__ u,
+// MINB: resident blocks per SM the register allocation must allow.  ncu (profiles/r02_ncu_summary.txt): 62 registers -> 4 blocks
+// -> 49 % of the warp slots, every warp on the long scoreboard: the kernel wants more random accesses in flight.
+template <int ES, int MINB = 4>
+__global__ void __launch_bounds__(256, MINB) bin_scatter_kernel(BinParams P, i64 count, const double *__restrict__ u,
                                                           const double *__restrict__ v, const i64 *__restrict__ wbin,
                                                           const double *__restrict__ vis, uint32_t *__restrict__ offs,
                                                           VisRec *__restrict__ rec) {
@@ -324,7 +326,10 @@ static int plan_fill(skagrid_ctx *ctx, skagrid_plan *p, i64 count, const double 
     scan_apply<<<(unsigned)nb, SCAN_T, 0, st>>>(p->d_offs, n, p->d_blocksums);
     SK_LAUNCH_CHECK(ctx);
     if (count > 0) {
-        if (es == 1) bin_scatter_kernel<1><<<blocks, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
+        static const int occ = getenv("SKAGRID_SCATTER_OCC") ? atoi(getenv("SKAGRID_SCATTER_OCC")) : 0;  // tuning experiments
+        if (es == 1 && occ == 6) bin_scatter_kernel<1, 6><<<ctx->sm_count * 6, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
+        else if (es == 1 && occ == 8) bin_scatter_kernel<1, 8><<<ctx->sm_count * 8, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
+        else if (es == 1) bin_scatter_kernel<1><<<blocks, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
         else if (es == 3) bin_scatter_kernel<3><<<blocks, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
         else bin_scatter_kernel<5><<<blocks, 256, 0, st>>>(P, count, u, v, wbin, vis, p->d_offs, p->d_rec);
         SK_LAUNCH_CHECK(ctx);
