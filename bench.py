@@ -462,7 +462,7 @@ def run_config5(env, args):
     ts = D.TileShardedGridder(N5, N5, table, check=False)
     bounds = ts.balance(v)   # once per data set: slabs with equal visibility counts (the uv coverage is known up front) ...
     calib = []
-    for _ in range(2 if world > 1 else 0):   # ... then with equal measured gridding + degridding time (dense core slabs are cheaper per visibility)
+    for _ in range(4 if world > 1 else 0):   # ... then with equal measured time per slab (dense core slabs are cheaper per visibility)
         recs, _ = ts.route(u, v, wb, vis)
         tmp = torch.zeros((ts.rows[1] - ts.rows[0], N5), dtype=torch.complex128, device=env.dev)
         part = torch.empty(recs.shape[0], dtype=torch.complex128, device=env.dev)
@@ -480,10 +480,10 @@ def run_config5(env, args):
         pl.degrid(table, tmp, part)
         b.record()
         torch.cuda.synchronize()
-        calib.append(env.max_over_ranks(a.elapsed_time(b)))
         del tmp, part, recs, rows_nz
         ts._last_rec = None
         bounds = ts.rebalance(a.elapsed_time(b) * 1e-3)
+        calib.append([round(x * 1e3, 1) for x in ts.last_times])
     peer = env.pg is not None
     if peer:
         slab = ts.enable_peer(env.pg, send_capacity=int(V * 1.15) + 4096, recv_capacity=int(V * 1.3) + 4096)
@@ -567,8 +567,9 @@ def run_config5(env, args):
         "config": {"workload": f"config 5: {N5}^2 c128 grid, support {S5}, oversampling {QPX}, {NW5} w-planes, uv-tile-sharded (row slabs balanced by "
                                "the row histogram, routing by hand-written count/pack kernels + one all-to-all, no grid reduce)",
                    "vis_per_gpu_per_step": V, "vis_total_per_step": V * world, "routed_records": routed, "slab_bounds": bounds,
-                   "slab_balance": "row-histogram quantiles, then two rounds of re-weighting by the measured gridding+degridding time per slab"
-                                   f" (slowest rank before each round: {[round(x, 1) for x in calib]} ms)",
+                   "slab_balance": "row-histogram quantiles, then rounds of re-weighting the rows by the measured time per slab (binning, gridding, row "
+                                   "transforms, degridding); ms per rank before each round in slab_balance_rounds_ms",
+                   "slab_balance_rounds_ms": calib,
                    "nonzero_rows_rank0": list(nz),
                    "step": "route (count, pack, all-to-all) -> bin+bucket -> tiled gridder into the owned slab -> slab grid->image -> degridder on the "
                            "owned rows -> all-to-all of the partial sums -> scatter-add"},

@@ -60,6 +60,31 @@ __global__ void ipc_barrier_kernel(IpcFlags F, uint32_t epoch, uint32_t *err_fla
     atomicOr(err_flag, 4u);  // a peer never arrived (bit 2 of the context's error word): do not hang the device forever
 }
 
+// dst[s][i] = src[s][i] for every segment s: the SMs pull from peer memory (8-byte elements: routed records are 24 or 40 bytes
+// long, so segments are only 8-byte aligned).  Several times the rate of a copy-engine pull per peer on this box
+// (profiles/r02_config5_substages.md).
+struct IpcSegs {
+    const double *src[IPC_MAX];
+    double *dst[IPC_MAX];
+    long long n[IPC_MAX];
+    int count;
+};
+__global__ void __launch_bounds__(256) ipc_gather_kernel(IpcSegs S) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int s = 0; s < S.count; ++s) {
+        const double *__restrict__ src = S.src[s];
+        double *__restrict__ dst = S.dst[s];
+        const i64 n = S.n[s];
+        i64 i = t;
+        for (; i + 3 * stride < n; i += 4 * stride) {  // four independent loads in flight per thread
+            const double a = __ldcv(src + i), b = __ldcv(src + i + stride), c = __ldcv(src + i + 2 * stride), d = __ldcv(src + i + 3 * stride);
+            dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+        }
+        for (; i < n; i += stride) dst[i] = __ldcv(src + i);
+    }
+}
+
 extern "C" int skagrid_ipc_alloc(skagrid_ctx *ctx, int64_t bytes, void **d_ptr, unsigned char handle[64]) {
     SK_TRY(sk_api_enter(ctx));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
@@ -121,6 +146,31 @@ extern "C" int skagrid_dev_peer_sum(skagrid_ctx *ctx, int npeers, const double *
     }
     const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((ncomplex + 255) / 256, (i64)ctx->sm_count * 8));
     ipc_sum_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(reinterpret_cast<double2 *>(d_own), P, ncomplex);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_dev_peer_gather(skagrid_ctx *ctx, int nseg, void *const *d_dst, const void *const *d_src, const int64_t *bytes, void *stream) {
+    SK_TRY(sk_api_enter(ctx));
+    if (nseg < 0 || nseg > IPC_MAX) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather: 0..%d segments", IPC_MAX);
+    if (nseg == 0) return SKAGRID_OK;
+    if (!d_dst || !d_src || !bytes) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather: NULL argument");
+    IpcSegs S;
+    S.count = 0;
+    i64 total = 0;
+    for (int k = 0; k < nseg; ++k) {
+        if (bytes[k] <= 0) continue;
+        if (!d_dst[k] || !d_src[k]) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather: segment %d is NULL", k);
+        if ((bytes[k] & 7) || ((uintptr_t)d_dst[k] & 7) || ((uintptr_t)d_src[k] & 7)) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather: segment %d is not 8-byte aligned", k);
+        S.src[S.count] = static_cast<const double *>(d_src[k]);
+        S.dst[S.count] = static_cast<double *>(d_dst[k]);
+        S.n[S.count] = bytes[k] / 8;
+        total += bytes[k] / 8;
+        ++S.count;
+    }
+    if (S.count == 0) return SKAGRID_OK;
+    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 8));
+    ipc_gather_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(S);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }

@@ -95,7 +95,9 @@ class PeerGroup:
         self.flags = PeerBuffer(self, 4096)
         self._flag_ptrs = (C.c_void_p * self.world)(*[C.c_void_p(p) for p in self.flags.ptrs])
         self.epoch = 0
-        self.streams = [torch.cuda.Stream() for _ in range(max(4, min(self.world - 1, 8)))]
+        ns = max(4, min(self.world - 1, 8))
+        self.pools = [[torch.cuda.Stream() for _ in range(ns)] for _ in range(2)]   # two pools: pulls of different pools never queue behind each other
+        self.streams = self.pools[0]
         self._fork = torch.cuda.Event()
 
     def barrier(self):
@@ -112,36 +114,49 @@ class PeerGroup:
         arr = (C.c_void_p * max(len(others), 1))(*[C.c_void_p(p) for p in others])
         self.ctx.check(self.ctx.lib.skagrid_dev_peer_sum(self.ctx.h, len(others), arr, C.c_void_p(buf.local + offset_bytes), int(ncomplex), _stream()))
 
-    def pull(self, copies, join=True):
+    def gather(self, copies):
+        """copies: iterable of (dst address, src address, bytes), 8-byte aligned: ONE kernel on the current stream in which the
+        SMs pull every segment out of peer memory (skagrid_dev_peer_gather).  For bulk moves nothing overlaps with."""
+        copies = [c for c in copies if c[2] > 0]
+        if not copies:
+            return
+        n = len(copies)
+        dst = (C.c_void_p * n)(*[C.c_void_p(c[0]) for c in copies])
+        src = (C.c_void_p * n)(*[C.c_void_p(c[1]) for c in copies])
+        nb = (C.c_int64 * n)(*[int(c[2]) for c in copies])
+        self.ctx.check(self.ctx.lib.skagrid_dev_peer_gather(self.ctx.h, n, dst, src, nb, _stream()))
+
+    def pull(self, copies, join=True, pool=0):
         """copies: iterable of (dst address, src address, bytes) or (dst, dpitch, src, spitch, width_bytes, rows): enqueued
         round-robin on the side streams after everything already on the current stream.  join=True: the current stream
         waits for them; join=False: returns an object whose wait() does that later (the pulls overlap what is enqueued on
-        the current stream in between)."""
+        the current stream in between).  pool: which of the two stream pools carries the copies."""
         main = torch.cuda.current_stream()
         self._fork.record(main)
         lib, h = self.ctx.lib, self.ctx.h
+        streams = self.pools[pool]
         used = set()
         # large contiguous copies are cut into pieces so that several copy engines work on them when there are few peers
         pieces = []
         for c in copies:
-            if len(c) == 3 and c[2] > (256 << 20) and len(copies) < len(self.streams):
-                k = min(4, len(self.streams))
+            if len(c) == 3 and c[2] > (256 << 20) and len(copies) < len(streams):
+                k = min(4, len(streams))
                 step = (-(-c[2] // k) + 255) // 256 * 256
                 for off in range(0, c[2], step):
                     pieces.append((c[0] + off, c[1] + off, min(step, c[2] - off)))
             else:
                 pieces.append(c)
         for i, c in enumerate(pieces):
-            s = self.streams[i % len(self.streams)]
-            if i < len(self.streams):
+            s = streams[i % len(streams)]
+            if i < len(streams):
                 s.wait_event(self._fork)
-            used.add(i % len(self.streams))
+            used.add(i % len(streams))
             sp = C.c_void_p(s.cuda_stream)
             if len(c) == 3:
                 self.ctx.check(lib.skagrid_dev_peer_copy(h, C.c_void_p(c[0]), C.c_void_p(c[1]), int(c[2]), sp))
             else:
                 self.ctx.check(lib.skagrid_dev_peer_copy2d(h, C.c_void_p(c[0]), int(c[1]), C.c_void_p(c[2]), int(c[3]), int(c[4]), int(c[5]), sp))
-        pending = _Pending([self.streams[i] for i in sorted(used)])
+        pending = _Pending([streams[i] for i in sorted(used)])
         if join:
             pending.wait()
             return None

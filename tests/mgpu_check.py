@@ -103,7 +103,7 @@ def main():
     img2, (c0, c1), mx2 = D.slab_grid_to_image(hslab, ts.bounds, nonzero=nz)
     himg = np.real(orc.ifft(orc.make_grid_hermitian(hfull)))
     err_t = max(err_t, np.abs(img2.cpu().numpy() - himg[:, c0:c1]).max() / np.abs(himg).max(), abs(mx2 - himg.max()) / abs(himg.max()))
-    if nz[0] < min(r1, n // 2 - s // 2 - 1):
+    if nz[1] > nz[0] and nz[0] < n // 2 - s // 2 - 1:
         err_t = 1.0  # v >= 0: no row below the centre minus half a kernel can be non-zero
     # doweight over sharded visibilities: counts all-reduced between the two phases (bit-exact: integer counts, one division)
     theta, lam = 0.01, n * 100
