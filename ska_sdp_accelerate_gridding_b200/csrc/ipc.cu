@@ -61,8 +61,8 @@ __global__ void ipc_barrier_kernel(IpcFlags F, uint32_t epoch, uint32_t *err_fla
 }
 
 // dst[s][i] = src[s][i] for every segment s: the SMs pull from peer memory (8-byte elements: routed records are 24 or 40 bytes
-// long, so segments are only 8-byte aligned).  Several times the rate of a copy-engine pull per peer on this box
-// (profiles/r02_config5_substages.md).
+// long, so segments are only 8-byte aligned).  Alternative to the copy-engine pulls (peer_copy); which one is faster is a
+// measurement (profiles/r02_config5_substages.md).
 struct IpcSegs {
     const double *src[IPC_MAX];
     double *dst[IPC_MAX];
@@ -82,6 +82,36 @@ __global__ void __launch_bounds__(256) ipc_gather_kernel(IpcSegs S) {
             dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
         }
         for (; i < n; i += stride) dst[i] = __ldcv(src + i);
+    }
+}
+
+// Strided form, 16-byte elements: dst[s][r * dpitch + c] = src[s][r * spitch + c] for r < rows, c < width (all in complex128
+// units).  The transpose of the slab-distributed grid -> image: every rank pulls its column block of every peer's rows.
+struct IpcSegs2d {
+    const double2 *src[IPC_MAX];
+    double2 *dst[IPC_MAX];
+    long long rows[IPC_MAX], spitch[IPC_MAX];
+    long long width, dpitch;
+    int count;
+};
+__global__ void __launch_bounds__(256) ipc_gather2d_kernel(IpcSegs2d S) {
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int s = 0; s < S.count; ++s) {
+        const double2 *__restrict__ src = S.src[s];
+        double2 *__restrict__ dst = S.dst[s];
+        const i64 n = S.rows[s] * S.width, sp = S.spitch[s];
+        i64 i = t;
+        for (; i + stride < n; i += 2 * stride) {  // two independent loads in flight per thread
+            const i64 r0 = i / S.width, c0 = i - r0 * S.width, j = i + stride, r1 = j / S.width, c1 = j - r1 * S.width;
+            const double2 a = __ldcv(src + r0 * sp + c0), b = __ldcv(src + r1 * sp + c1);
+            dst[r0 * S.dpitch + c0] = a;
+            dst[r1 * S.dpitch + c1] = b;
+        }
+        for (; i < n; i += stride) {
+            const i64 r0 = i / S.width, c0 = i - r0 * S.width;
+            dst[r0 * S.dpitch + c0] = __ldcv(src + r0 * sp + c0);
+        }
     }
 }
 
@@ -171,6 +201,35 @@ extern "C" int skagrid_dev_peer_gather(skagrid_ctx *ctx, int nseg, void *const *
     if (S.count == 0) return SKAGRID_OK;
     const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 8));
     ipc_gather_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(S);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
+// All segments share the destination pitch and the width (one column block); pitches and width in BYTES, multiples of 16.
+extern "C" int skagrid_dev_peer_gather2d(skagrid_ctx *ctx, int nseg, void *const *d_dst, int64_t dpitch, const void *const *d_src,
+                                         const int64_t *spitch, int64_t width_bytes, const int64_t *rows, void *stream) {
+    SK_TRY(sk_api_enter(ctx));
+    if (nseg < 0 || nseg > IPC_MAX) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather2d: 0..%d segments", IPC_MAX);
+    if (nseg == 0 || width_bytes <= 0) return SKAGRID_OK;
+    if (!d_dst || !d_src || !spitch || !rows) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather2d: NULL argument");
+    if ((width_bytes & 15) || (dpitch & 15)) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather2d: width and pitches must be multiples of 16 bytes");
+    IpcSegs2d S;
+    S.count = 0; S.width = width_bytes / 16; S.dpitch = dpitch / 16;
+    i64 total = 0;
+    for (int k = 0; k < nseg; ++k) {
+        if (rows[k] <= 0) continue;
+        if (!d_dst[k] || !d_src[k] || (spitch[k] & 15) || ((uintptr_t)d_dst[k] & 15) || ((uintptr_t)d_src[k] & 15))
+            return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather2d: segment %d is NULL or not 16-byte aligned", k);
+        S.src[S.count] = static_cast<const double2 *>(d_src[k]);
+        S.dst[S.count] = static_cast<double2 *>(d_dst[k]);
+        S.rows[S.count] = rows[k];
+        S.spitch[S.count] = spitch[k] / 16;
+        total += rows[k] * S.width;
+        ++S.count;
+    }
+    if (S.count == 0) return SKAGRID_OK;
+    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 8));
+    ipc_gather2d_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(S);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }

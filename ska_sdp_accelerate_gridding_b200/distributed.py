@@ -295,7 +295,10 @@ def peer_slab_grid_to_image(pg, pbuf, row_base, spans, n, group=None, want_image
         src = pbuf.ptrs[s_] + ((sa - row_base[s_]) * n + c0) * 16
         copies.append((cols.data_ptr() + sa * cw * 16, cw * 16, src, n * 16, cw * 16, sb - sa))
     _mark("image: barrier + zeroed columns")
-    pg.pull(copies)
+    if cw * 16 <= (32 << 10):
+        pg.gather2d(copies)     # short rows (many ranks, small grid): one SM kernel; a strided copy-engine copy pays per row
+    else:
+        pg.pull(copies)
     _mark("image: transpose pulled")
     img, mx = dv.slab_fft_cols_(n, c0, cols, want_image=want_image)
     if P > 1:
@@ -627,7 +630,7 @@ class TileShardedGridder:
             if n:
                 copies.append((rec.data_ptr() + off * W * 8, self.psend.ptrs[s] + seg * W * 8, n * W * 8))
             off += n
-        self.pg.gather(copies)
+        self.pg.bulk(copies)
         _mark("route: pulled")
         return rec, {"sidx": sidx, "cnt": cnt, "offs_in_owner": None}
 
@@ -648,7 +651,7 @@ class TileShardedGridder:
             if n:
                 copies.append((back.data_ptr() + seg * 16, self.ppart.ptrs[g] + off * 16, n * 16))
             seg += n
-        self.pg.gather(copies)
+        self.pg.bulk(copies)
         _mark("return: pulled")
         out = torch.zeros(count, dtype=torch.complex128, device=self.slab.device)
         dv.scatter_add_(out, route["sidx"], back)

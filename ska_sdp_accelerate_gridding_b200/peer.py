@@ -4,6 +4,7 @@ CUDA IPC handles; the data path afterwards is the library's own kernels and cuda
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 import torch.distributed as dist
@@ -114,6 +115,16 @@ class PeerGroup:
         arr = (C.c_void_p * max(len(others), 1))(*[C.c_void_p(p) for p in others])
         self.ctx.check(self.ctx.lib.skagrid_dev_peer_sum(self.ctx.h, len(others), arr, C.c_void_p(buf.local + offset_bytes), int(ncomplex), _stream()))
 
+    # SKAGRID_PEER_PULL = ce | sm: copy engines or SM kernels for the bulk pulls of the uv-tile-sharded mode (A/B measurements)
+    SM_PULL = os.environ.get("SKAGRID_PEER_PULL", "ce") == "sm"
+
+    def bulk(self, copies):
+        """Bulk pull nothing overlaps with: SM gather kernel or copy engines (joined), see SM_PULL."""
+        if self.SM_PULL:
+            self.gather(copies)
+        else:
+            self.pull(copies)
+
     def gather(self, copies):
         """copies: iterable of (dst address, src address, bytes), 8-byte aligned: ONE kernel on the current stream in which the
         SMs pull every segment out of peer memory (skagrid_dev_peer_gather).  For bulk moves nothing overlaps with."""
@@ -125,6 +136,19 @@ class PeerGroup:
         src = (C.c_void_p * n)(*[C.c_void_p(c[1]) for c in copies])
         nb = (C.c_int64 * n)(*[int(c[2]) for c in copies])
         self.ctx.check(self.ctx.lib.skagrid_dev_peer_gather(self.ctx.h, n, dst, src, nb, _stream()))
+
+    def gather2d(self, copies):
+        """copies: iterable of (dst, dpitch, src, spitch, width_bytes, rows) with one common width and destination pitch, 16-byte
+        aligned: ONE kernel on the current stream pulls every block out of peer memory (skagrid_dev_peer_gather2d)."""
+        copies = [c for c in copies if c[5] > 0 and c[4] > 0]
+        if not copies:
+            return
+        n = len(copies)
+        dst = (C.c_void_p * n)(*[C.c_void_p(c[0]) for c in copies])
+        src = (C.c_void_p * n)(*[C.c_void_p(c[2]) for c in copies])
+        sp = (C.c_int64 * n)(*[int(c[3]) for c in copies])
+        rows = (C.c_int64 * n)(*[int(c[5]) for c in copies])
+        self.ctx.check(self.ctx.lib.skagrid_dev_peer_gather2d(self.ctx.h, n, dst, int(copies[0][1]), src, sp, int(copies[0][4]), rows, _stream()))
 
     def pull(self, copies, join=True, pool=0):
         """copies: iterable of (dst address, src address, bytes) or (dst, dpitch, src, spitch, width_bytes, rows): enqueued
