@@ -345,7 +345,9 @@ int skagrid_dev_scatter_add(skagrid_ctx *ctx, int64_t n, const uint32_t *d_sidx,
  * ipc_alloc: a device buffer (zero-filled) plus its 64-byte CUDA IPC handle; the ranks exchange the handles by any means
  * and ipc_open each other's (peer access between the devices is required); ipc_close / ipc_free release them.
  *   peer_sum      d_own[i] += sum_k d_peers[k][i] over `ncomplex` complex values; d_peers is a HOST array of opened peer
- *                 pointers: the reduce-scatter of the visibility-sharded mode (permute (+) is a sum, src/Gridding.hs:377)
+ *                 pointers: the reduce-scatter of the visibility-sharded mode (permute (+) is a sum, src/Gridding.hs:377).
+ *                 broadcast != 0: the sum is also stored to every d_peers[k][i] by the same kernel (reduce-scatter and
+ *                 all-gather fused; every rank must call it on ITS slab between two barriers)
  *   peer_barrier  stream-ordered barrier of `nranks` ranks: d_flags is a HOST array with every rank's flag buffer (at least
  *                 64 uint32, ipc_alloc'ed; entry `rank` is the local one), epoch increases by one per barrier on every
  *                 rank.  A peer that does not arrive within ~30 s sets bit 2 of the device error word (dev_take_error)
@@ -358,8 +360,8 @@ int skagrid_ipc_alloc(skagrid_ctx *ctx, int64_t bytes, void **d_ptr, unsigned ch
 int skagrid_ipc_free(skagrid_ctx *ctx, void *d_ptr);
 int skagrid_ipc_open(skagrid_ctx *ctx, const unsigned char handle[64], void **d_ptr);
 int skagrid_ipc_close(skagrid_ctx *ctx, void *d_ptr);
-int skagrid_dev_peer_sum(skagrid_ctx *ctx, int npeers, const double *const *d_peers, double *d_own, int64_t ncomplex,
-                         void *stream);
+int skagrid_dev_peer_sum(skagrid_ctx *ctx, int npeers, double *const *d_peers, double *d_own, int64_t ncomplex,
+                         int broadcast, void *stream);
 int skagrid_dev_peer_barrier(skagrid_ctx *ctx, int nranks, int rank, uint32_t *const *d_flags, uint32_t epoch,
                              void *stream);
 int skagrid_dev_peer_copy(skagrid_ctx *ctx, void *d_dst, const void *d_src, int64_t bytes, void *stream);

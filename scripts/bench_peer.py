@@ -53,6 +53,7 @@ def main():
     res["sm_pull_ms"] = timed(lambda: pg.gather(pulls))
     res["sm_push_ms"] = timed(lambda: pg.gather(pushes))
     res["peer_sum_ms"] = timed(lambda: pg.peer_sum_(buf, rank * seg, seg // 16))
+    res["peer_sum_bcast_ms"] = timed(lambda: pg.peer_sum_(buf, rank * seg, seg // 16, broadcast=True))
     w, cw = 16384, 16384 // world       # bytes per row of the source, bytes per row pulled (a column block)
     rows = seg // w
     c2d = [(dstbuf.local + p * rows * cw, cw, buf.ptrs[p] + rank * cw, w, cw, rows) for p in others]

@@ -75,7 +75,7 @@ _SIGS = {
     "skagrid_ipc_free": [vp, vp],
     "skagrid_ipc_open": [vp, vp, C.POINTER(vp)],
     "skagrid_ipc_close": [vp, vp],
-    "skagrid_dev_peer_sum": [vp, ip, vp, vp, i64, vp],
+    "skagrid_dev_peer_sum": [vp, ip, vp, vp, i64, ip, vp],
     "skagrid_dev_peer_barrier": [vp, ip, ip, vp, C.c_uint32, vp],
     "skagrid_dev_peer_copy": [vp, vp, vp, i64, vp],
     "skagrid_dev_peer_gather": [vp, ip, vp, vp, vp, vp],

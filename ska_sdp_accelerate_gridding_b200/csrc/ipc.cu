@@ -4,7 +4,8 @@
 // then on the kernels below dereference peer memory directly and the copy engines move slabs between devices.
 //
 //   peer_sum       own[i] += sum over peers of peer[i]   -- the reduce-scatter of the visibility-sharded mode (gridding is
-//                  linear in the visibilities, permute (+), src/Gridding.hs:377): rank r sums row slab r of every peer's grid
+//                  linear in the visibilities, permute (+), src/Gridding.hs:377): rank r sums row slab r of every peer's grid;
+//                  with `broadcast` the same kernel writes the sum back into every peer's grid (all-reduce in one pass)
 //   peer_barrier   stream-ordered barrier between the ranks: a flag per (rank, peer) in peer memory, written with
 //                  st.release.sys, polled with ld.acquire.sys (bounded), so no host thread and no collective is involved
 //   peer_copy(2d)  cudaMemcpyAsync / cudaMemcpy2DAsync between an opened peer buffer and a local one (copy engines over
@@ -17,7 +18,7 @@
 constexpr int IPC_MAX = 64;
 
 struct IpcPeers {
-    const double2 *p[IPC_MAX];
+    double2 *p[IPC_MAX];
     int n;
 };
 struct IpcFlags {
@@ -25,6 +26,10 @@ struct IpcFlags {
     int n, me;
 };
 
+// BCAST: the sum is also written back into every peer's copy -- reduce-scatter and all-gather in ONE kernel: an element is
+// read from and then written to each peer by the same thread, and no other rank touches this rank's slab of anybody's grid,
+// so no ordering beyond the barriers around the kernel is needed; loads and stores travel in opposite NVLink directions.
+template <bool BCAST>
 __global__ void __launch_bounds__(256) ipc_sum_kernel(double2 *own, IpcPeers peers, i64 n) {
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -40,6 +45,8 @@ __global__ void __launch_bounds__(256) ipc_sum_kernel(double2 *own, IpcPeers pee
                 if (k0 + k < peers.n) { a.x += v[k].x; a.y += v[k].y; }
         }
         own[i] = a;
+        if (BCAST)
+            for (int k = 0; k < peers.n; ++k) peers.p[k][i] = a;
     }
 }
 
@@ -163,7 +170,7 @@ extern "C" int skagrid_ipc_close(skagrid_ctx *ctx, void *d_ptr) {
     return SKAGRID_OK;
 }
 
-extern "C" int skagrid_dev_peer_sum(skagrid_ctx *ctx, int npeers, const double *const *d_peers, double *d_own, int64_t ncomplex, void *stream) {
+extern "C" int skagrid_dev_peer_sum(skagrid_ctx *ctx, int npeers, double *const *d_peers, double *d_own, int64_t ncomplex, int broadcast, void *stream) {
     SK_TRY(sk_api_enter(ctx));
     if (npeers < 0 || npeers > IPC_MAX) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_sum: 0..%d peers", IPC_MAX);
     if (ncomplex <= 0 || npeers == 0) return SKAGRID_OK;
@@ -172,10 +179,11 @@ extern "C" int skagrid_dev_peer_sum(skagrid_ctx *ctx, int npeers, const double *
     P.n = npeers;
     for (int k = 0; k < npeers; ++k) {
         if (!d_peers[k]) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_sum: peer %d is NULL", k);
-        P.p[k] = reinterpret_cast<const double2 *>(d_peers[k]);
+        P.p[k] = reinterpret_cast<double2 *>(d_peers[k]);
     }
     const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((ncomplex + 255) / 256, (i64)ctx->sm_count * 8));
-    ipc_sum_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(reinterpret_cast<double2 *>(d_own), P, ncomplex);
+    if (broadcast) ipc_sum_kernel<true><<<blocks, 256, 0, sk_stream(ctx, stream)>>>(reinterpret_cast<double2 *>(d_own), P, ncomplex);
+    else ipc_sum_kernel<false><<<blocks, 256, 0, sk_stream(ctx, stream)>>>(reinterpret_cast<double2 *>(d_own), P, ncomplex);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }

@@ -403,18 +403,20 @@ class VisShardedGridder:
         lo, m = self.active
         return (lo + r * m) * self.w * 16
 
-    def grid_slabs_peer(self, u=None, v=None, wbin=None, vis=None, variant=0):
+    def grid_slabs_peer(self, u=None, v=None, wbin=None, vis=None, variant=0, broadcast=False):
         """Reduce-scatter over NVLink peer memory: grid into the local peer-visible grid, barrier, then ONE kernel on every
         rank sums its row slab of all peers' grids in place (all peers in flight), barrier.  Returns this rank's reduced
-        slab (a view of rows spans()[rank] of `self.work`).  u = None: the plan was already updated by the caller."""
+        slab (a view of rows spans()[rank] of `self.work`).  u = None: the plan was already updated by the caller.
+        broadcast: the summing kernel also stores its slab into every peer's grid -- afterwards `self.work` holds the whole
+        reduced grid on every rank and no gather is needed."""
         lo, m = self.active
         plan = self.plan if u is None else self._plan(u, v, wbin, vis)
         self.pg.barrier()                      # every peer has finished pulling the previous pass's slabs from this grid
         self.work[lo:lo + m * self.world].zero_()
         plan.grid(self.table, self.work, variant=variant)
         self.pg.barrier()                      # all local grids are complete
-        self.pg.peer_sum_(self.pgrid, self._slab_off(self.rank), m * self.w)
-        self.pg.barrier()                      # all slabs are reduced
+        self.pg.peer_sum_(self.pgrid, self._slab_off(self.rank), m * self.w, broadcast=broadcast)
+        self.pg.barrier()                      # all slabs are reduced (and, with broadcast, delivered)
         return self.work[lo + self.rank * m:lo + (self.rank + 1) * m]
 
     def gather_slabs_peer(self, join=True):

@@ -109,11 +109,12 @@ class PeerGroup:
         self.epoch += 1
         self.ctx.check(self.ctx.lib.skagrid_dev_peer_barrier(self.ctx.h, self.world, self.rank, self._flag_ptrs, self.epoch & 0xFFFFFFFF, _stream()))
 
-    def peer_sum_(self, buf: PeerBuffer, offset_bytes: int, ncomplex: int):
-        """local[offset ...] += sum over the other ranks of theirs[offset ...] (complex128 values), one kernel, all peers in flight."""
+    def peer_sum_(self, buf: PeerBuffer, offset_bytes: int, ncomplex: int, broadcast: bool = False):
+        """local[offset ...] += sum over the other ranks of theirs[offset ...] (complex128 values), one kernel, all peers in flight.
+        broadcast: the same kernel stores the sum into every peer's buffer too (reduce-scatter + all-gather fused)."""
         others = [buf.ptrs[k] + offset_bytes for k in range(self.world) if k != self.rank]
         arr = (C.c_void_p * max(len(others), 1))(*[C.c_void_p(p) for p in others])
-        self.ctx.check(self.ctx.lib.skagrid_dev_peer_sum(self.ctx.h, len(others), arr, C.c_void_p(buf.local + offset_bytes), int(ncomplex), _stream()))
+        self.ctx.check(self.ctx.lib.skagrid_dev_peer_sum(self.ctx.h, len(others), arr, C.c_void_p(buf.local + offset_bytes), int(ncomplex), int(bool(broadcast)), _stream()))
 
     # SKAGRID_PEER_PULL = ce | sm: copy engines or SM kernels for the bulk pulls of the uv-tile-sharded mode (A/B measurements)
     SM_PULL = os.environ.get("SKAGRID_PEER_PULL", "ce") == "sm"

@@ -64,14 +64,16 @@ def main():
     vp.enable_peer(pg)
     vp.work.fill_(5.0 - 2j)   # garbage in the active rows must not survive
     vp.work[:vp.active[0]].zero_(); vp.work[vp.active[0] + vp.active[1] * world:].zero_()
-    for _ in range(2):        # twice: the second pass exercises the barrier that protects the gathered grid
-        ps = vp.grid_slabs_peer(lu, lv, lwb, lvis)
+    for it in range(3):       # repeated passes exercise the barrier that protects the gathered grid; the last one is the fused form
+        fused = it == 2       # reduce-scatter + all-gather in one kernel: no gather afterwards
+        ps = vp.grid_slabs_peer(lu, lv, lwb, lvis, broadcast=fused)
         err_p = np.abs(ps.cpu().numpy() - full[a:b]).max() / peak
         pis = PeerBuffer(pg, ps.numel() * 16)
         pis.tensor(torch.complex128, tuple(ps.shape)).copy_(ps)
-        hnd = vp.gather_slabs_peer(join=False)
+        hnd = None if fused else vp.gather_slabs_peer(join=False)
         pimg, (pc0, pc1), pmx = D.peer_slab_grid_to_image(pg, pis, [x[0] for x in vp.spans()], vp.spans(), n)
-        hnd.wait()
+        if hnd is not None:
+            hnd.wait()
         err_p = max(err_p, np.abs(pimg.cpu().numpy() - oimg[:, pc0:pc1]).max() / np.abs(oimg).max(), abs(pmx - oimg.max()) / abs(oimg.max()))
         err_p = max(err_p, np.abs(vp.work.cpu().numpy() - full).max() / peak)
         dp = vp.degrid(vp.work).cpu().numpy()
