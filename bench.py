@@ -338,7 +338,7 @@ class Config4Step:
             pg.barrier()                                   # all local grids complete
             # all-reduce in ONE kernel: every rank sums its slab of all peers' grids (loads over NVLink) and stores the sum back
             # into every peer's grid (stores in the other direction) -- afterwards each rank holds the whole reduced grid
-            fused = not env.args.gather_ce
+            fused = env.world >= 4 and not env.args.gather_ce   # measured: two GPUs are served better by copy-engine pulls, four and more by the fused kernel
             pg.peer_sum_(vs.pgrid, vs._slab_off(env.rank), m * N_GRID, broadcast=fused)
             pg.barrier()                                   # all slabs reduced (and delivered)
             rec(3)

@@ -76,19 +76,21 @@ struct IpcSegs {
     long long n[IPC_MAX];
     int count;
 };
-__global__ void __launch_bounds__(256) ipc_gather_kernel(IpcSegs S) {
+__global__ void __launch_bounds__(256) ipc_gather_kernel(IpcSegs S, long long nmax) {
+    // element i of EVERY segment per trip: one load per peer in flight per thread (a kernel that walks the segments one after
+    // the other reads from one peer at a time: 217 GB/s per rank on 8 GPUs against 635 GB/s for the all-peers-at-once
+    // pattern of ipc_sum_kernel, profiles/r02_peer_primitives_n8.json)
     const i64 stride = (i64)gridDim.x * blockDim.x;
-    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int s = 0; s < S.count; ++s) {
-        const double *__restrict__ src = S.src[s];
-        double *__restrict__ dst = S.dst[s];
-        const i64 n = S.n[s];
-        i64 i = t;
-        for (; i + 3 * stride < n; i += 4 * stride) {  // four independent loads in flight per thread
-            const double a = __ldcv(src + i), b = __ldcv(src + i + stride), c = __ldcv(src + i + 2 * stride), d = __ldcv(src + i + 3 * stride);
-            dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nmax; i += stride) {
+        for (int k0 = 0; k0 < S.count; k0 += 8) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k0 + k < S.count && i < S.n[k0 + k]) v[k] = __ldcv(S.src[k0 + k] + i);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k0 + k < S.count && i < S.n[k0 + k]) S.dst[k0 + k][i] = v[k];
         }
-        for (; i < n; i += stride) dst[i] = __ldcv(src + i);
     }
 }
 
@@ -101,23 +103,19 @@ struct IpcSegs2d {
     long long width, dpitch;
     int count;
 };
-__global__ void __launch_bounds__(256) ipc_gather2d_kernel(IpcSegs2d S) {
+__global__ void __launch_bounds__(256) ipc_gather2d_kernel(IpcSegs2d S, long long rmax) {
     const i64 stride = (i64)gridDim.x * blockDim.x;
-    const i64 t = (i64)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int s = 0; s < S.count; ++s) {
-        const double2 *__restrict__ src = S.src[s];
-        double2 *__restrict__ dst = S.dst[s];
-        const i64 n = S.rows[s] * S.width, sp = S.spitch[s];
-        i64 i = t;
-        for (; i + stride < n; i += 2 * stride) {  // two independent loads in flight per thread
-            const i64 r0 = i / S.width, c0 = i - r0 * S.width, j = i + stride, r1 = j / S.width, c1 = j - r1 * S.width;
-            const double2 a = __ldcv(src + r0 * sp + c0), b = __ldcv(src + r1 * sp + c1);
-            dst[r0 * S.dpitch + c0] = a;
-            dst[r1 * S.dpitch + c1] = b;
-        }
-        for (; i < n; i += stride) {
-            const i64 r0 = i / S.width, c0 = i - r0 * S.width;
-            dst[r0 * S.dpitch + c0] = __ldcv(src + r0 * sp + c0);
+    const i64 nmax = rmax * S.width;
+    for (i64 i = (i64)blockIdx.x * blockDim.x + threadIdx.x; i < nmax; i += stride) {  // element (r, c) of every segment per trip
+        const i64 r = i / S.width, c = i - r * S.width;
+        for (int k0 = 0; k0 < S.count; k0 += 8) {
+            double2 v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k0 + k < S.count && r < S.rows[k0 + k]) v[k] = __ldcv(S.src[k0 + k] + r * S.spitch[k0 + k] + c);
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (k0 + k < S.count && r < S.rows[k0 + k]) S.dst[k0 + k][r * S.dpitch + c] = v[k];
         }
     }
 }
@@ -195,7 +193,7 @@ extern "C" int skagrid_dev_peer_gather(skagrid_ctx *ctx, int nseg, void *const *
     if (!d_dst || !d_src || !bytes) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather: NULL argument");
     IpcSegs S;
     S.count = 0;
-    i64 total = 0;
+    i64 total = 0, nmax = 0;
     for (int k = 0; k < nseg; ++k) {
         if (bytes[k] <= 0) continue;
         if (!d_dst[k] || !d_src[k]) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather: segment %d is NULL", k);
@@ -204,11 +202,13 @@ extern "C" int skagrid_dev_peer_gather(skagrid_ctx *ctx, int nseg, void *const *
         S.dst[S.count] = static_cast<double *>(d_dst[k]);
         S.n[S.count] = bytes[k] / 8;
         total += bytes[k] / 8;
+        nmax = std::max<i64>(nmax, bytes[k] / 8);
         ++S.count;
     }
     if (S.count == 0) return SKAGRID_OK;
-    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 8));
-    ipc_gather_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(S);
+    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((nmax + 255) / 256, (i64)ctx->sm_count * 8));
+    (void)total;
+    ipc_gather_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(S, nmax);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
@@ -223,7 +223,7 @@ extern "C" int skagrid_dev_peer_gather2d(skagrid_ctx *ctx, int nseg, void *const
     if ((width_bytes & 15) || (dpitch & 15)) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather2d: width and pitches must be multiples of 16 bytes");
     IpcSegs2d S;
     S.count = 0; S.width = width_bytes / 16; S.dpitch = dpitch / 16;
-    i64 total = 0;
+    i64 total = 0, rmax = 0;
     for (int k = 0; k < nseg; ++k) {
         if (rows[k] <= 0) continue;
         if (!d_dst[k] || !d_src[k] || (spitch[k] & 15) || ((uintptr_t)d_dst[k] & 15) || ((uintptr_t)d_src[k] & 15))
@@ -233,11 +233,13 @@ extern "C" int skagrid_dev_peer_gather2d(skagrid_ctx *ctx, int nseg, void *const
         S.rows[S.count] = rows[k];
         S.spitch[S.count] = spitch[k] / 16;
         total += rows[k] * S.width;
+        rmax = std::max<i64>(rmax, rows[k]);
         ++S.count;
     }
     if (S.count == 0) return SKAGRID_OK;
-    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((total + 255) / 256, (i64)ctx->sm_count * 8));
-    ipc_gather2d_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(S);
+    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((rmax * S.width + 255) / 256, (i64)ctx->sm_count * 8));
+    (void)total;
+    ipc_gather2d_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(S, rmax);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
