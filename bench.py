@@ -78,7 +78,10 @@ def parse():
     ap.add_argument("--c5-grid", type=int, default=32768)
     ap.add_argument("--allreduce", action="store_true", help="N > 1: full-grid all-reduce + replicated grid -> image (the round-1 step) instead of reduce-scatter + slabs")
     ap.add_argument("--one-group", action="store_true", help="N > 1, --nccl: the image all-to-all shares the NCCL communicator of the all-gather (no overlap between them)")
-    ap.add_argument("--gather-ce", action="store_true", help="N > 1, peer mode: reduce-scatter kernel + copy-engine all-gather instead of the fused sum-and-broadcast kernel")
+    ap.add_argument("--allgather", default="auto", choices=["auto", "fused", "sm", "ce"],
+                    help="N > 1, peer mode, how the reduced slabs reach every rank: fused = the summing kernel also stores its slab into every peer's grid; "
+                         "sm / ce = reduce-scatter kernel, then an all-gather by one SM kernel / by copy-engine pulls overlapping the image stage; "
+                         "auto = ce on 2 GPUs, sm from 4 on (measured)")
     ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL collectives (reduce-scatter, all-gather, all-to-all) for the exchange steps instead of the "
                                                         "library's own peer-memory kernels and copy-engine pulls over NVLink (csrc/ipc.cu)")
     args = ap.parse_args()
@@ -338,12 +341,13 @@ class Config4Step:
             pg.barrier()                                   # all local grids complete
             # all-reduce in ONE kernel: every rank sums its slab of all peers' grids (loads over NVLink) and stores the sum back
             # into every peer's grid (stores in the other direction) -- afterwards each rank holds the whole reduced grid
-            fused = env.world >= 4 and not env.args.gather_ce   # measured: two GPUs are served better by copy-engine pulls, four and more by the fused kernel
+            mode = env.args.allgather if env.args.allgather != "auto" else ("sm" if env.world >= 4 else "ce")
+            fused = mode == "fused"
             pg.peer_sum_(vs.pgrid, vs._slab_off(env.rank), m * N_GRID, broadcast=fused)
             pg.barrier()                                   # all slabs reduced (and delivered)
             rec(3)
             self.islab.copy_(self.slab)
-            h = None if fused else vs.gather_slabs_peer(join=False)   # --gather-ce: all-gather by the copy engines, overlapping the image stage
+            h = None if fused else vs.gather_slabs_peer(join=False, sm=(mode == "sm"))   # all-gather overlapping the image stage
             _, _, mx = D.peer_slab_grid_to_image(pg, self.pislab, [a for a, _ in self.spans], self.spans, N_GRID, want_image=False, sync_max=False)
             self.image_max = mx
             if h is not None:
@@ -787,8 +791,9 @@ def main():
             "step": ("bin+bucket -> tiled gridder -> hermitian+IFFT+real/max -> degridder" if world == 1 else
                      ("bin+bucket -> tiled gridder -> NCCL all-reduce -> hermitian+IFFT+real/max (replicated) -> degridder" if args.allreduce else
                       ("bin+bucket -> tiled gridder -> NCCL reduce-scatter of the active rows -> [slab-distributed grid->image || NCCL all-gather] -> degridder" if args.nccl else
-                       "bin+bucket -> tiled gridder -> peer-memory all-reduce of the active rows (ONE kernel per rank: sums its slab of every peer's grid over NVLink and "
-                       "stores the sum back into every peer's grid) -> slab-distributed grid->image with the transpose pulled from peer memory -> degridder"))),
+                       "bin+bucket -> tiled gridder -> peer-memory reduce-scatter of the active rows (ONE kernel per rank sums its slab of every peer's grid over NVLink) -> "
+                       "[slab-distributed grid->image with the transpose pulled from peer memory || all-gather of the reduced slabs by one SM kernel reading all peers "
+                       f"at once (copy engines on 2 GPUs)] -> degridder; --allgather {args.allgather}"))),
             "exchange": ("none" if world == 1 else ("nccl" if (args.nccl or args.allreduce) else "peer memory over NVLink (CUDA IPC; csrc/ipc.cu): device barrier, peer-sum kernel, copy-engine pulls")),
             "l2": f"inputs ({V * 40 / 1e9:.1f} GB) and grid ({N_GRID * N_GRID * 16 / 1e9:.2f} GB) exceed the 126 MB L2; no explicit flush",
             "gridder_variant": args.variant, "plan": stats,

@@ -7,6 +7,6 @@ timeout 600 $TR --master-port 29511 tests/mgpu_check.py > gpurun_out/r2p_mgpu_ch
 echo "mgpu_check rc=$?" >> gpurun_out/r2p_mgpu_check.log
 timeout 900 $TR --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --skip aw,e2e,config5 > gpurun_out/r2p_n2.json 2> gpurun_out/r2p_n2.err
 echo "bench rc=$?" >> gpurun_out/r2p_mgpu_check.log
-timeout 900 $TR --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --skip aw,e2e,config5,parity --gather-ce > gpurun_out/r2p_n2_ce.json 2> gpurun_out/r2p_n2_ce.err
+timeout 900 $TR --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --skip aw,e2e,config5,parity --allgather ce > gpurun_out/r2p_n2_ce.json 2> gpurun_out/r2p_n2_ce.err
 SKAGRID_PEER_PULL=sm timeout 900 $TR --master-port 29514 bench.py --gpus 2 --steps 3 --warmup 3 --skip aw,e2e,strong,parity > gpurun_out/r2p_n2_c5_sm.json 2> gpurun_out/r2p_n2_c5_sm.err
 grep "world=\|rc=" gpurun_out/r2p_mgpu_check.log; tail -2 gpurun_out/r2p_n2.err

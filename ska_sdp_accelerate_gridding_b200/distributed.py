@@ -419,13 +419,23 @@ class VisShardedGridder:
         self.pg.barrier()                      # all slabs are reduced (and, with broadcast, delivered)
         return self.work[lo + self.rank * m:lo + (self.rank + 1) * m]
 
-    def gather_slabs_peer(self, join=True):
-        """All-gather of the reduced slabs by the copy engines: every rank pulls the other ranks' slabs out of their grids
-        into the same rows of its own.  join=False returns a handle; wait() before reading `self.work`."""
+    def gather_slabs_peer(self, join=True, sm=None):
+        """All-gather of the reduced slabs: every rank pulls the other ranks' slabs out of their grids into the same rows of its
+        own -- by the copy engines (one copy per peer) or, sm=True, by ONE SM kernel that reads all peers at once on a side
+        stream (default from four ranks on: 637 against 270 GB/s per rank on 8 GPUs, the other way round on 2;
+        profiles/r02_peer_primitives_*.json).  join=False returns a handle; wait() before reading `self.work`."""
         lo, m = self.active
         nbytes = m * self.w * 16
         copies = [(self.pgrid.local + self._slab_off(p), self.pgrid.ptrs[p] + self._slab_off(p), nbytes) for p in range(self.world) if p != self.rank]
-        return self.pg.pull(copies, join=join, pool=1)
+        if sm is None:
+            sm = self.world >= 4
+        if not sm:
+            return self.pg.pull(copies, join=join, pool=1)
+        h = self.pg.gather_async(copies)
+        if join:
+            h.wait()
+            return None
+        return h
 
     def degrid(self, grid, u=None, v=None, wbin=None, out=None):
         """Every rank holds the full (model) grid; each degrids its own visibilities.  u = None: at the coordinates of the

@@ -50,6 +50,11 @@ class PeerBuffer:
         """A torch view (no copy) of the LOCAL buffer."""
         itemsize = torch.empty(0, dtype=torch.float64 if dtype == torch.complex128 else dtype).element_size()
         if dtype == torch.complex128:
+            n = 1
+            for s in shape:
+                n *= int(s)
+            if offset_bytes < 0 or offset_bytes + n * 16 > self.nbytes:
+                raise ValueError("view exceeds the peer buffer")
             t = torch.as_tensor(_DevArray(self.local + offset_bytes, tuple(shape) + (2,), "<f8"), device=torch.device("cuda", self.ctx.device))
             return torch.view_as_complex(t)
         n = 1
@@ -127,9 +132,20 @@ class PeerGroup:
         else:
             self.pull(copies)
 
+    def gather_async(self, copies):
+        """`gather` on a side stream, after everything already on the current stream; returns a handle whose wait() joins it."""
+        main = torch.cuda.current_stream()
+        side = self.pools[1][0]
+        self._fork.record(main)
+        side.wait_event(self._fork)
+        with torch.cuda.stream(side):
+            self.gather(copies)
+        return _Pending([side])
+
     def gather(self, copies):
         """copies: iterable of (dst address, src address, bytes), 8-byte aligned: ONE kernel on the current stream in which the
-        SMs pull every segment out of peer memory (skagrid_dev_peer_gather).  For bulk moves nothing overlaps with."""
+        SMs pull (or, with peer addresses as destinations, push) every segment through peer memory, all peers at once
+        (skagrid_dev_peer_gather)."""
         copies = [c for c in copies if c[2] > 0]
         if not copies:
             return

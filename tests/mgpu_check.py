@@ -70,7 +70,7 @@ def main():
         err_p = np.abs(ps.cpu().numpy() - full[a:b]).max() / peak
         pis = PeerBuffer(pg, ps.numel() * 16)
         pis.tensor(torch.complex128, tuple(ps.shape)).copy_(ps)
-        hnd = None if fused else vp.gather_slabs_peer(join=False)
+        hnd = None if fused else vp.gather_slabs_peer(join=False, sm=(it == 1))   # copy engines, then the SM kernel, then fused
         pimg, (pc0, pc1), pmx = D.peer_slab_grid_to_image(pg, pis, [x[0] for x in vp.spans()], vp.spans(), n)
         if hnd is not None:
             hnd.wait()
