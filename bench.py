@@ -760,17 +760,26 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
     alg_bytes = BYTES_PER_VIS * V + 16 * N_GRID * N_GRID + table.numel() * 16
     fl = flop_per_vis(SUPPORT)
+    # dram__bytes_read + dram__bytes_write of the gridder per launch: from the committed `ncu --set full` capture of this very
+    # workload and kernel (profiles/r02_ncu_traffic.json, scripts/gpu_r2j.sh); null for any other workload
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+    if os.path.exists(tpath) and (N_GRID, SUPPORT, NW) == (8192, 15, 32) and not args.uniform and args.variant == 0:
+        tj = json.load(open(tpath))
+        k = tj.get("grid_dense_kernel<16, 2, 8>")
+        if k and int(tj.get("vis_per_launch", 0)) == V:
+            traffic, traffic_src = k["dram_bytes_read"] + k["dram_bytes_write"], "profiles/r02_ncu_traffic.json: " + tj["source"]
     achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
     tap_tbs = 16.0 * SUPPORT * SUPPORT * V / (kern_ms * 1e-3) / 1e12
     roofline = {
         "bound": "hbm", "binding_bound": "l2_to_sm (kernel taps streamed from the L2-resident table; see l2_taps)",
         "kernel": "grid_dense_kernel<R=16,MT=2,TY=8>" if SUPPORT in (14, 15) else ("grid_dense_kernel<R=32,MT=2,TY=16>" if SUPPORT in (30, 31) else "grid_tiled_kernel"),
         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-        "traffic": None, "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "kernel_ms": kern_ms,
+        "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": alg_bytes, "peak_source": peak_src, "kernel_ms": kern_ms,
         "note": "top-level achieved/peak/frac: compulsory-HBM accounting as the contract asks (64 B/vis + 16 N^2 + table).  The kernel is NOT "
                 "HBM-bound: its taps (16 B x S^2 per visibility, 3.6-4 KB) stream L2->SM with ~1 % L1 hits, and it runs at l2_taps.frac of the "
                 "L2->SM bandwidth measured in this run with the same access pattern; halving its instruction count (round 2) left its time "
-                "unchanged, DESIGN.md 4.2.  traffic: see profiles/ (ncu), not re-measured here",
+                "unchanged, DESIGN.md 4.2.  traffic (4.9 GB per launch, from the committed ncu capture) is BELOW the algorithmic bytes: no re-reads",
         "fp64": {"achieved_tflops": fl * V / (kern_ms * 1e-3) / 1e12, "peak_tflops_measured": fp64_peak,
                  "frac": fl * V / (kern_ms * 1e-3) / 1e12 / fp64_peak if fp64_peak else None},
         "l2_taps": {"achieved_tbs": tap_tbs, "peak_tbs_measured": l2_peak, "frac": tap_tbs / l2_peak if l2_peak else None,
