@@ -136,6 +136,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -324,17 +328,23 @@ __global__ void __launch_bounds__(16 * TY, (R == 16 ? (TY == 8 ? 8 : 6) : (R == 
 // r01 SASS of grid_tiled_kernel<16,2,3,8>: ~43 instructions per record and thread for 8 DFMA + 2 LDG; this kernel:
 // see profiles/r02_sass_grid_dense.txt.
 template <int R, int TY> struct DenseCfg {
-    static constexpr int rec_batch = R == 16 ? 48 : 126;  // multiples of 3
+    static constexpr int rec_batch = R == 16 ? 48 : 126;  // multiples of 6
     static constexpr int min_blocks = R == 16 ? (TY == 8 ? 8 : (TY == 4 ? 10 : 4)) : 2;
 };
 
-template <int R, int MT, int TY, int LD = 0>
+// PAIR: the staged records are split into a visibility array and an array of 8-byte (table offset, loc) pairs, and the loop
+// runs six records per trip so that ONE 128-bit shared-memory load brings the pairs of two records: 1.5 instead of 2
+// broadcast loads per record and warp on the LSU data pipe the kernel saturates (96 %, 27 points of it these broadcasts).
+template <int R, int MT, int TY, int LD = 0, bool PAIR = false>
 __global__ void __launch_bounds__(16 * TY, DenseCfg<R, TY>::min_blocks) grid_dense_kernel(const GridArgs A) {
     constexpr int CY = R / TY, CX = R / 16;  // residues per thread
     constexpr int NT = 16 * TY;
     constexpr int REC_BATCH = DenseCfg<R, TY>::rec_batch;
-    static_assert(REC_BATCH % 3 == 0 && REC_BATCH <= NT, "one staging thread per record, batches in threes");
+    static_assert(REC_BATCH % 6 == 0 && REC_BATCH <= NT, "one staging thread per record, batches in threes (sixes when PAIR)");
+    constexpr uint32_t GROUP = PAIR ? 6u : 3u;   // records per trip: the last batch of an item is padded to a multiple of it
     extern __shared__ double2 sg[];
+    // !PAIR: records as they are, [2*j] = visibility, [2*j+1] = (offset, loc, index, tile).  PAIR: [j] = visibility for
+    // j < REC_BATCH, then REC_BATCH/2 uint4 holding the (offset, loc) of two records each
     __shared__ __align__(16) uint4 s_rec[2][REC_BATCH * 2];
     __shared__ uint32_t s_item;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -355,14 +365,16 @@ __global__ void __launch_bounds__(16 * TY, DenseCfg<R, TY>::min_blocks) grid_den
         // stages batch `bi` into buffer bi & 1: cp.async for real records, plain stores of dummies up to the next multiple of 3
         auto stage = [&](uint32_t bi) {
             const uint32_t r = bi * REC_BATCH + (uint32_t)tid;
-            uint4 *dst = &s_rec[bi & 1][2 * tid];
             if (tid < REC_BATCH) {
+                uint4 *vdst = PAIR ? &s_rec[bi & 1][tid] : &s_rec[bi & 1][2 * tid];
+                uint2 *mdst = PAIR ? reinterpret_cast<uint2 *>(&s_rec[bi & 1][REC_BATCH]) + tid : reinterpret_cast<uint2 *>(&s_rec[bi & 1][2 * tid + 1]);
                 if (r < nrec) {
-                    cp_async16(dst, recq + 2 * (size_t)(it.begin + r));
-                    cp_async16(dst + 1, recq + 2 * (size_t)(it.begin + r) + 1);
-                } else if (r < (nrec + 2u) / 3u * 3u) {
-                    dst[0] = make_uint4(0u, 0u, 0u, 0u);         // vis = 0
-                    dst[1] = make_uint4(0u, 0x00010000u, 0u, 0u);  // table offset 0 (leading zero slice), micro-tile (0,0)
+                    cp_async16(vdst, recq + 2 * (size_t)(it.begin + r));
+                    if constexpr (PAIR) cp_async8(mdst, recq + 2 * (size_t)(it.begin + r) + 1);
+                    else cp_async16(mdst, recq + 2 * (size_t)(it.begin + r) + 1);
+                } else if (r < (nrec + GROUP - 1u) / GROUP * GROUP) {
+                    *vdst = make_uint4(0u, 0u, 0u, 0u);        // vis = 0
+                    *mdst = make_uint2(0u, 0x00010000u);       // table offset 0 (leading zero slice), micro-tile (0,0)
                 }
             }
             cp_async_commit();
@@ -380,8 +392,7 @@ __global__ void __launch_bounds__(16 * TY, DenseCfg<R, TY>::min_blocks) grid_den
             for (int b = 0; b < CX; ++b) { acc[a][b] = make_double2(0.0, 0.0); cell_cur[a][b] = 0; tp[a][b] = A.table; }
 
         struct Slot { double2 k[CY][CX]; int cell[CY][CX]; bool sw; };
-        auto issue = [&](const uint4 *buf, uint32_t j, Slot &s) {
-            const uint2 m = *reinterpret_cast<const uint2 *>(&buf[2 * j + 1]);  // table offset, loc (broadcast read)
+        auto issue_m = [&](const uint2 m, Slot &s) {
             const uint32_t key = m.y & mtkey_mask;
             s.sw = key != key_cur;
             if (s.sw) {  // block-uniform: all threads walk the same records
@@ -403,8 +414,11 @@ __global__ void __launch_bounds__(16 * TY, DenseCfg<R, TY>::min_blocks) grid_den
 #pragma unroll
                 for (int b = 0; b < CX; ++b) s.k[a][b] = ld_tap<LD>(tp[a][b] + m.x);
         };
+        auto issue = [&](const uint4 *buf, uint32_t j, Slot &s) {  // !PAIR: one 64-bit broadcast read per record
+            issue_m(*reinterpret_cast<const uint2 *>(&buf[2 * j + 1]), s);
+        };
         auto consume = [&](const uint4 *buf, uint32_t j, const Slot &s) {
-            const double2 vis = *reinterpret_cast<const double2 *>(&buf[2 * j]);
+            const double2 vis = *reinterpret_cast<const double2 *>(&buf[PAIR ? j : 2 * j]);
             if (s.sw) {  // fold the register accumulators into the thread's own subgrid cells and retarget them
 #pragma unroll
                 for (int a = 0; a < CY; ++a)
@@ -436,23 +450,60 @@ __global__ void __launch_bounds__(16 * TY, DenseCfg<R, TY>::min_blocks) grid_den
             __syncthreads();      // (first iteration: also orders the subgrid zeroing before any fold)
             const uint4 *buf = s_rec[bi & 1];
             const uint32_t m = min((uint32_t)REC_BATCH, nrec - bi * REC_BATCH);
-            const uint32_t m3 = (m + 2u) / 3u * 3u;  // records incl. dummies
+            const uint32_t m3 = (m + GROUP - 1u) / GROUP * GROUP;  // records incl. dummies
             Slot s0, s1, s2;
-            issue(buf, 0, s0);
-            issue(buf, 1, s1);
-            uint32_t j = 0;
-            for (; j + 3 < m3; j += 3) {
+            if constexpr (!PAIR) {
+                issue(buf, 0, s0);
+                issue(buf, 1, s1);
+                uint32_t j = 0;
+                for (; j + 3 < m3; j += 3) {
+                    issue(buf, j + 2, s2);
+                    consume(buf, j, s0);
+                    issue(buf, j + 3, s0);
+                    consume(buf, j + 1, s1);
+                    issue(buf, j + 4, s1);
+                    consume(buf, j + 2, s2);
+                }
                 issue(buf, j + 2, s2);
                 consume(buf, j, s0);
-                issue(buf, j + 3, s0);
                 consume(buf, j + 1, s1);
-                issue(buf, j + 4, s1);
                 consume(buf, j + 2, s2);
+            } else {
+                const uint4 *meta = buf + REC_BATCH;  // meta[p] = (offset, loc) of records 2p and 2p+1
+                uint4 mm = meta[0];
+                issue_m(make_uint2(mm.x, mm.y), s0);
+                issue_m(make_uint2(mm.z, mm.w), s1);
+                uint32_t j = 0;
+                for (; j + 6 < m3; j += 6) {
+                    mm = meta[(j >> 1) + 1];
+                    issue_m(make_uint2(mm.x, mm.y), s2);
+                    consume(buf, j, s0);
+                    issue_m(make_uint2(mm.z, mm.w), s0);
+                    consume(buf, j + 1, s1);
+                    mm = meta[(j >> 1) + 2];
+                    issue_m(make_uint2(mm.x, mm.y), s1);
+                    consume(buf, j + 2, s2);
+                    issue_m(make_uint2(mm.z, mm.w), s2);
+                    consume(buf, j + 3, s0);
+                    mm = meta[(j >> 1) + 3];
+                    issue_m(make_uint2(mm.x, mm.y), s0);
+                    consume(buf, j + 4, s1);
+                    issue_m(make_uint2(mm.z, mm.w), s1);
+                    consume(buf, j + 5, s2);
+                }
+                mm = meta[(j >> 1) + 1];
+                issue_m(make_uint2(mm.x, mm.y), s2);
+                consume(buf, j, s0);
+                issue_m(make_uint2(mm.z, mm.w), s0);
+                consume(buf, j + 1, s1);
+                mm = meta[(j >> 1) + 2];
+                issue_m(make_uint2(mm.x, mm.y), s1);
+                consume(buf, j + 2, s2);
+                issue_m(make_uint2(mm.z, mm.w), s2);
+                consume(buf, j + 3, s0);
+                consume(buf, j + 4, s1);
+                consume(buf, j + 5, s2);
             }
-            issue(buf, j + 2, s2);
-            consume(buf, j, s0);
-            consume(buf, j + 1, s1);
-            consume(buf, j + 2, s2);
             __syncthreads();  // every warp is done with buf before it is refilled
         }
 #pragma unroll
@@ -814,16 +865,16 @@ static int launch_tiled(skagrid_ctx *ctx, const GridArgs &A, cudaStream_t st) {
     return SKAGRID_OK;
 }
 
-template <int R, int MT, int TY, int LD = 0>
+template <int R, int MT, int TY, int LD = 0, bool PAIR = false>
 static int launch_dense(skagrid_ctx *ctx, const GridArgs &A, cudaStream_t st) {
     constexpr int NT = 16 * TY;
     const size_t smem = (size_t)A.SG * A.SG * sizeof(double2);
-    if (ctx->smem_configured.insert((const void *)grid_dense_kernel<R, MT, TY, LD>).second)
-        SK_CUDA(ctx, cudaFuncSetAttribute(grid_dense_kernel<R, MT, TY, LD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    if (ctx->smem_configured.insert((const void *)grid_dense_kernel<R, MT, TY, LD, PAIR>).second)
+        SK_CUDA(ctx, cudaFuncSetAttribute(grid_dense_kernel<R, MT, TY, LD, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     int per_sm = 0;
-    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_dense_kernel<R, MT, TY, LD>, NT, smem));
+    SK_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, grid_dense_kernel<R, MT, TY, LD, PAIR>, NT, smem));
     if (per_sm < 1) return sk_fail(ctx, SKAGRID_ECUDA, "dense gridder does not fit on an SM (smem %zu)", smem);
-    grid_dense_kernel<R, MT, TY, LD><<<ctx->sm_count * per_sm, NT, smem, st>>>(A);
+    grid_dense_kernel<R, MT, TY, LD, PAIR><<<ctx->sm_count * per_sm, NT, smem, st>>>(A);
     SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
@@ -853,11 +904,13 @@ extern "C" int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const doub
         if (R == 16) {
             if (variant == 5) return MT == 2 ? launch_dense<16, 2, 4>(ctx, A, st) : launch_dense<16, 4, 4>(ctx, A, st);
             if (variant == 6) return MT == 2 ? launch_dense<16, 2, 16>(ctx, A, st) : launch_dense<16, 4, 16>(ctx, A, st);  // 16x16 threads, one residue each
+            if (variant == 7 && MT == 2) return launch_dense<16, 2, 8, 0, true>(ctx, A, st);  // paired (offset, loc) broadcasts
             if (MT == 2 && tap_load_mode() == 1) return launch_dense<16, 2, 8, 1>(ctx, A, st);
             if (MT == 2 && tap_load_mode() == 2) return launch_dense<16, 2, 8, 2>(ctx, A, st);
             return MT == 2 ? launch_dense<16, 2, 8>(ctx, A, st) : launch_dense<16, 4, 8>(ctx, A, st);
         }
         if (variant == 5) return MT == 2 ? launch_dense<32, 2, 32>(ctx, A, st) : launch_dense<32, 4, 32>(ctx, A, st);
+        if (variant == 7 && MT == 2) return launch_dense<32, 2, 16, 0, true>(ctx, A, st);
         if (MT == 2 && tap_load_mode() == 1) return launch_dense<32, 2, 16, 1>(ctx, A, st);
         if (MT == 2 && tap_load_mode() == 2) return launch_dense<32, 2, 16, 2>(ctx, A, st);
         return MT == 2 ? launch_dense<32, 2, 16>(ctx, A, st) : launch_dense<32, 4, 16>(ctx, A, st);
