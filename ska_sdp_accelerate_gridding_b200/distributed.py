@@ -270,8 +270,9 @@ def peer_slab_grid_to_image(pg, pbuf, row_base, spans, n, group=None, want_image
     """slab_grid_to_image with the transpose pulled over NVLink peer memory instead of an all-to-all: rank s holds grid rows
     [row_base[s], ...) as [rows, n] complex128 at the start of its peer-visible buffer `pbuf`; spans[s] = (a, b) are the rows
     of rank s that can be non-zero (host list, all ranks).  Row transforms in place, device barrier, then every rank pulls its
-    column block of every peer's rows with ONE strided copy-engine copy per peer straight into place (no pack, no unpack),
-    column transforms.  Returns (image columns or None, (c0, c1), max)."""
+    column block of every peer's rows straight into place (no pack, no unpack) -- one SM kernel reading all peers at once, or
+    one strided copy-engine copy per peer between two or three ranks -- and does the column transforms.
+    Returns (image columns or None, (c0, c1), max)."""
     from . import device as dv
     P, me = pg.world, pg.rank
     a, b = spans[me]

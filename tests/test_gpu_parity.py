@@ -501,6 +501,83 @@ def test_route_kernels_against_torch_reference(orc):
     p2.update(_t(u[ok]), _t(v[ok]), _t(wb[ok]), _t(vis[ok]))
 
 
+def test_peer_memory_kernels_single_device():
+    """csrc/ipc.cu on ONE device: the exchange kernels do not care whether a pointer is local or an opened peer buffer, so local
+    buffers stand in for the peers (tests/mgpu_check.py runs the real thing on 2-8 GPUs).  The barrier protocol is exercised by
+    two streams playing rank 0 and rank 1 against each other."""
+    import ctypes as C
+    import torch
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    from ska_sdp_accelerate_gridding_b200.peer import PeerBuffer, PeerGroup
+    pg = PeerGroup()                       # world 1: allocation, export and views work without torch.distributed
+    ctx, lib, h = pg.ctx, pg.ctx.lib, pg.ctx.h
+    assert pg.world == 1 and pg.flags.ptrs == [pg.flags.local]
+    rng = np.random.default_rng(9)
+    n = 50000
+    bufs = [PeerBuffer(pg, n * 16) for _ in range(4)]
+    vals = [_rand_c(rng, n) for _ in range(4)]
+    for b, v in zip(bufs, vals):
+        b.tensor(torch.complex128, (n,)).copy_(_t(v))
+    with pytest.raises(ValueError):
+        bufs[0].tensor(torch.complex128, (n + 1,))
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    peers = (C.c_void_p * 3)(*[C.c_void_p(b.local) for b in bufs[1:]])
+    # own += sum of the three "peers"; then the fused form: the sum is stored back into every one of them
+    ctx.check(lib.skagrid_dev_peer_sum(h, 3, peers, C.c_void_p(bufs[0].local), n, 0, st))
+    want = vals[0] + vals[1] + vals[2] + vals[3]
+    assert rel_err(bufs[0].tensor(torch.complex128, (n,)).cpu().numpy(), want) < 1e-15
+    assert np.array_equal(bufs[1].tensor(torch.complex128, (n,)).cpu().numpy(), vals[1])
+    bufs[0].tensor(torch.complex128, (n,)).copy_(_t(vals[0]))
+    ctx.check(lib.skagrid_dev_peer_sum(h, 3, peers, C.c_void_p(bufs[0].local), n, 1, st))
+    for b in bufs:
+        assert rel_err(b.tensor(torch.complex128, (n,)).cpu().numpy(), want) < 1e-15
+    # gather of unequal, 8-byte aligned segments (routed records are 24 or 40 bytes long) and the strided form
+    src = _t(rng.standard_normal(4096 * 5))
+    dst = torch.zeros(4096 * 5, dtype=torch.float64, device="cuda")
+    segs = [(0, 0, 40 * 100), (40 * 100, 40 * 300, 40 * 7), (40 * 107 + 8, 40 * 500 + 8, 8 * 999)]
+    pg.gather([(dst.data_ptr() + d, src.data_ptr() + s_, nb) for d, s_, nb in segs])
+    ref = np.zeros(4096 * 5)
+    hs = src.cpu().numpy()
+    for d, s_, nb in segs:
+        ref[d // 8:(d + nb) // 8] = hs[s_ // 8:(s_ + nb) // 8]
+    assert np.array_equal(dst.cpu().numpy(), ref)
+    with pytest.raises(Exception):
+        pg.gather([(dst.data_ptr() + 4, src.data_ptr(), 64)])       # misaligned
+    rows, wid, cw = 37, 64, 16
+    a = _t(_rand_c(rng, (2, rows, wid)))
+    cols = torch.zeros((2 * rows, cw), dtype=torch.complex128, device="cuda")
+    c0 = 32
+    pg.gather2d([(cols.data_ptr() + k * rows * cw * 16, cw * 16, a[k].data_ptr() + c0 * 16, wid * 16, cw * 16, rows - k) for k in range(2)])
+    hc = cols.cpu().numpy()
+    ha = a.cpu().numpy()
+    assert np.array_equal(hc[:rows], ha[0][:, c0:c0 + cw]) and np.array_equal(hc[rows:2 * rows - 1], ha[1][:rows - 1, c0:c0 + cw])
+    assert np.all(hc[2 * rows - 1] == 0)
+    cols.zero_()
+    pg.pull([(cols.data_ptr(), cw * 16, a[0].data_ptr() + c0 * 16, wid * 16, cw * 16, rows)])      # copy-engine form of the same
+    assert np.array_equal(cols.cpu().numpy()[:rows], ha[0][:, c0:c0 + cw])
+    # the barrier: two streams are rank 0 and rank 1 of a 2-rank barrier over two flag buffers; three epochs
+    f = [PeerBuffer(pg, 4096) for _ in range(2)]
+    fl = (C.c_void_p * 2)(C.c_void_p(f[0].local), C.c_void_p(f[1].local))
+    s0, s1 = torch.cuda.Stream(), torch.cuda.Stream()
+    mark = torch.zeros(2, dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    for epoch in (1, 2, 3):
+        with torch.cuda.stream(s0):
+            torch.cuda._sleep(20_000_000)                     # rank 0 arrives late ...
+            mark[0] = epoch
+            ctx.check(lib.skagrid_dev_peer_barrier(h, 2, 0, fl, epoch, C.c_void_p(s0.cuda_stream)))
+        with torch.cuda.stream(s1):
+            ctx.check(lib.skagrid_dev_peer_barrier(h, 2, 1, fl, epoch, C.c_void_p(s1.cuda_stream)))
+            seen = mark[0].clone()                            # ... and rank 1 must not get past the barrier before it has
+        s1.synchronize()
+        assert float(seen.item()) == epoch
+    torch.cuda.synchronize()
+    dv.check_errors(ctx)                                      # no barrier timed out
+    for b in bufs + f:
+        b.close()
+    pg.close()
+
+
 def test_two_gpu_torchrun_if_available():
     import subprocess
     import sys
