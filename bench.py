@@ -587,7 +587,7 @@ def run_config5(env, args):
                   "fp64_tflops_per_gpu_plan_plus_grid": flop_per_vis(S5) * (routed / world) / (kern * 1e-3) / 1e12},
         "gpu_launches": launches, "parity": parity,
     }
-    out["config"]["exchange"] = "none" if world == 1 else ("peer memory over NVLink (copy-engine pulls of routed records, partial sums and the image transpose)" if peer else "nccl all-to-all")
+    out["config"]["exchange"] = "none" if world == 1 else ("peer memory over NVLink (routed records, partial sums and the image transpose pulled by SM gather kernels reading all peers at once; copy engines on 2 GPUs)" if peer else "nccl all-to-all")
     ts._plan.close()
     if peer:
         del slab
@@ -803,7 +803,7 @@ def main():
                        "bin+bucket -> tiled gridder -> peer-memory reduce-scatter of the active rows (ONE kernel per rank sums its slab of every peer's grid over NVLink) -> "
                        "[slab-distributed grid->image with the transpose pulled from peer memory || all-gather of the reduced slabs by one SM kernel reading all peers "
                        f"at once (copy engines on 2 GPUs)] -> degridder; --allgather {args.allgather}"))),
-            "exchange": ("none" if world == 1 else ("nccl" if (args.nccl or args.allreduce) else "peer memory over NVLink (CUDA IPC; csrc/ipc.cu): device barrier, peer-sum kernel, copy-engine pulls")),
+            "exchange": ("none" if world == 1 else ("nccl" if (args.nccl or args.allreduce) else "peer memory over NVLink (CUDA IPC; csrc/ipc.cu): device barrier, peer-sum kernel, SM gather kernels reading all peers at once (copy-engine pulls on 2 GPUs)")),
             "l2": f"inputs ({V * 40 / 1e9:.1f} GB) and grid ({N_GRID * N_GRID * 16 / 1e9:.2f} GB) exceed the 126 MB L2; no explicit flush",
             "gridder_variant": args.variant, "plan": stats,
             "active_rows": (None if not c4.slabbed else {"first": c4.vs.active[0], "per_rank": c4.vs.active[1]}),
