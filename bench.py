@@ -209,9 +209,16 @@ class Env:
             if args.nccl and not args.one_group and not args.allreduce:
                 self.img_group = dist.new_group()   # second communicator: the image transpose overlaps the all-gather
         self.ctx = get_context(self.local)
+        self.peer_problem = None
         if self.world > 1 and not args.nccl and not args.allreduce:
             from ska_sdp_accelerate_gridding_b200.peer import PeerGroup
-            self.pg = PeerGroup()
+            try:
+                self.pg = PeerGroup()
+            except RuntimeError as e:   # raised on EVERY rank (peer.py agrees on the outcome): the NCCL form of the same steps runs instead
+                self.pg, self.peer_problem = None, str(e)
+                args.nccl = True
+                if not args.one_group:
+                    self.img_group = dist.new_group()
 
     def ev(self):
         return self.torch.cuda.Event(enable_timing=True)
@@ -803,7 +810,7 @@ def main():
                        "bin+bucket -> tiled gridder -> peer-memory reduce-scatter of the active rows (ONE kernel per rank sums its slab of every peer's grid over NVLink) -> "
                        "[slab-distributed grid->image with the transpose pulled from peer memory || all-gather of the reduced slabs by one SM kernel reading all peers "
                        f"at once (copy engines on 2 GPUs)] -> degridder; --allgather {args.allgather}"))),
-            "exchange": ("none" if world == 1 else ("nccl" if (args.nccl or args.allreduce) else "peer memory over NVLink (CUDA IPC; csrc/ipc.cu): device barrier, peer-sum kernel, SM gather kernels reading all peers at once (copy-engine pulls on 2 GPUs)")),
+            "exchange": ("none" if world == 1 else (("nccl" + (f" (peer memory unavailable: {env.peer_problem})" if env.peer_problem else "")) if (args.nccl or args.allreduce) else "peer memory over NVLink (CUDA IPC; csrc/ipc.cu): device barrier, peer-sum kernel, SM gather kernels reading all peers at once (copy-engine pulls on 2 GPUs)")),
             "l2": f"inputs ({V * 40 / 1e9:.1f} GB) and grid ({N_GRID * N_GRID * 16 / 1e9:.2f} GB) exceed the 126 MB L2; no explicit flush",
             "gridder_variant": args.variant, "plan": stats,
             "active_rows": (None if not c4.slabbed else {"first": c4.vs.active[0], "per_rank": c4.vs.active[1]}),

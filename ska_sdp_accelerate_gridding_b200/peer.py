@@ -24,8 +24,12 @@ class PeerBuffer:
         lib, h = self.ctx.lib, self.ctx.h
         handle = (C.c_ubyte * 64)()
         p = C.c_void_p()
-        self.ctx.check(lib.skagrid_ipc_alloc(h, self.nbytes, C.byref(p), handle))
-        self.local = int(p.value)
+        problem = None
+        if lib.skagrid_ipc_alloc(h, self.nbytes, C.byref(p), handle) != 0:
+            if pg.world == 1:
+                self.ctx.check(-3)
+            problem = f"rank {pg.rank} cannot allocate {self.nbytes} bytes: " + lib.skagrid_last_error(h).decode()   # reported collectively below
+        self.local = int(p.value or 0)
         dev = torch.device("cuda", self.ctx.device)
         mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
         every = torch.empty(64 * pg.world, dtype=torch.uint8, device=dev)
@@ -39,12 +43,28 @@ class PeerBuffer:
             if k == pg.rank:
                 self.ptrs.append(self.local)
                 continue
+            if problem is not None or not host[64 * k:64 * (k + 1)].any():   # this rank, or rank k, has no buffer to share
+                self.ptrs.append(0)
+                continue
             hk = (C.c_ubyte * 64)(*host[64 * k:64 * (k + 1)].tolist())
             q = C.c_void_p()
-            self.ctx.check(lib.skagrid_ipc_open(h, hk, C.byref(q)))
-            self.ptrs.append(int(q.value))
+            rc = lib.skagrid_ipc_open(h, hk, C.byref(q))
+            if rc != 0 and problem is None:
+                problem = f"rank {pg.rank} cannot open the buffer of rank {k}: " + lib.skagrid_last_error(h).decode()
+            self.ptrs.append(int(q.value) if rc == 0 else 0)
         if pg.world > 1:
-            dist.barrier(group=pg.group)   # nobody frees before everybody has opened
+            # agree on the outcome: a rank that could not map a peer must not leave the others waiting at a barrier
+            bad = torch.tensor([1 if problem else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=pg.group)   # also: nobody frees before everybody has opened
+            if int(bad.item()):
+                for k, q in enumerate(self.ptrs):
+                    if k != pg.rank and q:
+                        lib.skagrid_ipc_close(h, C.c_void_p(q))
+                dist.barrier(group=pg.group)
+                if self.local:
+                    lib.skagrid_ipc_free(h, C.c_void_p(self.local))
+                self.ptrs = None
+                raise RuntimeError("peer memory is not available between these devices" + (": " + problem if problem else " (another rank failed)"))
 
     def tensor(self, dtype, shape, offset_bytes=0):
         """A torch view (no copy) of the LOCAL buffer."""
