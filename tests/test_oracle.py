@@ -167,3 +167,23 @@ def test_mirror_doweight_pipeline():
     cells = y * 30 + x
     counts = np.bincount(cells, minlength=900)[cells]
     assert np.array_equal(wt, 1.0 / counts + 0j)
+
+
+def test_shift_convention_is_the_one_written_out_in_ShiftExample():
+    """old/ShiftExample.hs:98-106 spells accelerate-fft's shift1D out as a backpermute: out[i] = in[(i + n `quot` 2 + (1 if odd n)) `rem` n].
+    The oracle's shift2d / ishift2d (numpy fftshift / ifftshift) must be that index map per axis -- for odd sizes too, where the
+    two differ -- and ifft = shift2D . fft2D Inverse . ishift2D (src/Gridding.hs:828-829) must reduce to the (-1)^(x+y) modulation
+    the CUDA path uses for the even sizes of the hot path."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(11)
+    for n in (4, 5, 8, 9, 30):
+        a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        sh = n // 2 + (n % 2)
+        idx = (np.arange(n) + sh) % n
+        assert np.array_equal(orc.shift2d(a), a[np.ix_(idx, idx)])
+        assert np.array_equal(orc.ishift2d(orc.shift2d(a)), a)
+    n = 8
+    a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    yy, xx = np.mgrid[0:n, 0:n]
+    m = np.where((yy + xx) % 2 == 1, -1.0, 1.0)
+    assert np.abs(orc.ifft(a) - m * np.fft.ifft2(m * a)).max() < 1e-15
