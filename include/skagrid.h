@@ -203,6 +203,12 @@ int skagrid_aw_gridding(skagrid_ctx *ctx, double theta, int64_t lam, int64_t nw,
  * conjugate != 0 applies the `map conjugate` of w_cache_imaging (src/Gridding.hs:441). */
 int skagrid_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *w, int64_t npixff,
                       int64_t npixkern, int64_t qpx, int conjugate, double *out);
+/* The same with the KernelOptions that move the far-field coordinates (kernel_coordinates, src/Gridding.hs:620-635):
+ * (l, m) = theta * coordinates2 -> (t00 l + t10 m, t01 l + t11 m) -> + (dl, dm).  transmat = patTransMat as 4 doubles,
+ * row-major t[r][c] (NULL: identity); dl, dm = patHorShift, patVerShift. */
+int skagrid_w_kernels_ex(skagrid_ctx *ctx, double theta, int64_t nw, const double *w, int64_t npixff,
+                         int64_t npixkern, int64_t qpx, int conjugate, const double *transmat, double dl, double dm,
+                         double *out);
 
 /* ================================================================== multi-GPU, single process
  * ONE host thread drives `nctx` (1..16) contexts, one per device (ctxs[i] from skagrid_create(device_i); contexts on the

@@ -304,6 +304,23 @@ inline Matrix<Visibility> aw_imaging(const Context &ctx, F theta, Index lam, con
     return out;
 }
 
+// KernelOptions (src/Gridding.hs:30-38); a negative size means Nothing
+struct KernelOptions {
+    Index patHorShift = 0, patVerShift = 0;
+    std::vector<F> patTransMat;   // empty = Nothing, else 2 x 2 row-major
+    Index wstep = -1, qpx = -1, npixFF = -1, npixKern = -1;
+};
+
+// w_kernel (src/Gridding.hs:610-619) for a list of w -> [nw, qpx, qpx, npixKern, npixKern]; conjugate as w_cache_imaging does (:441)
+inline NdArray<Visibility> w_kernel(const Context &ctx, F theta, const std::vector<F> &w, const KernelOptions &k, bool conjugate = false) {
+    if (k.qpx <= 0 || k.npixFF <= 0 || k.npixKern <= 0) throw Error(SKAGRID_EINVAL, "w_kernel: qpx, npixFF and npixKern must be given");
+    if (!k.patTransMat.empty() && k.patTransMat.size() != 4) throw Error(SKAGRID_EINVAL, "w_kernel: patTransMat must be 2 x 2");
+    NdArray<Visibility> out({(Index)w.size(), k.qpx, k.qpx, k.npixKern, k.npixKern});
+    ctx.check(skagrid_w_kernels_ex(ctx.get(), theta, (Index)w.size(), w.data(), k.npixFF, k.npixKern, k.qpx, conjugate ? 1 : 0,
+                                   k.patTransMat.empty() ? nullptr : k.patTransMat.data(), (F)k.patHorShift, (F)k.patVerShift, cptr(out.data)));
+    return out;
+}
+
 // map real . ifft . make_grid_hermitian and its maximum, fused (src/ImageDataset.hs:74-77)
 inline std::pair<Matrix<F>, F> grid_to_image(const Context &ctx, const Matrix<Visibility> &g) {
     Matrix<F> img(g.height, g.width);

@@ -356,11 +356,22 @@ def extract_oversampled(a, qpx, n):
     return out * float(qpx * qpx)
 
 
-def w_kernel(theta, w, npixff, npixkern, qpx):
-    """w_kernel (src/Gridding.hs:610-619) = kernel_coordinates (:620-635, no shifts/transforms)
-    -> w_kernel_function -> kernel_oversample (:669-680).  Returns [qpx,qpx,npixkern,npixkern]."""
-    l, m = coordinates2(npixff)
-    ff = w_kernel_function(l * theta, m * theta, w)
+def kernel_coordinates(n, theta, dl=0, dm=0, transmat=None):
+    """src/Gridding.hs:620-635: theta * coordinates2, through patTransMat t as (x, y) -> (t[0,0] x + t[1,0] y, t[0,1] x + t[1,1] y),
+    then shifted by (patHorShift, patVerShift)."""
+    l, m = coordinates2(n)
+    l, m = l * theta, m * theta
+    if transmat is not None:
+        t = np.asarray(transmat, dtype=np.float64).reshape(2, 2)
+        l, m = t[0, 0] * l + t[1, 0] * m, t[0, 1] * l + t[1, 1] * m
+    return l + float(dl), m + float(dm)
+
+
+def w_kernel(theta, w, npixff, npixkern, qpx, dl=0, dm=0, transmat=None):
+    """w_kernel (src/Gridding.hs:610-619) = kernel_coordinates (:620-635) -> w_kernel_function ->
+    kernel_oversample (:669-680).  Returns [qpx,qpx,npixkern,npixkern]."""
+    l, m = kernel_coordinates(npixff, theta, dl, dm, transmat)
+    ff = w_kernel_function(l, m, w)
     padff = pad_mid(ff, npixff * qpx)
     af = ifft(padff)
     return extract_oversampled(af, qpx, npixkern)

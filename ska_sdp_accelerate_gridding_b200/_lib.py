@@ -58,6 +58,7 @@ _SIGS = {
     "skagrid_aw_imaging": [vp, dbl, i64, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp],
     "skagrid_aw_gridding": [vp, dbl, i64, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp, vp, vp, vp, dbl, vp, vp, vp, vp],
     "skagrid_w_kernels": [vp, dbl, i64, vp, i64, i64, i64, ip, vp],
+    "skagrid_w_kernels_ex": [vp, dbl, i64, vp, i64, i64, i64, ip, vp, dbl, dbl, vp],
     "skagrid_convgrid2_mgpu_vis": [C.POINTER(vp), ip, i64, i64, i64, i64, vp, i64, i64, vp, i64, vp, vp, vp, vp],
     "skagrid_convdegrid2_mgpu_vis": [C.POINTER(vp), ip, i64, i64, i64, i64, vp, i64, i64, vp, i64, vp, vp, vp, vp],
     "skagrid_convgrid2_mgpu_tile": [C.POINTER(vp), ip, i64, i64, i64, i64, vp, i64, i64, vp, i64, vp, vp, vp, vp, vp],

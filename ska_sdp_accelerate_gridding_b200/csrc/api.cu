@@ -770,6 +770,21 @@ extern "C" int skagrid_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, con
 }
 
 // Device-output variant used by bench.py to build the kernel table without a host round trip.
+// w_kernel with the KernelOptions of src/Gridding.hs:30-38 that move the far-field coordinates (kernel_coordinates, :620-635):
+// transmat = patTransMat as 4 doubles, row-major t[r][c] (NULL: identity), dl / dm = patHorShift / patVerShift.
+extern "C" int skagrid_w_kernels_ex(skagrid_ctx *ctx, double theta, int64_t nw, const double *w, int64_t npixff, int64_t npixkern, int64_t qpx,
+                                    int conjugate, const double *transmat, double dl, double dm, double *out) {
+    SK_TRY(sk_api_enter(ctx));
+    NEED(ctx, nw > 0 && w && out, "w_kernels_ex: NULL pointer or nw <= 0");
+    Timer t(ctx);
+    const size_t bytes = (size_t)(nw * qpx * qpx * npixkern * npixkern) * 16;
+    void *dout;
+    SK_TRY(sk_scratch(ctx, "wkern_out", bytes, &dout));
+    SK_TRY(sk_w_kernels_ex_dev(ctx, theta, nw, w, npixff, npixkern, qpx, conjugate, transmat, dl, dm, (double *)dout, ctx->stream));
+    SK_TRY(down(ctx, out, dout, bytes));
+    return t.finish();
+}
+
 extern "C" int skagrid_dev_w_kernels(skagrid_ctx *ctx, double theta, int64_t nw, const double *w_host, int64_t npixff, int64_t npixkern,
                                      int64_t qpx, int conjugate, double *d_out, void *stream) {
     SK_TRY(sk_api_enter(ctx));

@@ -196,6 +196,8 @@ int sk_slab_fft_cols_dev(skagrid_ctx *ctx, i64 n, i64 col0, i64 ncols, double *c
 int sk_pad_crop_dev(skagrid_ctx *ctx, i64 n_in, const double *in, i64 n_out, double *out, cudaStream_t st);
 int sk_w_kernels_dev(skagrid_ctx *ctx, double theta, i64 nw, const double *w, i64 npixff, i64 npixkern,
                      i64 qpx, int conjugate, double *out, cudaStream_t st);
+int sk_w_kernels_ex_dev(skagrid_ctx *ctx, double theta, i64 nw, const double *w, i64 npixff, i64 npixkern, i64 qpx, int conjugate,
+                        const double *transmat, double dl, double dm, double *out, cudaStream_t st);
 
 // host-pointer plumbing of api.cu shared with the multi-device entry points (mgpu.cu)
 int sk_api_enter(skagrid_ctx *ctx);  // cudaSetDevice + clear the error string

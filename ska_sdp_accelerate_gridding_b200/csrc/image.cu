@@ -357,7 +357,12 @@ int sk_pad_crop_dev(skagrid_ctx *ctx, i64 n_in, const double *in, i64 n_out, dou
 // of coordinates2 (:637-648) scaled by theta, centre-padded to npixff*qpx (the transposing padder is
 // harmless: the far field is symmetric in l,m -- we still honour it), centred inverse FFT,
 // extract_oversampled (:709-728): out[yf,xf,y,x] = qpx^2 * af[c0 - yf + qpx*y, c0 - xf + qpx*x].
-__global__ void __launch_bounds__(256) wfarfield_kernel(i64 npixff, i64 big, double theta, double w, double2 *__restrict__ out) {
+// kernel_coordinates (:620-635): (l, m) = theta * coordinates2, optionally through the 2 x 2 matrix t
+// (l, m) -> (t00 l + t10 m, t01 l + t11 m), then shifted by (dl, dm) = (patHorShift, patVerShift).
+struct WCoord {
+    double t00, t10, t01, t11, dl, dm;
+};
+__global__ void __launch_bounds__(256) wfarfield_kernel(i64 npixff, i64 big, double theta, double w, WCoord K, double2 *__restrict__ out) {
     const i64 total = big * big;
     const i64 stride = (i64)gridDim.x * blockDim.x;
     const i64 before = big / 2 - npixff / 2;
@@ -369,8 +374,12 @@ __global__ void __launch_bounds__(256) wfarfield_kernel(i64 npixff, i64 big, dou
         double2 v = make_double2(0.0, 0.0);
         if (oy >= 0 && oy < npixff && ox >= 0 && ox < npixff) {
             // padder reads ff[ox, oy] (transpose); ff[r, c] uses l = base[c], m = base[r]
-            const double l = ((double)(-n2) * step + (double)oy * step) * theta;
-            const double m = ((double)(-n2) * step + (double)ox * step) * theta;
+            // pad_mid returns the far field untouched -- NOT transposed -- when no padding is needed (qpx = 1, :688)
+            const i64 ci = big == npixff ? ox : oy, ri = big == npixff ? oy : ox;
+            const double l1 = ((double)(-n2) * step + (double)ci * step) * theta;
+            const double m1 = ((double)(-n2) * step + (double)ri * step) * theta;
+            const double l = K.t00 * l1 + K.t10 * m1 + K.dl;
+            const double m = K.t01 * l1 + K.t11 * m1 + K.dm;
             const double r2 = l * l + m * m;
             const double ph = 1.0 - sqrt(1.0 - r2);
             double sn, cs;
@@ -401,6 +410,13 @@ __global__ void __launch_bounds__(256) extract_oversampled_kernel(i64 big, const
 
 int sk_w_kernels_dev(skagrid_ctx *ctx, double theta, i64 nw, const double *w_host, i64 npixff, i64 npixkern, i64 qpx, int conjugate,
                      double *out, cudaStream_t st) {
+    return sk_w_kernels_ex_dev(ctx, theta, nw, w_host, npixff, npixkern, qpx, conjugate, nullptr, 0.0, 0.0, out, st);
+}
+
+int sk_w_kernels_ex_dev(skagrid_ctx *ctx, double theta, i64 nw, const double *w_host, i64 npixff, i64 npixkern, i64 qpx, int conjugate,
+                        const double *transmat, double dl, double dm, double *out, cudaStream_t st) {
+    WCoord K = {1.0, 0.0, 0.0, 1.0, dl, dm};
+    if (transmat) { K.t00 = transmat[0]; K.t01 = transmat[1]; K.t10 = transmat[2]; K.t11 = transmat[3]; }  // row-major t[r][c]
     if (nw <= 0 || npixff <= 0 || npixkern <= 0 || qpx <= 0) return sk_fail(ctx, SKAGRID_EINVAL, "w_kernels: non-positive size");
     const i64 big = npixff * qpx;
     if (qpx * (npixkern / 2) > big / 2 || big > (1 << 15)) return sk_fail(ctx, SKAGRID_EINVAL, "w_kernels: kernel %lld x oversampling %lld does not fit the %lld far field", npixkern, qpx, npixff);
@@ -408,7 +424,7 @@ int sk_w_kernels_dev(skagrid_ctx *ctx, double theta, i64 nw, const double *w_hos
     SK_TRY(sk_scratch(ctx, "wkern_ff", (size_t)(big * big) * sizeof(double2), &buf));
     const i64 per = qpx * qpx * npixkern * npixkern;
     for (i64 i = 0; i < nw; ++i) {
-        wfarfield_kernel<<<nblocks(ctx, big * big), 256, 0, st>>>(npixff, big, theta, w_host[i], (double2 *)buf);
+        wfarfield_kernel<<<nblocks(ctx, big * big), 256, 0, st>>>(npixff, big, theta, w_host[i], K, (double2 *)buf);
         SK_LAUNCH_CHECK(ctx);
         SK_TRY(sk_fft2c_dev(ctx, big, (double *)buf, (double *)buf, 1, st));
         extract_oversampled_kernel<<<nblocks(ctx, per), 256, 0, st>>>(big, (const double2 *)buf, qpx, npixkern, conjugate, (double2 *)out + i * per);

@@ -268,12 +268,15 @@ def aw_kernel_fn2(yf, xf, wkerns, akerns, wbin, a1, a2, ctx=None):
 def w_kernel(theta, w, kernops: KernelOptions, conjugate=False, ctx=None):
     """src/Gridding.hs:610-619 for one or many w -> [qpx,qpx,s,s] (scalar w) or [nw,qpx,qpx,s,s]."""
     ctx = ctx or get_context()
-    if kernops.patHorShift or kernops.patVerShift or kernops.patTransMat is not None:
-        raise NotImplementedError("w_kernel: pattern shifts / transformation matrices are not supported by the CUDA generator")
     ws = f64(np.atleast_1d(w))
     npixff, npixkern, qpx = int(kernops.npixFF), int(kernops.npixKern), int(kernops.qpx)
     out = np.empty((ws.size, qpx, qpx, npixkern, npixkern), np.complex128)
-    ctx.check(ctx.lib.skagrid_w_kernels(ctx.h, float(theta), ws.size, ptr(ws), npixff, npixkern, qpx, int(bool(conjugate)), ptr(out)))
+    if kernops.patHorShift or kernops.patVerShift or kernops.patTransMat is not None:   # kernel_coordinates, src/Gridding.hs:620-635
+        t = None if kernops.patTransMat is None else f64(kernops.patTransMat).reshape(2, 2)
+        ctx.check(ctx.lib.skagrid_w_kernels_ex(ctx.h, float(theta), ws.size, ptr(ws), npixff, npixkern, qpx, int(bool(conjugate)), ptr(t),
+                                               float(kernops.patHorShift or 0), float(kernops.patVerShift or 0), ptr(out)))
+    else:
+        ctx.check(ctx.lib.skagrid_w_kernels(ctx.h, float(theta), ws.size, ptr(ws), npixff, npixkern, qpx, int(bool(conjugate)), ptr(out)))
     return out[0] if np.ndim(w) == 0 else out
 
 
@@ -368,10 +371,11 @@ def _round_half_away(x):
 
 
 def w_cache_imaging(kernops: KernelOptions, otargs: OtherImagingArgs, theta, lam, uvw, src, vis, ctx=None):
-    """src/Gridding.hs:399-449: w rounded to multiples of wstep, one conjugated w-kernel per step, convgrid2."""
+    """src/Gridding.hs:399-449: w rounded to multiples of wstep, one conjugated w-kernel per step, convgrid2.
+    otargs.kernelFunction / otargs.kernelCache (KernelF, :48-53: theta w a1 a2 t f kernops -> [qpx,qpx,s,s]) replace the default
+    w_kernel exactly as in the reference: kernel_cache = fromMaybe kernel_fn kernel_cache', called with the four Maybe arguments
+    set to Nothing (:410-412); the result is conjugated (:441)."""
     ctx = ctx or get_context()
-    if otargs.kernelCache is not None or otargs.kernelFunction is not None:
-        raise NotImplementedError("w_cache_imaging: custom kernel functions are not supported; the default w_kernel is used")
     u, v, w = _uvw(uvw)
     wstep = int(kernops.wstep if kernops.wstep is not None else 2000)
     rounded = (wstep * _round_half_away(w / float(wstep))).astype(np.int64)
@@ -379,7 +383,13 @@ def w_cache_imaging(kernops: KernelOptions, otargs: OtherImagingArgs, theta, lam
     steps = (wmax - wmin) // wstep + 1
     wbins = (rounded - wmin) // wstep
     ws = np.array([float(i * wstep + wmin) for i in range(steps)])
-    kernels = w_kernel(theta, ws, kernops, conjugate=True, ctx=ctx)
+    kernel_fn = otargs.kernelCache if otargs.kernelCache is not None else otargs.kernelFunction
+    if kernel_fn is None:
+        kernels = w_kernel(theta, ws, kernops, conjugate=True, ctx=ctx)
+    else:   # a caller-supplied kernel generator runs on the host, once per w step; the gridding stays on the GPU
+        kernels = np.conj(np.stack([c128(kernel_fn(theta, float(wi), None, None, None, None, kernops)) for wi in ws]))
+        if kernels.ndim != 5 or kernels.shape[1] != kernels.shape[2]:
+            raise ValueError("kernelFunction must return [qpx, qpx, s, s] kernels")
     return conv_imaging2(kernels, theta, lam, (u, v, w), wbins, vis, ctx=ctx)
 
 

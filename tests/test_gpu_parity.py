@@ -291,6 +291,23 @@ def test_aw_gridding_end_to_end(G, orc):
     assert abs(lhs - rhs) < 1e-10 * abs(lhs)
 
 
+def test_w_kernel_pattern_shift_and_transformation(G, orc):
+    """KernelOptions.patHorShift / patVerShift / patTransMat (kernel_coordinates, src/Gridding.hs:620-635): the far field is no
+    longer symmetric under transposition, so this also pins the transposing padder (:875) -- and its absence when qpx = 1 (:688)."""
+    theta = 0.05
+    t = np.array([[0.9, 0.2], [-0.1, 1.1]])
+    for qpx, npixff, s, dl, dm, tm in ((4, 32, 9, 0, 0, t), (4, 32, 9, 0.01, -0.02, None), (1, 32, 9, 0.01, -0.02, t), (2, 64, 15, -0.015, 0.005, t)):
+        ko = G.KernelOptions(qpx=qpx, npixFF=npixff, npixKern=s, patHorShift=dl, patVerShift=dm, patTransMat=tm)
+        for w in (0.0, 37.5, -120.0):
+            k = G.w_kernel(theta, w, ko)
+            ok = orc.w_kernel(theta, w, npixff, s, qpx, dl=dl, dm=dm, transmat=tm)
+            assert k.shape == ok.shape == (qpx, qpx, s, s)
+            assert rel_err(k, ok) < 1e-11
+    plain = G.w_kernel(theta, 37.5, G.KernelOptions(qpx=4, npixFF=32, npixKern=9))
+    assert rel_err(plain, G.w_kernel(theta, 37.5, G.KernelOptions(qpx=4, npixFF=32, npixKern=9, patTransMat=np.eye(2)))) < 1e-15
+    assert rel_err(plain, orc.w_kernel(theta, 37.5, 32, 9, 4)) < 1e-11
+
+
 def test_aw_gridding_config1_shape(G, orc):
     """BASELINE.json configs 1-3 at THEIR shape (src/ImageDataset.hs:32-33: theta 0.008 x lam 300000 = a 2400^2 grid; S = 15, Q = 8,
     64 w-planes, 64 antennas: the R' stand-in of SURVEY 8d, generated by scripts/bench_aw.py) against the oracle, image and grid;
@@ -347,6 +364,22 @@ def test_w_kernel_and_w_cache_imaging(G, orc):
     kern = np.stack([np.conj(orc.w_kernel(theta, float(i * 200 + wmin), 64, 15, 4)) for i in range(steps)])
     og = orc.convgrid(kern, np.zeros((200, 200), complex), u / lam, v / lam, vis, wbin=(rw - wmin) // 200)
     assert rel_err(g, og) < TOL
+    # OtherImagingArgs.kernelFunction / kernelCache (src/Gridding.hs:401-412): a caller-supplied KernelF replaces w_kernel, called
+    # with the four Maybe arguments as Nothing; kernelCache wins over kernelFunction when both are given
+    calls = []
+
+    def shifted(theta_, w_, a1, a2, t, f, kernops):
+        assert (a1, a2, t, f) == (None, None, None, None)
+        calls.append(w_)
+        return orc.w_kernel(theta_, w_, 64, 15, 4, dl=0.01, dm=-0.005)
+
+    g2 = G.w_cache_imaging(ko, G.OtherImagingArgs(kernelFunction=shifted), theta, lam, (u, v, w), None, vis)
+    assert calls == [float(i * 200 + wmin) for i in range(steps)]
+    kern2 = np.stack([np.conj(orc.w_kernel(theta, float(i * 200 + wmin), 64, 15, 4, dl=0.01, dm=-0.005)) for i in range(steps)])
+    assert rel_err(g2, orc.convgrid(kern2, np.zeros((200, 200), complex), u / lam, v / lam, vis, wbin=(rw - wmin) // 200)) < TOL
+    plain = lambda theta_, w_, a1, a2, t, f, kernops: orc.w_kernel(theta_, w_, 64, 15, 4)
+    g3 = G.w_cache_imaging(ko, G.OtherImagingArgs(kernelFunction=shifted, kernelCache=plain), theta, lam, (u, v, w), None, vis)
+    assert rel_err(g3, og) < TOL
 
 
 def test_do_imaging(G, orc):

@@ -187,3 +187,16 @@ def test_shift_convention_is_the_one_written_out_in_ShiftExample():
     yy, xx = np.mgrid[0:n, 0:n]
     m = np.where((yy + xx) % 2 == 1, -1.0, 1.0)
     assert np.abs(orc.ifft(a) - m * np.fft.ifft2(m * a)).max() < 1e-15
+
+
+def test_kernel_coordinates_options():
+    """src/Gridding.hs:620-635 in the oracle: identity options reproduce the plain w-kernel, the matrix acts as
+    (x, y) -> (t00 x + t10 y, t01 x + t11 y), the shifts are added last."""
+    from oracle import oracle as orc
+    l0, m0 = orc.kernel_coordinates(8, 0.1)
+    sc, sr = orc.coordinates2(8)
+    assert np.array_equal(l0, sc * 0.1) and np.array_equal(m0, sr * 0.1)
+    t = np.array([[2.0, 3.0], [5.0, 7.0]])
+    l, m = orc.kernel_coordinates(8, 0.1, dl=0.25, dm=-0.5, transmat=t)
+    assert np.allclose(l, 2.0 * l0 + 5.0 * m0 + 0.25) and np.allclose(m, 3.0 * l0 + 7.0 * m0 - 0.5)
+    assert np.array_equal(orc.w_kernel(0.05, 10.0, 16, 5, 2), orc.w_kernel(0.05, 10.0, 16, 5, 2, dl=0, dm=0, transmat=np.eye(2)))
