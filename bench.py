@@ -4,7 +4,7 @@
 Headline (`value`, every N): config 4 -- synthetic SKA1-Low-shaped visibilities, 8192^2 complex128 grid, support 15,
 oversampling 8, 32 w-planes, visibility-sharded over N GPUs, 1e8 visibilities PER GPU (weak scaling).  One step = one imaging
 major-cycle pass over one batch:
-    N = 1:  bin + uv-tile bucket sort -> tiled gridder -> hermitian + centred inverse FFT + real/max -> degridder
+    N = 1:  bin + uv-tile bucket sort -> tiled gridder -> hermitian half + complex-to-real centred inverse FFT + max -> degridder
     N > 1:  bin + bucket sort -> gridder -> NCCL reduce-scatter of the ACTIVE grid rows into row slabs
             -> [slab-distributed grid -> image (row FFTs, all-to-all transpose, column FFTs)  ||  NCCL all-gather of the
                reduced slabs] -> degridder of the rank's visibilities on the gathered grid
@@ -322,16 +322,16 @@ class Config4Step:
         if not self.slabbed:
             self.plan.update(self.u, self.v, self.wb, self.vis, check=False)   # bit-exact binning + bucket sort (part of gridding)
             rec(1)
-            self.grid.zero_()
+            (self.act if N_GRID % 2 == 0 else self.grid).zero_()     # the other rows are never written (even N: grid -> image leaves the grid alone)
             self.plan.grid(self.table, self.act, variant=self.variant)
             rec(2)
             if env.world > 1:
-                env.dist.all_reduce(env.torch.view_as_real(self.grid))
+                env.dist.all_reduce(env.torch.view_as_real(self.act))
             rec(3)
-            _, mx = dv.grid_to_image(self.grid, want_image=False)   # in place: the buffer now holds the transformed plane
+            _, mx = dv.grid_to_image(self.grid, want_image=False)   # hermitian half -> complex-to-real transform -> max
             self.image_max = mx
             rec(4)
-            self.plan.degrid(self.table, self.act, self.vis_out)    # adjoint pass over the same batch; the transformed plane stands in for the model grid
+            self.plan.degrid(self.table, self.act, self.vis_out)    # adjoint pass over the same batch; the gridded sum stands in for the model grid
             rec(5)
             return
         vs = self.vs

@@ -33,8 +33,9 @@
  * skagrid_conv_imaging2 (grid_out) and skagrid_grid_to_image accept a NULL grid pointer, meaning "the grid the
  * previous of these calls on this context left on the device" (no upload, no download; SKAGRID_EINVAL if there
  * is none of that shape).  A chain conv_imaging2 -> grid_to_image -> convdegrid2 then moves only visibilities
- * over PCIe, as the reference's single fused Accelerate program does.  skagrid_grid_to_image transforms in
- * place, so afterwards the resident buffer holds the (complex) image plane.
+ * over PCIe, as the reference's single fused Accelerate program does.  skagrid_grid_to_image leaves the resident grid
+ * as it is when n is even (complex-to-real route); for odd n it transforms in place and the resident buffer then holds the
+ * (complex) image plane.
  * Resident coordinates: the same four table functions (and the _mgpu_vis forms) keep the (u, v, wbin) they uploaded on
  * the device (up to 2^28 visibilities; for skagrid_conv_imaging2 the coordinates after the division by lam).  The next
  * call may pass u == v == wbin == NULL with the same count, meaning "at the coordinates of the previous call": an imaging
@@ -286,8 +287,10 @@ int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, 
 /* vis_out[k] = sum conj(table[slice_k][i,j]) * grid[...] for the plan's visibilities (others = 0). */
 int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, const double *grid,
                        double *vis_out, void *stream);
-/* In-place grid -> image stage on an n x n device grid: hermitian + centred inverse FFT; writes
- * real(image) into image (n*n doubles, may alias nothing) and the maximum into max_out (1 double). */
+/* Grid -> image stage on an n x n device grid: hermitian + centred inverse FFT; writes real(image) into image (n*n
+ * doubles, may be NULL) and the maximum into max_out (1 double).  Even n: only the real part is wanted, so the hermitian
+ * half of the spectrum goes through a complex-to-REAL transform (half the passes of the complex one) and `grid` is not
+ * modified; odd n: `grid` is transformed in place. */
 int skagrid_dev_grid_to_image(skagrid_ctx *ctx, int64_t n, double *grid, double *image,
                               double *max_out, void *stream);
 /* Synthetic SKA1-Low-shaped visibilities generated on the device: counter-based

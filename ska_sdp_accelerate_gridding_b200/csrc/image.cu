@@ -14,6 +14,8 @@
 //   pass 2  (-1)^(x+y) / N^2, real part, block maximum -> one atomic per block.
 // For even N, shift2D . ifft2 . ishift2D (G) == M .* ifft2(M .* G), M = (-1)^(x+y); odd N uses
 // explicit rotations.
+#include <cstdlib>
+
 #include "common.cuh"
 
 static const char *cufft_str(cufftResult r) {
@@ -60,6 +62,35 @@ static int get_fft_plan(skagrid_ctx *ctx, i64 n, cufftHandle *out) {
     }
     ctx->fft_plans[n] = h;
     ctx->fft_work[n] = wb;
+    *out = h;
+    return SKAGRID_OK;
+}
+
+// n x n complex-to-real plan (hermitian half-spectrum [n][n/2+1] -> real [n][n]); key 3 << 40 | n in the plan cache
+static int get_fft_plan_z2d(skagrid_ctx *ctx, i64 n, cufftHandle *out) {
+    const i64 key = ((i64)3 << 40) | n;
+    auto it = ctx->fft_plans.find(key);
+    if (it != ctx->fft_plans.end()) { *out = it->second; return SKAGRID_OK; }
+    if (n <= 0 || n > (1 << 17)) return sk_fail(ctx, SKAGRID_EINVAL, "fft: size %lld out of range", n);
+    cufftHandle h;
+    SK_CUFFT(ctx, cufftCreate(&h));
+    size_t ws = 0;
+    cufftResult r = cufftSetAutoAllocation(h, 0);
+    if (r == CUFFT_SUCCESS) r = cufftMakePlan2d(h, (int)n, (int)n, CUFFT_Z2D, &ws);
+    if (r != CUFFT_SUCCESS) { cufftDestroy(h); return sk_fail(ctx, SKAGRID_ECUDA, "cufftMakePlan2d(%lld, Z2D): %s", n, cufft_str(r)); }
+    DevBuf wb;
+    if (ws > 0) {
+        if (cudaMalloc(&wb.p, ws) != cudaSuccess) {
+            cudaGetLastError();
+            cufftDestroy(h);
+            return sk_fail(ctx, SKAGRID_ENOMEM, "fft: work area of %zu bytes for n=%lld (Z2D)", ws, n);
+        }
+        wb.bytes = ws;
+        r = cufftSetWorkArea(h, wb.p);
+        if (r != CUFFT_SUCCESS) { cudaFree(wb.p); cufftDestroy(h); return sk_fail(ctx, SKAGRID_ECUDA, "cufftSetWorkArea: %s", cufft_str(r)); }
+    }
+    ctx->fft_plans[key] = h;
+    ctx->fft_work[key] = wb;
     *out = h;
     return SKAGRID_OK;
 }
@@ -193,9 +224,73 @@ __global__ void __launch_bounds__(256) real_max_kernel(i64 n, const double2 *__r
 
 __global__ void set_double_kernel(double *p, double v) { *p = v; }
 
-// In place on `grid`: hermitian -> centred inverse FFT; image = real part; max_out = maximum pixel.
+// Even n, real output only: real(ifft(A)) = ifft(Herm(A)) with Herm(A)[k] = (A[k] + conj(A[-k])) / 2, and an exactly hermitian
+// spectrum needs only its half [n][n/2+1] and a complex-to-REAL transform -- half the passes of the Z2Z route and no N^2 complex
+// intermediate.  With A = M (.) make_grid_hermitian(g), M = (-1)^(x+y) (src/Gridding.hs:585-605, :828-829):
+//   x != 0 and y != 0:  make_grid_hermitian already pairs the cells: Herm(A) = M (g[y,x] + conj g[n-y,n-x])
+//   row 0 / column 0:    left unsymmetrised by the reference (its ifft has an imaginary part there, which `map real` drops):
+//                        Herm(A) = M (g[y,x] + conj g[(n-y)%n,(n-x)%n]) / 2
+// half[y][x] for x <= n/2.  The grid itself is NOT modified.
+__global__ void __launch_bounds__(256) herm_half_kernel(i64 n, const double2 *__restrict__ g, double2 *__restrict__ half) {
+    const i64 hw = n / 2 + 1;
+    const i64 total = n * hw;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += stride) {
+        const i64 y = c / hw, x = c - y * hw;
+        const i64 ym = y == 0 ? 0 : n - y, xm = x == 0 ? 0 : n - x;
+        const double2 a = g[y * n + x], b = g[ym * n + xm];
+        double f = (x == 0 || y == 0) ? 0.5 : 1.0;
+        if ((x + y) & 1) f = -f;
+        half[c] = make_double2(f * (a.x + b.x), f * (a.y - b.y));
+    }
+}
+
+// image[y,x] = (-1)^(x+y) / n^2 * re[y,x] (in place when image == re); block maximum into max_out
+__global__ void __launch_bounds__(256) real_finish_kernel(i64 n, const double *re, double *image, double scale, double *__restrict__ max_out) {
+    __shared__ double wmax[8];
+    const i64 total = n * n;
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    double m = -INFINITY;
+    for (i64 c = (i64)blockIdx.x * blockDim.x + threadIdx.x; c < total; c += stride) {
+        const i64 y = c / n, x = c - y * n;
+        const double r = (((x + y) & 1) ? -scale : scale) * re[c];
+        if (image) image[c] = r;
+        m = fmax(m, r);
+    }
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; ++i) m = fmax(m, wmax[i]);
+        if (max_out) atomic_max_double(max_out, m);
+    }
+}
+
+static int grid_to_image_c2r(skagrid_ctx *ctx, i64 n, const double *grid, double *image, double *max_out, cudaStream_t st) {
+    cufftHandle plan;
+    SK_TRY(get_fft_plan_z2d(ctx, n, &plan));
+    SK_CUFFT(ctx, cufftSetStream(plan, st));
+    void *half, *re = image;
+    SK_TRY(sk_scratch(ctx, "g2i_half", (size_t)(n * (n / 2 + 1)) * sizeof(double2), &half));
+    if (!re) SK_TRY(sk_scratch(ctx, "g2i_real", (size_t)(n * n) * sizeof(double), &re));
+    herm_half_kernel<<<nblocks(ctx, n * (n / 2 + 1)), 256, 0, st>>>(n, (const double2 *)grid, (double2 *)half);
+    SK_LAUNCH_CHECK(ctx);
+    SK_CUFFT(ctx, cufftExecZ2D(plan, (cufftDoubleComplex *)half, (cufftDoubleReal *)re));
+    ctx->launches++;
+    real_finish_kernel<<<nblocks(ctx, n * n), 256, 0, st>>>(n, (const double *)re, image, 1.0 / ((double)n * (double)n), max_out);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
+// hermitian -> centred inverse FFT; image = real part; max_out = maximum pixel.  Even n: complex-to-real route above, `grid`
+// is left as it is.  Odd n (and SKAGRID_G2I_Z2Z=1): in place on `grid`, which then holds the complex image plane.
 int sk_grid_to_image_dev(skagrid_ctx *ctx, i64 n, double *grid, double *image, double *max_out, cudaStream_t st) {
     if (n <= 0) return sk_fail(ctx, SKAGRID_EINVAL, "grid_to_image: n = %lld", n);
+    static const int force_z2z = getenv("SKAGRID_G2I_Z2Z") ? atoi(getenv("SKAGRID_G2I_Z2Z")) : 0;  // A/B measurements
+    if (n % 2 == 0 && !force_z2z) {
+        if (max_out) { set_double_kernel<<<1, 1, 0, st>>>(max_out, -INFINITY); SK_LAUNCH_CHECK(ctx); }
+        return grid_to_image_c2r(ctx, n, grid, image, max_out, st);
+    }
     cufftHandle plan;
     SK_TRY(get_fft_plan(ctx, n, &plan));
     SK_CUFFT(ctx, cufftSetStream(plan, st));

@@ -345,7 +345,8 @@ def scatter_add_(out, sidx, back, ctx=None):
 
 
 def grid_to_image(grid, want_image=True, ctx=None):
-    """In place on `grid` (n x n complex128 CUDA tensor): hermitian -> centred IFFT; returns (image or None, max tensor)."""
+    """hermitian -> centred IFFT -> real of an n x n complex128 CUDA grid; returns (image or None, max tensor).  `grid` is
+    left untouched for even n (complex-to-real transform of the hermitian half), transformed in place for odd n."""
     ctx = ctx or context_for_current_device()
     _chk(grid, torch.complex128, "grid")
     n = grid.shape[0]
