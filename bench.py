@@ -544,6 +544,8 @@ def run_config5(env, args):
         rec(2)
         if peer:
             _, _, mx = ts.image_peer(anz, want_image=False, sync_max=False)
+        elif world == 1:
+            _, mx = dv.grid_to_image(slab, want_image=False)      # one GPU holds the whole grid: hermitian half + complex-to-real transform
         else:
             _, _, mx = D.slab_grid_to_image(slab, bounds, want_image=False, nonzero=nz, sync_max=False)   # in place: slab -> transformed rows
         marks["max"] = mx
