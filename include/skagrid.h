@@ -364,7 +364,9 @@ int skagrid_dev_scatter_add(skagrid_ctx *ctx, int64_t n, const uint32_t *d_sidx,
  *                 (width_bytes x rows, pitches in bytes)
  *   peer_gather   the same for up to 64 (destination, source, bytes) segments in ONE kernel: the SMs pull from peer memory
  *                 (8-byte aligned segments; HOST arrays of pointers / sizes); peer_gather2d the strided form for 16-byte
- *                 elements, all segments with the same width and destination pitch (the transpose of the slab image) */
+ *                 elements, all segments with the same width and destination pitch (the transpose of the slab image).
+ *                 max_blocks > 0 caps the kernel's grid (one block per SM, say) so that kernels on another stream run
+ *                 beside the exchange; 0 = fill the device */
 int skagrid_ipc_alloc(skagrid_ctx *ctx, int64_t bytes, void **d_ptr, unsigned char handle[64]);
 int skagrid_ipc_free(skagrid_ctx *ctx, void *d_ptr);
 int skagrid_ipc_open(skagrid_ctx *ctx, const unsigned char handle[64], void **d_ptr);
@@ -375,9 +377,9 @@ int skagrid_dev_peer_barrier(skagrid_ctx *ctx, int nranks, int rank, uint32_t *c
                              void *stream);
 int skagrid_dev_peer_copy(skagrid_ctx *ctx, void *d_dst, const void *d_src, int64_t bytes, void *stream);
 int skagrid_dev_peer_gather(skagrid_ctx *ctx, int nseg, void *const *d_dst, const void *const *d_src, const int64_t *bytes,
-                            void *stream);
+                            int max_blocks, void *stream);
 int skagrid_dev_peer_gather2d(skagrid_ctx *ctx, int nseg, void *const *d_dst, int64_t dpitch, const void *const *d_src,
-                              const int64_t *spitch, int64_t width_bytes, const int64_t *rows, void *stream);
+                              const int64_t *spitch, int64_t width_bytes, const int64_t *rows, int max_blocks, void *stream);
 int skagrid_dev_peer_copy2d(skagrid_ctx *ctx, void *d_dst, int64_t dpitch, const void *d_src, int64_t spitch,
                             int64_t width_bytes, int64_t rows, void *stream);
 /* frac_coord (src/Gridding.hs:126-140) on device arrays. */

@@ -186,7 +186,8 @@ extern "C" int skagrid_dev_peer_sum(skagrid_ctx *ctx, int npeers, double *const 
     return SKAGRID_OK;
 }
 
-extern "C" int skagrid_dev_peer_gather(skagrid_ctx *ctx, int nseg, void *const *d_dst, const void *const *d_src, const int64_t *bytes, void *stream) {
+extern "C" int skagrid_dev_peer_gather(skagrid_ctx *ctx, int nseg, void *const *d_dst, const void *const *d_src, const int64_t *bytes, int max_blocks,
+                                       void *stream) {
     SK_TRY(sk_api_enter(ctx));
     if (nseg < 0 || nseg > IPC_MAX) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather: 0..%d segments", IPC_MAX);
     if (nseg == 0) return SKAGRID_OK;
@@ -206,7 +207,8 @@ extern "C" int skagrid_dev_peer_gather(skagrid_ctx *ctx, int nseg, void *const *
         ++S.count;
     }
     if (S.count == 0) return SKAGRID_OK;
-    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((nmax + 255) / 256, (i64)ctx->sm_count * 8));
+    // max_blocks > 0 caps the grid (e.g. one block per SM) so that kernels of another stream can run beside the exchange
+    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((nmax + 255) / 256, max_blocks > 0 ? (i64)max_blocks : (i64)ctx->sm_count * 8));
     (void)total;
     ipc_gather_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(S, nmax);
     SK_LAUNCH_CHECK(ctx);
@@ -215,7 +217,7 @@ extern "C" int skagrid_dev_peer_gather(skagrid_ctx *ctx, int nseg, void *const *
 
 // All segments share the destination pitch and the width (one column block); pitches and width in BYTES, multiples of 16.
 extern "C" int skagrid_dev_peer_gather2d(skagrid_ctx *ctx, int nseg, void *const *d_dst, int64_t dpitch, const void *const *d_src,
-                                         const int64_t *spitch, int64_t width_bytes, const int64_t *rows, void *stream) {
+                                         const int64_t *spitch, int64_t width_bytes, const int64_t *rows, int max_blocks, void *stream) {
     SK_TRY(sk_api_enter(ctx));
     if (nseg < 0 || nseg > IPC_MAX) return sk_fail(ctx, SKAGRID_EINVAL, "dev_peer_gather2d: 0..%d segments", IPC_MAX);
     if (nseg == 0 || width_bytes <= 0) return SKAGRID_OK;
@@ -237,7 +239,7 @@ extern "C" int skagrid_dev_peer_gather2d(skagrid_ctx *ctx, int nseg, void *const
         ++S.count;
     }
     if (S.count == 0) return SKAGRID_OK;
-    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((rmax * S.width + 255) / 256, (i64)ctx->sm_count * 8));
+    const unsigned blocks = (unsigned)std::max<i64>(1, std::min<i64>((rmax * S.width + 255) / 256, max_blocks > 0 ? (i64)max_blocks : (i64)ctx->sm_count * 8));
     (void)total;
     ipc_gather2d_kernel<<<blocks, 256, 0, sk_stream(ctx, stream)>>>(S, rmax);
     SK_LAUNCH_CHECK(ctx);

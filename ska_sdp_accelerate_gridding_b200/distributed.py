@@ -433,7 +433,9 @@ class VisShardedGridder:
             sm = self.world >= 4
         if not sm:
             return self.pg.pull(copies, join=join, pool=1)
-        h = self.pg.gather_async(copies)
+        # one block per SM: 148 x 256 threads x 7 peers x 16 bytes in flight cover the NVLink bandwidth-delay product, and the small
+        # kernels of the image stage run beside the exchange instead of behind it
+        h = self.pg.gather_async(copies, max_blocks=0 if join else self.pg.ctx_sm_count())
         if join:
             h.wait()
             return None

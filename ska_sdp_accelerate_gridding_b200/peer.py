@@ -126,6 +126,9 @@ class PeerGroup:
         self.streams = self.pools[0]
         self._fork = torch.cuda.Event()
 
+    def ctx_sm_count(self):
+        return int(torch.cuda.get_device_properties(self.ctx.device).multi_processor_count)
+
     def barrier(self):
         """Stream-ordered barrier on the current stream: the kernels enqueued after it on ANY rank start only when every
         rank's stream has reached it.  No host synchronisation."""
@@ -152,17 +155,18 @@ class PeerGroup:
         else:
             self.pull(copies)
 
-    def gather_async(self, copies):
-        """`gather` on a side stream, after everything already on the current stream; returns a handle whose wait() joins it."""
+    def gather_async(self, copies, max_blocks=0):
+        """`gather` on a side stream, after everything already on the current stream; returns a handle whose wait() joins it.
+        max_blocks caps the kernel's grid so that what the current stream launches next runs beside it."""
         main = torch.cuda.current_stream()
         side = self.pools[1][0]
         self._fork.record(main)
         side.wait_event(self._fork)
         with torch.cuda.stream(side):
-            self.gather(copies)
+            self.gather(copies, max_blocks=max_blocks)
         return _Pending([side])
 
-    def gather(self, copies):
+    def gather(self, copies, max_blocks=0):
         """copies: iterable of (dst address, src address, bytes), 8-byte aligned: ONE kernel on the current stream in which the
         SMs pull (or, with peer addresses as destinations, push) every segment through peer memory, all peers at once
         (skagrid_dev_peer_gather)."""
@@ -173,7 +177,13 @@ class PeerGroup:
         dst = (C.c_void_p * n)(*[C.c_void_p(c[0]) for c in copies])
         src = (C.c_void_p * n)(*[C.c_void_p(c[1]) for c in copies])
         nb = (C.c_int64 * n)(*[int(c[2]) for c in copies])
-        self.ctx.check(self.ctx.lib.skagrid_dev_peer_gather(self.ctx.h, n, dst, src, nb, _stream()))
+        if all(c[2] % 16 == 0 and c[0] % 16 == 0 and c[1] % 16 == 0 for c in copies) and len({c[2] for c in copies}) == 1:
+            # equal, 16-byte aligned segments (slabs): the strided kernel with one "row" per segment moves 16 bytes per load
+            one = (C.c_int64 * n)(*[1] * n)
+            sp = (C.c_int64 * n)(*[int(c[2]) for c in copies])
+            self.ctx.check(self.ctx.lib.skagrid_dev_peer_gather2d(self.ctx.h, n, dst, int(copies[0][2]), src, sp, int(copies[0][2]), one, int(max_blocks), _stream()))
+            return
+        self.ctx.check(self.ctx.lib.skagrid_dev_peer_gather(self.ctx.h, n, dst, src, nb, int(max_blocks), _stream()))
 
     def gather2d(self, copies):
         """copies: iterable of (dst, dpitch, src, spitch, width_bytes, rows) with one common width and destination pitch, 16-byte
@@ -186,7 +196,7 @@ class PeerGroup:
         src = (C.c_void_p * n)(*[C.c_void_p(c[2]) for c in copies])
         sp = (C.c_int64 * n)(*[int(c[3]) for c in copies])
         rows = (C.c_int64 * n)(*[int(c[5]) for c in copies])
-        self.ctx.check(self.ctx.lib.skagrid_dev_peer_gather2d(self.ctx.h, n, dst, int(copies[0][1]), src, sp, int(copies[0][4]), rows, _stream()))
+        self.ctx.check(self.ctx.lib.skagrid_dev_peer_gather2d(self.ctx.h, n, dst, int(copies[0][1]), src, sp, int(copies[0][4]), rows, 0, _stream()))
 
     def pull(self, copies, join=True, pool=0):
         """copies: iterable of (dst address, src address, bytes) or (dst, dpitch, src, spitch, width_bytes, rows): enqueued

@@ -576,6 +576,13 @@ def test_peer_memory_kernels_single_device():
     assert np.array_equal(dst.cpu().numpy(), ref)
     with pytest.raises(Exception):
         pg.gather([(dst.data_ptr() + 4, src.data_ptr(), 64)])       # misaligned
+    # equal 16-byte aligned segments take the 16-byte kernel, also with a capped grid and from a side stream
+    dst2 = torch.zeros(3 * 4096, dtype=torch.float64, device="cuda")
+    src2 = _t(rng.standard_normal(3 * 4096))
+    hnd = pg.gather_async([(dst2.data_ptr() + k * 4096 * 8, src2.data_ptr() + (2 - k) * 4096 * 8, 4096 * 8) for k in range(3)], max_blocks=2)
+    hnd.wait()
+    hs2 = src2.cpu().numpy()
+    assert np.array_equal(dst2.cpu().numpy(), np.concatenate([hs2[2 * 4096:], hs2[4096:2 * 4096], hs2[:4096]]))
     rows, wid, cw = 37, 64, 16
     a = _t(_rand_c(rng, (2, rows, wid)))
     cols = torch.zeros((2 * rows, cw), dtype=torch.complex128, device="cuda")
