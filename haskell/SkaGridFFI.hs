@@ -18,6 +18,7 @@ module SkaGridFFI
   , convgrid, convgrid2, convgridAW, convdegrid2, convdegridAW
   , withSkaGrids, MultiMode(..), convgrid2Multi, convdegrid2Multi
   , makeGridHermitian, ifft, gridToImage, awImaging, awGridding
+  , gridSide, wKernel
   ) where
 
 import Control.Exception (bracket)
@@ -90,8 +91,32 @@ foreign import ccall safe "skagrid_aw_gridding"  c_aw_gridding
   -> Int64 -> Ptr Double -> Ptr Double -> Ptr Double -> Ptr Int64 -> Ptr Int64 -> CDouble -> Ptr Double
   -> Ptr Double -> Ptr Double -> Ptr Double -> IO CInt
 
+foreign import ccall unsafe "skagrid_grid_side"  c_grid_side   :: CDouble -> Int64 -> Int64   -- pure arithmetic: no blocking, `unsafe` is fine
+foreign import ccall safe "skagrid_w_kernels_ex" c_w_kernels_ex
+  :: Ctx -> CDouble -> Int64 -> Ptr Double -> Int64 -> Int64 -> Int64 -> CInt -> Ptr Double -> CDouble -> CDouble -> Ptr Double -> IO CInt
+
 type F = Double
 type Visibility = Complex Double
+
+-- | N = P.round (theta * lam) (src/Gridding.hs:466), the side every imaging entry point of the library allocates
+gridSide :: F -> Int -> Int
+gridSide theta lam = fromIntegral (c_grid_side (realToFrac theta) (fromIntegral lam))
+
+-- | w_kernel (src/Gridding.hs:610-619) for a list of w, with the KernelOptions fields that move the far-field coordinates
+-- (kernel_coordinates, :620-635): (patHorShift, patVerShift) and patTransMat as (t00, t01, t10, t11).
+-- -> [nw, qpx, qpx, npixKern, npixKern]; conjugate = True is what w_cache_imaging asks for (:441).
+wKernel :: Ctx -> F -> [F] -> (Int, Int, Int) -> (Int, Int) -> Maybe (F, F, F, F) -> Bool -> IO (Array DIM5 Visibility)
+wKernel ctx theta ws (qpx, npixFF, npixKern) (dl, dm) tmat conj = do
+  let nw = length ws
+      total = nw * qpx * qpx * npixKern * npixKern
+  out <- newCplx total
+  withArrayLen (map realToFrac ws :: [Double]) $ \_ pw -> withForeignPtr out $ \po ->
+    let call pt = c_w_kernels_ex ctx (realToFrac theta) (fromIntegral nw) pw (fromIntegral npixFF) (fromIntegral npixKern) (fromIntegral qpx)
+                                 (if conj then 1 else 0) pt (fromIntegral dl) (fromIntegral dm) po >>= check ctx "w_kernels_ex"
+    in case tmat of
+         Nothing -> call nullPtr
+         Just (a, b, c, d) -> withArrayLen [a, b, c, d] $ \_ pt -> call pt
+  return (fromForeignPtrs (Z :. nw :. qpx :. qpx :. npixKern :. npixKern) (castForeignPtr out))
 
 -- | One context per OS thread / GPU (include/skagrid.h "Threading").
 withSkaGrid :: Int -> (Ctx -> IO a) -> IO a
