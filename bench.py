@@ -17,6 +17,7 @@ Extra sub-records on the same JSON line:
            bucket -> tiled gridder into the owned slab -> slab-distributed grid -> image -> degridder on the owned rows ->
            all-to-all of the partial sums back -> scatter-add.  No grid reduction.
   parity   on-box correctness: linearity checksum of the reduced grid, GPU vs CPU oracle on a sample, adjoint identity
+  prepared (N = 1) the same step when the plan is kept and only the visibility values change (a major cycle over the same uvw)
   aw       (N = 1) the AW path of configs 1-3 on the R' stand-in through skagrid_aw_gridding, with oracle parity
   e2e      the config-4 step through the host-pointer C ABI from pinned host buffers, every host<->device copy (and, at
            N > 1, the NCCL reduction of the per-process grids) inside the timed region
@@ -66,7 +67,7 @@ def parse():
     ap.add_argument("--vis", type=float, default=1e8, help="visibilities per GPU per step (weak); total of the strong sub-record")
     ap.add_argument("--uniform", action="store_true", help="uniform uv coverage instead of the core-dominated mixture")
     ap.add_argument("--variant", type=int, default=0, help="gridder variant (gridder.cu: 0 default, 1 atomic scatter, 2..5 A/B layouts)")
-    ap.add_argument("--skip", default="", help="comma list of sub-records to skip: strong,config5,parity,aw,e2e,cpu")
+    ap.add_argument("--skip", default="", help="comma list of sub-records to skip: strong,config5,parity,prepared,aw,e2e,cpu")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-vis", type=float, default=None, help="visibilities per e2e step (default: --vis)")
@@ -834,6 +835,25 @@ def main():
                                    "sample": f"first {pr['oracle_sample']} visibilities of the same workload, grid + degrid on the host (oracle/oracle.c, OpenMP); "
                                              "the same run provides parity.grid/degrid_max_abs_err_over_peak",
                                    "grid_s": pr["cpu_grid_s"], "degrid_s": pr["cpu_degrid_s"]}
+    # ---------------------------------------------------------------- major cycle over the same uvw: the plan is kept, only the visibilities change
+    if world == 1 and "prepared" not in args.skip:
+        c4.plan.update(c4.u, c4.v, c4.wb, c4.vis, check=True)
+        e = [env.ev() for _ in range(2)]
+
+        def pstep():
+            c4.plan.set_vis(c4.vis)                      # rec[r].vis = vis[rec[r].index]: no binning, no sort
+            (c4.act if N_GRID % 2 == 0 else c4.grid).zero_()
+            c4.plan.grid(table, c4.act, variant=args.variant)
+            dv.grid_to_image(c4.grid, want_image=False)
+            c4.plan.degrid(table, c4.act, c4.vis_out)
+
+        ms_p, _, _ = env.time_steps(pstep, 3, max(3, min(args.steps, 10)))
+        e[0].record(); c4.plan.set_vis(c4.vis); e[1].record()
+        torch.cuda.synchronize()
+        out["prepared"] = {"value": V / (ms_p * 1e-3), "unit": "vis/s", "ms_per_step": ms_p, "set_vis_ms": e[0].elapsed_time(e[1]),
+                           "step": "Plan.set_vis (new visibility values into the sorted records) -> gridder -> grid->image -> degridder",
+                           "note": "NOT the headline: the headline step re-bins and re-sorts every time (SURVEY 8d counts the sort as part of gridding); this is "
+                                   "what a major cycle over the same uvw costs once the plan exists"}
     c4.close()
 
     # ---------------------------------------------------------------- strong scaling companion: 1e8 visibilities in total

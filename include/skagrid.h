@@ -274,6 +274,10 @@ int skagrid_dev_plan_alloc(skagrid_ctx *ctx, const skagrid_geom *geom, int64_t c
                            skagrid_plan **out);
 int skagrid_dev_plan_update_packed(skagrid_ctx *ctx, skagrid_plan *plan, int64_t count, const double *d_rec,
                                    int width, void *stream);
+/* New visibility values at the coordinates the plan was built from (d_vis: `count` complex numbers in the caller's order):
+ * the records keep their place, only their visibilities are refreshed.  For major cycles over the same uvw: the binning and
+ * the bucket sort are done once per data set. */
+int skagrid_dev_plan_set_vis(skagrid_ctx *ctx, skagrid_plan *plan, const double *d_vis, void *stream);
 /* Plan statistics: [0] visibilities kept, [1] dropped (no tap on the owned rows), [2] work items,
  * [3] uv tiles, [4] non-empty tiles.  Synchronises `stream`. */
 int skagrid_dev_plan_stats(skagrid_ctx *ctx, skagrid_plan *plan, void *stream, int64_t stats[5]);

@@ -425,6 +425,29 @@ extern "C" int skagrid_dev_plan_update_packed(skagrid_ctx *ctx, skagrid_plan *pl
                      sk_stream(ctx, stream));
 }
 
+// New visibility VALUES for the coordinates the plan was built from: rec[r].vis = vis[rec[r].index] (the caller's order).
+// An imaging major cycle grids residuals of the SAME uvw again and again; with this the binning and the bucket sort are paid
+// once per data set, not once per cycle (sequential pass over the records, one random 16-byte read per visibility).
+__global__ void __launch_bounds__(256) plan_set_vis_kernel(const uint32_t *__restrict__ counters, VisRec *rec, const double2 *__restrict__ vis) {
+    const i64 kept = (i64)counters[2];
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < kept; r += stride) {
+        const uint32_t idx = reinterpret_cast<const uint4 *>(rec + r)[1].z;
+        *reinterpret_cast<double2 *>(rec + r) = vis[idx];
+    }
+}
+
+extern "C" int skagrid_dev_plan_set_vis(skagrid_ctx *ctx, skagrid_plan *plan, const double *d_vis, void *stream) {
+    if (!ctx || !plan) return SKAGRID_EINVAL;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (plan->count == 0) return SKAGRID_OK;
+    if (!d_vis) return sk_fail(ctx, SKAGRID_EINVAL, "plan_set_vis: NULL visibilities");
+    plan_set_vis_kernel<<<ctx->sm_count * 8, 256, 0, sk_stream(ctx, stream)>>>(plan->d_counters, plan->d_rec, reinterpret_cast<const double2 *>(d_vis));
+    SK_LAUNCH_CHECK(ctx);
+    plan->has_vis = 1;
+    return SKAGRID_OK;
+}
+
 extern "C" int skagrid_dev_plan_stats(skagrid_ctx *ctx, skagrid_plan *plan, void *stream, int64_t stats[5]) {
     if (!ctx || !plan || !stats) return SKAGRID_EINVAL;
     SK_CUDA(ctx, cudaSetDevice(ctx->device));

@@ -237,6 +237,14 @@ class Plan:
     def check(self):
         check_errors(self.ctx)
 
+    def set_vis(self, vis):
+        """New visibility values (caller's order, same count) at the coordinates the plan was built from: no re-binning, no
+        re-sorting -- what a major cycle over the same uvw needs (skagrid_dev_plan_set_vis)."""
+        _chk(vis, torch.complex128, "vis")
+        if vis.numel() != self.count:
+            raise ValueError("vis must have one value per visibility of the plan's batch")
+        self.ctx.check(self.ctx.lib.skagrid_dev_plan_set_vis(self.ctx.h, self.h, _p(vis), _stream()))
+
     def stats(self):
         out = (C.c_int64 * 5)()
         self.ctx.check(self.ctx.lib.skagrid_dev_plan_stats(self.ctx.h, self.h, _stream(), C.byref(out)))

@@ -534,6 +534,29 @@ def test_route_kernels_against_torch_reference(orc):
     p2.update(_t(u[ok]), _t(v[ok]), _t(wb[ok]), _t(vis[ok]))
 
 
+def test_plan_set_vis_reuses_the_sort(orc):
+    """Plan.set_vis: new visibility values at the same coordinates grid exactly like a freshly built plan -- also for a plan that
+    was built without visibilities (degrid-only) and for a slab plan that drops part of the batch."""
+    import torch
+    from ska_sdp_accelerate_gridding_b200 import device as dv
+    rng = np.random.default_rng(12)
+    n, s, q, nw, cnt = 256, 15, 8, 3, 30000
+    gcf = _rand_c(rng, (nw, q, q, s, s))
+    u, v = rng.uniform(-0.52, 0.52, cnt), rng.uniform(-0.52, 0.52, cnt)
+    wb = rng.integers(0, nw, cnt)
+    va, vb = _rand_c(rng, cnt), _rand_c(rng, cnt)
+    for rows, first in (((0, n), va), ((64, 200), None)):
+        plan = dv.Plan(n, n, gcf.shape, _t(u), _t(v), _t(wb), None if first is None else _t(first), rows=rows)
+        plan.set_vis(_t(vb))
+        g = torch.zeros((rows[1] - rows[0], n), dtype=torch.complex128, device="cuda")
+        plan.grid(_t(gcf), g)
+        og = orc.convgrid(gcf, np.zeros((n, n), complex), u, v, vb, wbin=wb)
+        assert rel_err(g.cpu().numpy(), og[rows[0]:rows[1]]) < TOL
+        with pytest.raises(ValueError):
+            plan.set_vis(_t(vb[:-1]))
+        plan.close()
+
+
 def test_peer_memory_kernels_single_device():
     """csrc/ipc.cu on ONE device: the exchange kernels do not care whether a pointer is local or an opened peer buffer, so local
     buffers stand in for the peers (tests/mgpu_check.py runs the real thing on 2-8 GPUs).  The barrier protocol is exercised by
