@@ -274,10 +274,13 @@ int skagrid_dev_plan_alloc(skagrid_ctx *ctx, const skagrid_geom *geom, int64_t c
                            skagrid_plan **out);
 int skagrid_dev_plan_update_packed(skagrid_ctx *ctx, skagrid_plan *plan, int64_t count, const double *d_rec,
                                    int width, void *stream);
-/* New visibility values at the coordinates the plan was built from (d_vis: `count` complex numbers in the caller's order):
- * the records keep their place, only their visibilities are refreshed.  For major cycles over the same uvw: the binning and
- * the bucket sort are done once per data set. */
-int skagrid_dev_plan_set_vis(skagrid_ctx *ctx, skagrid_plan *plan, const double *d_vis, void *stream);
+/* New visibility values at the coordinates the plan was built from: the records keep their place, only their visibilities
+ * are refreshed.  For major cycles over the same uvw: the binning and the bucket sort are done once per data set.
+ * in_plan_order == 0: d_vis holds `count` complex numbers in the caller's order (one random 16-byte read per record);
+ * != 0: d_vis[r] belongs to record r -- the caller permuted its data once with plan_order (d_index[r] = position of record
+ * r's visibility in the caller's arrays, r < plan_stats[0]) and the refresh is a sequential pass. */
+int skagrid_dev_plan_set_vis(skagrid_ctx *ctx, skagrid_plan *plan, const double *d_vis, int in_plan_order, void *stream);
+int skagrid_dev_plan_order(skagrid_ctx *ctx, skagrid_plan *plan, uint32_t *d_index, void *stream);
 /* Plan statistics: [0] visibilities kept, [1] dropped (no tap on the owned rows), [2] work items,
  * [3] uv tiles, [4] non-empty tiles.  Synchronises `stream`. */
 int skagrid_dev_plan_stats(skagrid_ctx *ctx, skagrid_plan *plan, void *stream, int64_t stats[5]);

@@ -82,7 +82,8 @@ _SIGS = {
     "skagrid_dev_peer_gather": [vp, ip, vp, vp, vp, ip, vp],
     "skagrid_dev_peer_gather2d": [vp, ip, vp, i64, vp, vp, i64, vp, ip, vp],
     "skagrid_dev_peer_copy2d": [vp, vp, i64, vp, i64, i64, i64, vp],
-    "skagrid_dev_plan_set_vis": [vp, vp, vp, vp],
+    "skagrid_dev_plan_set_vis": [vp, vp, vp, ip, vp],
+    "skagrid_dev_plan_order": [vp, vp, vp, vp],
     "skagrid_dev_plan_stats": [vp, vp, vp, C.POINTER(i64 * 5)],
     "skagrid_dev_grid": [vp, vp, vp, vp, ip, vp],
     "skagrid_dev_degrid": [vp, vp, vp, vp, vp, vp],

@@ -428,23 +428,46 @@ extern "C" int skagrid_dev_plan_update_packed(skagrid_ctx *ctx, skagrid_plan *pl
 // New visibility VALUES for the coordinates the plan was built from: rec[r].vis = vis[rec[r].index] (the caller's order).
 // An imaging major cycle grids residuals of the SAME uvw again and again; with this the binning and the bucket sort are paid
 // once per data set, not once per cycle (sequential pass over the records, one random 16-byte read per visibility).
+// SORTED: vis is already in plan order (vis[r] belongs to record r: the caller permuted its data once with plan_order), so the
+// pass is purely sequential; otherwise one random 16-byte read per record.
+template <bool SORTED>
 __global__ void __launch_bounds__(256) plan_set_vis_kernel(const uint32_t *__restrict__ counters, VisRec *rec, const double2 *__restrict__ vis) {
     const i64 kept = (i64)counters[2];
     const i64 stride = (i64)gridDim.x * blockDim.x;
     for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < kept; r += stride) {
-        const uint32_t idx = reinterpret_cast<const uint4 *>(rec + r)[1].z;
+        const i64 idx = SORTED ? r : (i64) reinterpret_cast<const uint4 *>(rec + r)[1].z;
         *reinterpret_cast<double2 *>(rec + r) = vis[idx];
     }
 }
 
-extern "C" int skagrid_dev_plan_set_vis(skagrid_ctx *ctx, skagrid_plan *plan, const double *d_vis, void *stream) {
+// index[r] = position in the caller's arrays of the visibility behind record r (r < kept, plan_stats[0])
+__global__ void __launch_bounds__(256) plan_order_kernel(const uint32_t *__restrict__ counters, const VisRec *__restrict__ rec, uint32_t *__restrict__ index) {
+    const i64 kept = (i64)counters[2];
+    const i64 stride = (i64)gridDim.x * blockDim.x;
+    for (i64 r = (i64)blockIdx.x * blockDim.x + threadIdx.x; r < kept; r += stride) index[r] = reinterpret_cast<const uint4 *>(rec + r)[1].z;
+}
+
+extern "C" int skagrid_dev_plan_set_vis(skagrid_ctx *ctx, skagrid_plan *plan, const double *d_vis, int in_plan_order, void *stream) {
     if (!ctx || !plan) return SKAGRID_EINVAL;
     SK_CUDA(ctx, cudaSetDevice(ctx->device));
     if (plan->count == 0) return SKAGRID_OK;
     if (!d_vis) return sk_fail(ctx, SKAGRID_EINVAL, "plan_set_vis: NULL visibilities");
-    plan_set_vis_kernel<<<ctx->sm_count * 8, 256, 0, sk_stream(ctx, stream)>>>(plan->d_counters, plan->d_rec, reinterpret_cast<const double2 *>(d_vis));
+    if (in_plan_order)
+        plan_set_vis_kernel<true><<<ctx->sm_count * 8, 256, 0, sk_stream(ctx, stream)>>>(plan->d_counters, plan->d_rec, reinterpret_cast<const double2 *>(d_vis));
+    else
+        plan_set_vis_kernel<false><<<ctx->sm_count * 8, 256, 0, sk_stream(ctx, stream)>>>(plan->d_counters, plan->d_rec, reinterpret_cast<const double2 *>(d_vis));
     SK_LAUNCH_CHECK(ctx);
     plan->has_vis = 1;
+    return SKAGRID_OK;
+}
+
+extern "C" int skagrid_dev_plan_order(skagrid_ctx *ctx, skagrid_plan *plan, uint32_t *d_index, void *stream) {
+    if (!ctx || !plan) return SKAGRID_EINVAL;
+    SK_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (plan->count == 0) return SKAGRID_OK;
+    if (!d_index) return sk_fail(ctx, SKAGRID_EINVAL, "plan_order: NULL index array");
+    plan_order_kernel<<<ctx->sm_count * 8, 256, 0, sk_stream(ctx, stream)>>>(plan->d_counters, plan->d_rec, d_index);
+    SK_LAUNCH_CHECK(ctx);
     return SKAGRID_OK;
 }
 

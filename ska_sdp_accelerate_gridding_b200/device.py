@@ -237,13 +237,24 @@ class Plan:
     def check(self):
         check_errors(self.ctx)
 
-    def set_vis(self, vis):
-        """New visibility values (caller's order, same count) at the coordinates the plan was built from: no re-binning, no
-        re-sorting -- what a major cycle over the same uvw needs (skagrid_dev_plan_set_vis)."""
+    def set_vis(self, vis, in_plan_order=False):
+        """New visibility values at the coordinates the plan was built from: no re-binning, no re-sorting -- what a major cycle
+        over the same uvw needs (skagrid_dev_plan_set_vis).  vis: caller's order, one value per visibility of the batch; or,
+        in_plan_order=True, one value per KEPT record in the plan's own order (vis[order()]): a sequential refresh."""
         _chk(vis, torch.complex128, "vis")
-        if vis.numel() != self.count:
+        if not in_plan_order and vis.numel() != self.count:
             raise ValueError("vis must have one value per visibility of the plan's batch")
-        self.ctx.check(self.ctx.lib.skagrid_dev_plan_set_vis(self.ctx.h, self.h, _p(vis), _stream()))
+        if in_plan_order and vis.numel() < self.stats()["kept"]:
+            raise ValueError("vis must have one value per kept record")
+        self.ctx.check(self.ctx.lib.skagrid_dev_plan_set_vis(self.ctx.h, self.h, _p(vis), int(bool(in_plan_order)), _stream()))
+
+    def order(self):
+        """index[r] = position in the caller's arrays of the visibility behind record r (int32 CUDA tensor, one entry per kept
+        record): permute the data once with it and refresh / read back in plan order from then on."""
+        kept = self.stats()["kept"]
+        idx = torch.empty(kept, dtype=torch.int32, device=torch.device("cuda", self.ctx.device))
+        self.ctx.check(self.ctx.lib.skagrid_dev_plan_order(self.ctx.h, self.h, _p(idx), _stream()))
+        return idx
 
     def stats(self):
         out = (C.c_int64 * 5)()

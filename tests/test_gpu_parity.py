@@ -554,6 +554,14 @@ def test_plan_set_vis_reuses_the_sort(orc):
         assert rel_err(g.cpu().numpy(), og[rows[0]:rows[1]]) < TOL
         with pytest.raises(ValueError):
             plan.set_vis(_t(vb[:-1]))
+        # the plan's own order: permute once, refresh sequentially
+        order = plan.order()
+        assert order.numel() == plan.stats()["kept"] and len(set(order.tolist())) == order.numel()
+        plan.set_vis(_t(va)[order.long()], in_plan_order=True)
+        g.zero_()
+        plan.grid(_t(gcf), g)
+        oga = orc.convgrid(gcf, np.zeros((n, n), complex), u, v, va, wbin=wb)
+        assert rel_err(g.cpu().numpy(), oga[rows[0]:rows[1]]) < TOL
         plan.close()
 
 
