@@ -34,7 +34,8 @@ def main():
     out = ["# Round 2 — config 4 over 1 / 2 / 4 / 8 B200s (bench.py, final runs of the round)\n",
            "Stage columns: plan / gridder / reduce / image / degridder in ms (max over ranks).  Exchange at N > 1: peer memory over NVLink "
            "(csrc/ipc.cu): device barrier, peer-sum reduce-scatter kernel, all-gather by copy engines (N = 2) or by one SM kernel reading all peers at once "
-           "(N >= 4), transpose of the slab image pulled from peer memory.\n",
+           "(N >= 4), transpose of the slab image pulled from peer memory.  Every line is its own gpurun box: the same N = 1 step measured 51.8, 52.1 and "
+           "52.6 ms on three boxes of the pool (power cap), so efficiencies and speed-ups carry about +-1.5 %.\n",
            "| N | weak: ms/step | vis/s | efficiency | stages | strong (1e8 total): ms/step | speed-up | stages | e2e vis/s | parity: checksum / grid / degrid |",
            "|---|---|---|---|---|---|---|---|---|---|"]
     for n, j in finals.items():
