@@ -858,13 +858,14 @@ def main():
             (c4.act if N_GRID % 2 == 0 else c4.grid).zero_()
             c4.plan.grid(table, c4.act, variant=args.variant)
             dv.grid_to_image(c4.grid, want_image=False)
-            c4.plan.degrid(table, c4.act, c4.vis_out)
+            c4.plan.degrid(table, c4.act, c4.vis_out, plan_order=True)   # results in plan order too: sequential full-sector writes
 
         ms_s, _, _ = env.time_steps(sstep, 3, max(3, min(args.steps, 10)))
         del vis_sorted
         out["prepared"] = {"value": V / (ms_p * 1e-3), "unit": "vis/s", "ms_per_step": ms_p, "set_vis_ms": e[0].elapsed_time(e[1]),
                            "in_plan_order": {"value": V / (ms_s * 1e-3), "ms_per_step": ms_s,
-                                             "note": "the caller keeps its visibilities in the plan's order (Plan.order()): the refresh is sequential"},
+                                             "note": "the caller keeps its visibilities in the plan's order (Plan.order()): the refresh is sequential and the "
+                                                     "degridder writes its results in plan order (full sectors instead of half-sector scatters)"},
                            "step": "Plan.set_vis (new visibility values into the sorted records) -> gridder -> grid->image -> degridder",
                            "note": "NOT the headline: the headline step re-bins and re-sorts every time (SURVEY 8d counts the sort as part of gridding); this is "
                                    "what a major cycle over the same uvw costs once the plan exists"}

@@ -294,6 +294,10 @@ int skagrid_dev_grid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, 
 /* vis_out[k] = sum conj(table[slice_k][i,j]) * grid[...] for the plan's visibilities (others = 0). */
 int skagrid_dev_degrid(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, const double *grid,
                        double *vis_out, void *stream);
+/* The same with the results in the plan's own order: vis_out[r] belongs to record r (r < plan_stats[0], see plan_order) --
+ * sequential full-sector writes instead of one 16-byte store at a random index per visibility. */
+int skagrid_dev_degrid_plan_order(skagrid_ctx *ctx, skagrid_plan *plan, const double *table, const double *grid,
+                                  double *vis_out, void *stream);
 /* Grid -> image stage on an n x n device grid: hermitian + centred inverse FFT; writes real(image) into image (n*n
  * doubles, may be NULL) and the maximum into max_out (1 double).  Even n: only the real part is wanted, so the hermitian
  * half of the spectrum goes through a complex-to-REAL transform (half the passes of the complex one) and `grid` is not

@@ -87,6 +87,7 @@ _SIGS = {
     "skagrid_dev_plan_stats": [vp, vp, vp, C.POINTER(i64 * 5)],
     "skagrid_dev_grid": [vp, vp, vp, vp, ip, vp],
     "skagrid_dev_degrid": [vp, vp, vp, vp, vp, vp],
+    "skagrid_dev_degrid_plan_order": [vp, vp, vp, vp, vp, vp],
     "skagrid_dev_grid_to_image": [vp, i64, vp, vp, vp, vp],
     "skagrid_dev_synth_vis": [vp, C.c_uint64, i64, i64, i64, i64, i64, ip, vp, vp, vp, vp, vp],
     "skagrid_dev_w_kernels": [vp, dbl, i64, vp, i64, i64, i64, ip, vp, vp],

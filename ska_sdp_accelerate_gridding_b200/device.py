@@ -268,12 +268,15 @@ class Plan:
             raise ValueError("grid tensor does not match the plan's owned rows")
         self.ctx.check(self.ctx.lib.skagrid_dev_grid(self.ctx.h, self.h, _p(table), _p(grid), int(variant), _stream()))
 
-    def degrid(self, table, grid, out=None):
+    def degrid(self, table, grid, out=None, plan_order=False):
+        """vis_out[k] for the plan's visibilities in the caller's order (others 0) -- or, plan_order=True, vis_out[r] for record r in
+        the plan's own order (`order()`): sequential full-sector writes."""
         _chk(table, torch.complex128, "table"); _chk(grid, torch.complex128, "grid")
         if out is None:
             out = torch.empty(self.count, dtype=torch.complex128, device=grid.device)
         _chk(out, torch.complex128, "out")
-        self.ctx.check(self.ctx.lib.skagrid_dev_degrid(self.ctx.h, self.h, _p(table), _p(grid), _p(out), _stream()))
+        fn = self.ctx.lib.skagrid_dev_degrid_plan_order if plan_order else self.ctx.lib.skagrid_dev_degrid
+        self.ctx.check(fn(self.ctx.h, self.h, _p(table), _p(grid), _p(out), _stream()))
         return out
 
     def close(self):

@@ -562,6 +562,16 @@ def test_plan_set_vis_reuses_the_sort(orc):
         plan.grid(_t(gcf), g)
         oga = orc.convgrid(gcf, np.zeros((n, n), complex), u, v, va, wbin=wb)
         assert rel_err(g.cpu().numpy(), oga[rows[0]:rows[1]]) < TOL
+        # degridding in plan order: result r belongs to record r
+        model = _rand_c(rng, (n, n))
+        clipped = np.zeros_like(model)
+        clipped[rows[0]:rows[1]] = model[rows[0]:rows[1]]
+        od = orc.convdegrid(gcf, clipped, u, v, wbin=wb)
+        d_caller = plan.degrid(_t(gcf), _t(model[rows[0]:rows[1]].copy())).cpu().numpy()
+        assert rel_err(d_caller, od) < TOL
+        d_plan = plan.degrid(_t(gcf), _t(model[rows[0]:rows[1]].copy()), plan_order=True).cpu().numpy()
+        oi = order.cpu().numpy()
+        assert rel_err(d_plan[:oi.size], od[oi]) < TOL
         plan.close()
 
 
