@@ -638,17 +638,15 @@ class TileShardedGridder:
         self.pg.barrier()                                         # all send buffers are packed
         rec = torch.empty((recv, W), dtype=torch.float64, device=v.device)
         copies, off = [], 0
-        offs = []
         for s in range(P):
             seg = sum(cnt[s][:me])                                # start of my segment in rank s's send buffer
             n = cnt[s][me]
-            offs.append(off)
             if n:
                 copies.append((rec.data_ptr() + off * W * 8, self.psend.ptrs[s] + seg * W * 8, n * W * 8))
             off += n
         self.pg.bulk(copies)
         _mark("route: pulled")
-        return rec, {"sidx": sidx, "cnt": cnt, "offs_in_owner": None}
+        return rec, {"sidx": sidx, "cnt": cnt}
 
     def return_peer(self, count, route):
         """The owners' partial sums (in the peer-visible `ppart`, one per received record) travel back: every source pulls the

@@ -144,11 +144,9 @@ class PeerGroup:
         arr = (C.c_void_p * max(len(others), 1))(*[C.c_void_p(p) for p in others])
         self.ctx.check(self.ctx.lib.skagrid_dev_peer_sum(self.ctx.h, len(others), arr, C.c_void_p(buf.local + offset_bytes), int(ncomplex), int(bool(broadcast)), _stream()))
 
-    # SKAGRID_PEER_PULL = ce | sm: copy engines or SM kernels for the bulk pulls of the uv-tile-sharded mode (A/B measurements)
-    SM_PULL = os.environ.get("SKAGRID_PEER_PULL", "") == "sm"
-
     def bulk(self, copies):
-        """Bulk pull nothing overlaps with: SM gather kernel or copy engines (joined), see SM_PULL."""
+        """Bulk pull nothing overlaps with: the SM gather kernel, or copy engines (joined).  SKAGRID_PEER_PULL = ce | sm overrides
+        the default for A/B measurements."""
         mode = os.environ.get("SKAGRID_PEER_PULL", "")
         if mode == "sm" or (mode != "ce" and self.world >= 4):   # measured: copy engines win between two GPUs, the SM kernel from four on
             self.gather(copies)
