@@ -251,6 +251,8 @@ class Plan:
     def order(self):
         """index[r] = position in the caller's arrays of the visibility behind record r (int32 CUDA tensor, one entry per kept
         record): permute the data once with it and refresh / read back in plan order from then on."""
+        if self.count >= 2 ** 31:
+            raise ValueError("order(): batches of 2^31 visibilities or more do not fit the int32 index tensor")
         kept = self.stats()["kept"]
         idx = torch.empty(kept, dtype=torch.int32, device=torch.device("cuda", self.ctx.device))
         self.ctx.check(self.ctx.lib.skagrid_dev_plan_order(self.ctx.h, self.h, _p(idx), _stream()))
