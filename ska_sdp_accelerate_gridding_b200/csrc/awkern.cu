@@ -165,6 +165,167 @@ static int launch_tiled(skagrid_ctx *ctx, i64 count, const uint32_t *count_dev, 
     return SKAGRID_OK;
 }
 
+// Round 2: row-pair kernel.  Two changes against conv_tiled_kernel, same sums in the same order (bit-identical
+// results for finite operands):
+//   * a warp owns ONE column group, so tx0 is a compile-time constant of the code path it runs and the taps whose
+//     operand column tx+C-kx lies outside the kernel are not issued at all: 169 complex MACs per (ky, output row)
+//     instead of 240 for N = 15 (group by group 38 / 54 / 50 / 27 of 60) -- the x half of the 1.77x zero padding;
+//   * a thread owns TWO adjacent output rows.  Output row ty at step ky reads operand row ty+C-ky, so the window the
+//     lower output row loads at step ky is the one the upper row needs at step ky+1: one window load per step feeds
+//     2 x TX outputs, and the aT loads are shared by 8 outputs instead of 4 (0.2 shared-memory loads per complex MAC).
+// Lanes: (N+1)/2 row pairs of one output kernel, 32 / ((N+1)/2) output kernels per warp (N = 15: a quarter-warp per
+// kernel, so the aT loads are quarter-uniform); operand rows are stored even rows first, then odd rows, with a pitch
+// of 1 mod 8 taps: the rows a quarter-warp loads in one step have the same parity, hence consecutive slots and 8
+// distinct 16-byte bank groups.  Rows outside the kernel map to one all-zero row (the y half of the padding stays).
+template <int N>
+struct ConvPair {
+    static_assert(N % 2 == 1, "odd supports only");
+    static constexpr int TX = 4;
+    static constexpr int C = N / 2;
+    static constexpr int GX = (N + TX - 1) / TX;            // column groups = warps per block
+    static constexpr int RP = (N + 1) / 2;                  // row pairs per output kernel
+    static constexpr int HR = (N + 1) / 2;                  // even operand rows (slots 0..HR-1), odd rows follow
+    static constexpr int KPW = 32 / RP;                     // output kernels per warp = per block
+    static constexpr int PW = (N + 6) / 8 * 8 + 1;          // operand row pitch: >= N, 1 mod 8
+    static constexpr int THREADS = GX * 32;
+    static constexpr int SM_PER = N * N + (N + 1) * PW;     // double2 per output kernel: aT, bT rows + the zero row
+};
+
+template <int N, int G>
+struct ConvPairGroup {
+    using T = ConvPair<N>;
+    static constexpr int TX0 = G * T::TX;
+    static constexpr int TXN = (TX0 + T::TX <= N) ? T::TX : N - TX0;                        // outputs of this group that exist
+    static constexpr int QLO = (TX0 + T::C - (N - 1) > 0) ? TX0 + T::C - (N - 1) : 0;       // operand columns the group touches
+    static constexpr int QHI = (TX0 + TXN - 1 + T::C < N - 1) ? TX0 + TXN - 1 + T::C : N - 1;
+    static constexpr int WN = QHI - QLO + 1;
+};
+
+// acc[r][t] += sum_kx aT[ky][kx] * row_r[tx0 + t + C - kx]  for r = 0 (window lo) and 1 (window hi)
+template <int N, int G>
+__device__ __forceinline__ void conv_pair_mac(const double2 *__restrict__ arow, const double2 (&lo)[ConvPairGroup<N, G>::WN],
+                                              const double2 (&hi)[ConvPairGroup<N, G>::WN], double (&accr)[2][4], double (&acci)[2][4]) {
+    using GRP = ConvPairGroup<N, G>;
+    constexpr int C = N / 2;
+#pragma unroll
+    for (int kx = 0; kx < N; ++kx) {
+        if (GRP::TX0 + GRP::TXN - 1 + C - kx < 0 || GRP::TX0 + C - kx >= N) continue;      // no output of the group uses this tap
+        const double2 p = arow[kx];
+#pragma unroll
+        for (int t = 0; t < GRP::TXN; ++t) {
+            const int qx = GRP::TX0 + t + C - kx;
+            if (qx < 0 || qx >= N) continue;
+            const double2 q0 = lo[qx - GRP::QLO], q1 = hi[qx - GRP::QLO];
+            accr[0][t] = fma(p.x, q0.x, accr[0][t]); accr[0][t] = fma(-p.y, q0.y, accr[0][t]);
+            acci[0][t] = fma(p.x, q0.y, acci[0][t]); acci[0][t] = fma(p.y, q0.x, acci[0][t]);
+            accr[1][t] = fma(p.x, q1.x, accr[1][t]); accr[1][t] = fma(-p.y, q1.y, accr[1][t]);
+            acci[1][t] = fma(p.x, q1.y, acci[1][t]); acci[1][t] = fma(p.y, q1.x, acci[1][t]);
+        }
+    }
+}
+
+template <int N, int G>
+__device__ __forceinline__ void conv_pair_group(const double2 *__restrict__ saT, const double2 *__restrict__ sbT, int rp, double2 *__restrict__ po,
+                                                int conj_out) {
+    using T = ConvPair<N>;
+    using GRP = ConvPairGroup<N, G>;
+    constexpr int C = T::C, WN = GRP::WN;
+    auto row = [&](int q) { return sbT + ((q >= 0 && q < N) ? ((q >> 1) + (q & 1) * T::HR) : N) * T::PW + GRP::QLO; };
+    double accr[2][4], acci[2][4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) accr[0][t] = accr[1][t] = acci[0][t] = acci[1][t] = 0.0;
+    double2 lo[WN], hi[WN];
+    const int q00 = 2 * rp + C;  // operand row of the lower output row at ky = 0
+    {
+        const double2 *r = row(q00 + 1);
+#pragma unroll
+        for (int i = 0; i < WN; ++i) hi[i] = r[i];
+    }
+    // One copy of the multiply-accumulate code per column group: the step's window becomes the upper row's window of
+    // the next step by register moves (free next to 8 DFMA per tap on an FP64-bound loop).  Unrolling two steps to
+    // rotate the windows by renaming instead doubled the loop body to 46 KB over the four groups -- beyond the 32 KB
+    // instruction cache of the SM, and the kernel ran slower than round 1's (warps stalled on instruction fetch).
+#pragma unroll 1
+    for (int ky = 0; ky < N; ++ky) {
+        const double2 *r = row(q00 - ky);
+#pragma unroll
+        for (int i = 0; i < WN; ++i) lo[i] = r[i];
+        conv_pair_mac<N, G>(saT + ky * N, lo, hi, accr, acci);
+#pragma unroll
+        for (int i = 0; i < WN; ++i) hi[i] = lo[i];
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (2 * rp + r >= N) break;
+#pragma unroll
+        for (int t = 0; t < GRP::TXN; ++t) po[(2 * rp + r) * N + GRP::TX0 + t] = make_double2(accr[r][t], conj_out ? -acci[r][t] : acci[r][t]);
+    }
+}
+
+template <int N, int G>
+__device__ __forceinline__ void conv_pair_dispatch(int g, const double2 *__restrict__ saT, const double2 *__restrict__ sbT, int rp,
+                                                   double2 *__restrict__ po, int conj_out) {
+    if (g == G) conv_pair_group<N, G>(saT, sbT, rp, po, conj_out);
+    else if constexpr (G + 1 < ConvPair<N>::GX) conv_pair_dispatch<N, G + 1>(g, saT, sbT, rp, po, conj_out);
+}
+
+template <int N>
+__global__ void __launch_bounds__(ConvPair<N>::THREADS) conv_pair_kernel(i64 count, const uint32_t *__restrict__ count_dev,
+                                                                         const double2 *__restrict__ a, const i64 *__restrict__ ai,
+                                                                         const double2 *__restrict__ b, const i64 *__restrict__ bi,
+                                                                         double2 *__restrict__ out, int conj_out) {
+    using T = ConvPair<N>;
+    constexpr int N2 = N * N;
+    extern __shared__ double2 sm[];
+    __shared__ i64 s_ia[T::KPW], s_ib[T::KPW];
+    const i64 k0 = (i64)blockIdx.x * T::KPW;
+    const i64 limit = count_dev ? min(count, (i64)*count_dev) : count;
+    if (threadIdx.x < T::KPW) {
+        const i64 k = k0 + threadIdx.x;
+        const i64 ia = k < limit ? (ai ? ai[k] : k) : -1;
+        s_ia[threadIdx.x] = ia;
+        s_ib[threadIdx.x] = ia >= 0 ? (bi ? bi[k] : k) : -1;
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < T::KPW * N2; idx += T::THREADS) {
+        const int s = idx / N2, t = idx % N2;
+        const i64 ia = s_ia[s];
+        if (ia < 0) continue;
+        double2 *saT = sm + s * T::SM_PER, *sbT = saT + N2;
+        const int r = t % N, c = t / N;                                     // element [c, r] of the operands
+        saT[r * N + c] = a[ia * N2 + t];                                    // aT[ky][kx] = a[kx,ky]
+        sbT[((r >> 1) + (r & 1) * T::HR) * T::PW + c] = b[s_ib[s] * N2 + t];  // bT[qy][qx] = b[qx,qy], even rows first
+    }
+    for (int idx = threadIdx.x; idx < T::KPW * T::PW; idx += T::THREADS)
+        sm[(idx / T::PW) * T::SM_PER + N2 + N * T::PW + idx % T::PW] = make_double2(0.0, 0.0);  // the zero row
+    __syncthreads();
+    const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int s = lane / T::RP, rp = lane % T::RP;
+    if (s >= T::KPW || k0 + s >= limit) return;
+    double2 *po = out + (k0 + s) * N2;
+    if (s_ia[s] < 0) {  // a visibility whose indices were out of range: zero kernel
+        constexpr int TX = T::TX;
+        for (int r = 0; r < 2; ++r)
+            for (int t = 0; t < TX; ++t)
+                if (2 * rp + r < N && g * TX + t < N) po[(2 * rp + r) * N + g * TX + t] = make_double2(0.0, 0.0);
+        return;
+    }
+    const double2 *saT = sm + s * T::SM_PER;
+    conv_pair_dispatch<N, 0>(g, saT, saT + N2, rp, po, conj_out);
+}
+
+template <int N>
+static int launch_pair(skagrid_ctx *ctx, i64 count, const uint32_t *count_dev, const double2 *a, const i64 *ai, const double2 *b, const i64 *bi,
+                       double2 *out, int conj_out, cudaStream_t st) {
+    using T = ConvPair<N>;
+    const size_t smem = (size_t)T::KPW * T::SM_PER * sizeof(double2);
+    static_assert((size_t)T::KPW * T::SM_PER * sizeof(double2) <= 47 * 1024, "conv_pair_kernel: dynamic shared memory above the default limit");
+    const i64 blocks = (count + T::KPW - 1) / T::KPW;
+    conv_pair_kernel<N><<<(unsigned)blocks, T::THREADS, smem, st>>>(count, count_dev, a, ai, b, bi, out, conj_out);
+    SK_LAUNCH_CHECK(ctx);
+    return SKAGRID_OK;
+}
+
 // out[k] = convolve2d(a[ai[k]], b[bi[k]]) for k < min(count, *count_dev)
 static int conv_batch(skagrid_ctx *ctx, i64 n, i64 count, const uint32_t *count_dev, const double *a, const i64 *ai, const double *b, const i64 *bi,
                       double *out, int conj_out, cudaStream_t st) {
@@ -173,6 +334,19 @@ static int conv_batch(skagrid_ctx *ctx, i64 n, i64 count, const uint32_t *count_
     const double2 *pa = (const double2 *)a, *pb = (const double2 *)b;
     double2 *po = (double2 *)out;
     static const bool generic_only = getenv("SKAGRID_CONV_GENERIC") && atoi(getenv("SKAGRID_CONV_GENERIC")) != 0;  // A/B measurements
+    static const bool round1_tiled = getenv("SKAGRID_CONV_TILED") && atoi(getenv("SKAGRID_CONV_TILED")) != 0;     // the round-1 kernel
+    if (!generic_only && !round1_tiled) {
+        switch (n) {
+            case 5: return launch_pair<5>(ctx, count, count_dev, pa, ai, pb, bi, po, conj_out, st);
+            case 7: return launch_pair<7>(ctx, count, count_dev, pa, ai, pb, bi, po, conj_out, st);
+            case 9: return launch_pair<9>(ctx, count, count_dev, pa, ai, pb, bi, po, conj_out, st);
+            case 11: return launch_pair<11>(ctx, count, count_dev, pa, ai, pb, bi, po, conj_out, st);
+            case 13: return launch_pair<13>(ctx, count, count_dev, pa, ai, pb, bi, po, conj_out, st);
+            case 15: return launch_pair<15>(ctx, count, count_dev, pa, ai, pb, bi, po, conj_out, st);
+            case 17: return launch_pair<17>(ctx, count, count_dev, pa, ai, pb, bi, po, conj_out, st);
+            default: break;
+        }
+    }
     if (!generic_only) {
         switch (n) {
             case 5: return launch_tiled<5>(ctx, count, count_dev, pa, ai, pb, bi, po, conj_out, st);

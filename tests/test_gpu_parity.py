@@ -230,7 +230,9 @@ def test_convolve2d_and_aw_kernel(G, orc):
         a, b = _rand_c(rng, (n, n)), _rand_c(rng, (n, n))
         assert rel_err(G.convolve2d(a, b), orc.convolve2d(a, b)) < 1e-12
     # aw_kernel_fn2 in batches: distinct antenna pairs are convolved once (more visibilities than pairs, and fewer)
-    for nw, q, s, nant, cnt in ((3, 4, 15, 5, 200), (2, 2, 15, 40, 60), (2, 2, 9, 3, 50), (1, 1, 19, 4, 30)):
+    # (batch sizes that are not multiples of the output kernels per block of the row-pair kernel, every tiled support)
+    for nw, q, s, nant, cnt in ((3, 4, 15, 5, 203), (2, 2, 15, 40, 61), (2, 2, 9, 3, 50), (1, 1, 19, 4, 30), (2, 2, 5, 3, 27), (2, 2, 7, 3, 19),
+                                (1, 2, 11, 3, 23), (2, 2, 13, 7, 33), (1, 2, 17, 3, 10)):
         wk, ak = _rand_c(rng, (nw, q, q, s, s)), _rand_c(rng, (nant, s, s))
         wb, yf, xf = rng.integers(0, nw, cnt), rng.integers(0, q, cnt), rng.integers(0, q, cnt)
         a1, a2 = rng.integers(0, nant, cnt), rng.integers(0, nant, cnt)
