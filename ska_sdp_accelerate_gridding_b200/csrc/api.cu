@@ -24,7 +24,7 @@ static i64 vis_chunk(bool kernel_bound) {
     return (i64)1 << (kernel_bound ? 24 : 22);
 }
 static const i64 RES_MAX = (i64)1 << 28;   // at most this many coordinates are kept resident between calls (24 B each)
-static const i64 AW_CHUNK = (i64)1 << 17;   // most visibilities per chunk of the AW path (aw_core_dev)
+static const i64 AW_CHUNK = (i64)1 << 20;   // most visibilities per chunk of the AW path (aw_core_dev)
 
 static inline int up(skagrid_ctx *ctx, const char *name, const void *host, size_t bytes, void **dev) { return sk_api_up(ctx, name, host, bytes, dev); }
 static inline int check_flags(skagrid_ctx *ctx, const char *what) { return sk_api_check_flags(ctx, what); }
@@ -423,8 +423,10 @@ static int aw_core_dev(skagrid_ctx *ctx, i64 nw, i64 qpx, i64 s, const double *d
                        double *d_grid, i64 count, const double *du, const double *dv, const i64 *dwb, const i64 *da1, const i64 *da2,
                        double *dvis, int degrid) {
     if (count <= 0) return SKAGRID_OK;
-    // one S x S kernel per visibility: at most ~0.5 GB of them per chunk (131072 visibilities at S = 15, 8455 at S = 63)
-    i64 chunk = std::min<i64>(count, std::max<i64>(4096, std::min<i64>(AW_CHUNK, ((i64)512 << 20) / (s * s * 16))));
+    // one S x S kernel per visibility: at most 4 GB of them per chunk (2^20 visibilities at S = 15, 67 000 at S = 63).  Round 1
+    // used 0.5 GB; the gridder's cost per chunk is mostly per touched tile (zero + flush of the subgrid), not per visibility,
+    // at AW densities -- 1.0 ms per 131072 visibilities (profiles/r02_launches_aw_1e6_summary.txt) -- so fewer, larger chunks.
+    i64 chunk = std::min<i64>(count, std::max<i64>(4096, std::min<i64>(AW_CHUNK, ((i64)4096 << 20) / (s * s * 16))));
     if (const char *e = getenv("SKAGRID_AW_CHUNK")) {  // tests: force several chunks on a small input
         const i64 forced = atoll(e);
         if (forced > 0) chunk = std::min<i64>(count, forced);
