@@ -24,4 +24,6 @@ def main(path):
 
 
 if __name__ == "__main__":
+    import signal
+    signal.signal(signal.SIGPIPE, signal.SIG_DFL)  # `... | head` is the usual way to read it
     main(sys.argv[1])
