@@ -84,6 +84,46 @@ def test_convolve2d_direct_equals_fft_route(n):
         assert np.abs(d - sc(a, b, mode="same").T).max() < 1e-11 * np.abs(d).max()
 
 
+@pytest.mark.parametrize("n", [5, 7, 15, 17])
+def test_row_pair_schedule_of_the_formation_kernel(n):
+    """The schedule of conv_pair_kernel (csrc/awkern.cu) restated in numpy: column groups of 4 outputs that drop the taps
+    whose operand column lies outside the kernel, two output rows per worker sharing one operand window (the lower row's
+    window of step ky is the upper row's of step ky+1), operand rows outside the kernel read as zero.  Must equal
+    convolve2d: this pins the index arithmetic the CUDA kernel was written from."""
+    rng = np.random.default_rng(100 + n)
+    a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    b = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+    c, tx_per = n // 2, 4
+    aT, bT = a.T.copy(), b.T.copy()       # aT[ky][kx] = a[kx,ky], bT[qy][qx] = b[qx,qy]
+    zero = np.zeros(n, complex)
+    row = lambda q: bT[q] if 0 <= q < n else zero
+    out = np.zeros((n, n), complex)
+    macs = 0
+    for g in range((n + tx_per - 1) // tx_per):
+        tx0 = g * tx_per
+        txn = min(tx_per, n - tx0)
+        for rp in range((n + 1) // 2):
+            acc = np.zeros((2, txn), complex)
+            q00 = 2 * rp + c
+            hi = row(q00 + 1)
+            for ky in range(n):
+                lo = row(q00 - ky)
+                for kx in range(n):
+                    for t in range(txn):
+                        qx = tx0 + t + c - kx
+                        if 0 <= qx < n:  # resolved at compile time in the kernel
+                            acc[0, t] += aT[ky, kx] * lo[qx]
+                            acc[1, t] += aT[ky, kx] * hi[qx]
+                            macs += 1
+                hi = lo
+            for r in range(2):
+                if 2 * rp + r < n:
+                    out[2 * rp + r, tx0:tx0 + txn] = acc[r]
+    ref = orc.convolve2d(a, b)
+    assert np.abs(out - ref).max() < 1e-12 * np.abs(ref).max()
+    if n == 15:  # 169 of 240 taps per (output row, step): the x half of the zero padding is skipped
+        assert macs == 169 * 15 * 8
+
 def test_frac_coord_properties():
     rng = np.random.default_rng(1)
     p = rng.uniform(-0.5, 0.5, 20000)
